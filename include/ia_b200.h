@@ -1,0 +1,119 @@
+/*
+ * ia_b200.h -- C ABI of libia_b200.so, the B200 (sm_100a) implementation of InstantAvatar's per-ray hot
+ * path.  Plain pointers and sizes only; every pointer is a DEVICE pointer unless marked [host]; all
+ * buffers are owned by the caller (the library never allocates, frees or retains pointers, and never
+ * synchronises the device).  Every entry point enqueues work on `stream` and returns 0, or a negative
+ * IA_E* code with a message retrievable through ia_last_error() (thread-local).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference repo
+ * tijiang13/InstantAvatar @ 3cdfd49).
+ */
+#ifndef IA_B200_H
+#define IA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IA_ABI_VERSION 1
+#define IA_NUM_INIT 13      /* deformers/fast_snarf/deformer_torch.py:28 */
+#define IA_NUM_LEVELS 16    /* models/networks/ngp.py:30 */
+#define IA_MLP_HALFS 11008  /* padded fp16 weight block, see ia_params_to_half */
+#define IA_ENC_MLP_PARAMS 3072
+#define IA_COL_MLP_PARAMS 6144
+#define IA_MAX_SAMPLES 256  /* confs/renderer/raymarcher_acc.yaml:2 */
+
+#define IA_OK 0
+#define IA_EINVAL (-1)
+#define IA_ECUDA (-2)
+
+typedef void* ia_stream_t; /* cudaStream_t */
+
+/* Per-frame read-only state of the fused kernels. */
+typedef struct IaScene {
+    const float* field;      /* [D][H][W][12] fp32 blended 3x4 LBS transform per voxel (ia_precompute) */
+    int32_t D, H, W;
+    const float* offset_k;   /* [3] ForwardDeformer.offset_kernel (deformer_torch.py:154) */
+    const float* scale_k;    /* [3] ForwardDeformer.scale_kernel  (deformer_torch.py:155-158) */
+    const float* tfs;        /* [24][4][4] bone transforms (snarf_deformer.py:86) */
+    const uint32_t* occ_bits;/* [G*G*G/32] occupancy bitfield, bit index (nx*G+ny)*G+nz (ia_pack_occupancy) */
+    int32_t G;
+    const float* occ_aabb;   /* [6] min xyz, max xyz of the occupancy grid (DensityGrid.min_corner/max_corner) */
+    const void* table_h;     /* half2[total_entries] hash-grid features (ia_params_to_half) */
+    const void* mlp_h;       /* half[IA_MLP_HALFS] padded MLP weights (ia_params_to_half) */
+    const float* net_center; /* [3] NeRFNGPNet.center (ngp.py:64-71) */
+    const float* net_scale;  /* [3] NeRFNGPNet.scale */
+} IaScene;
+
+/* Work counters accumulated by the kernels (device memory, caller zeroes). */
+typedef struct IaStats {
+    unsigned long long samples;   /* occupied samples evaluated (M) */
+    unsigned long long gathers;   /* trilinear field samples taken by Broyden (M*13*kbar) */
+    unsigned long long net_evals; /* hash-grid + MLP evaluations (P) */
+    unsigned long long rays_hit;  /* rays with at least one occupied sample */
+} IaStats;
+
+int ia_abi_version(void);
+const char* ia_last_error(void);
+/* number of SMs of the current device (grid sizing is a multiple of this) [host result] */
+int ia_sm_count(void);
+
+/* tiny-cuda-nn HashGrid level table (models/networks/ngp.py:27-37 config). [host] outputs. */
+int ia_hashgrid_layout(uint32_t res[IA_NUM_LEVELS], float scale[IA_NUM_LEVELS], uint32_t size[IA_NUM_LEVELS],
+                       uint32_t offset[IA_NUM_LEVELS], uint32_t* total_entries);
+
+/* Replaces precompute_cuda.precompute (deformers/fast_snarf/cuda/precompute/precompute.cpp:7-13,
+ * precompute.cu:24-103).  voxel_w [24][D][H][W] skinning weights, tfs [24][4][4].
+ * field_out [D][H][W][12]; voxel_d_out [3][D][H][W] (nullable; reference layout, deformer.voxel_d);
+ * aabb_out [6] = min/max of voxel_d (nullable; SNARFDeformer.get_bbox_deformed, snarf_deformer.py:105-107).
+ * aabb_out must be pre-initialised by the caller to (+inf x3, -inf x3). */
+int ia_precompute(const float* voxel_w, const float* tfs, const float* offset_k, const float* scale_k, int D, int H,
+                  int W, float* field_out, float* voxel_d_out, float* aabb_out, ia_stream_t stream);
+
+/* fp32 master parameters -> fp16 working copies (tiny-cuda-nn casts params to fp16 every forward).
+ * enc_params [3072 + 2*total] = [W1 64x32 | W2 16x64 | grid]; col_params [6144] = [W3 64x16 | W4 64x64 | W5 16x64]
+ * (models/networks/ngp.py:27-57 `encoder.params`, `color_net.params`). */
+int ia_params_to_half(const float* enc_params, const float* col_params, void* table_h, void* mlp_h,
+                      ia_stream_t stream);
+
+/* bool [G][G][G] (DensityGrid.density_field) -> bitfield */
+int ia_pack_occupancy(const uint8_t* field_bool, uint32_t* bits, int G, ia_stream_t stream);
+
+/* Fused eval renderer.  Replaces Raymarcher.render_test (renderers/raymarcher_acc.py:82-138) together with
+ * raymarch_test / composite_test (renderers/cuda/raymarcher.cpp:16-29,65-75), SNARFDeformer.deform_test
+ * (deformers/snarf_deformer.py:126-141), fuse_broyden + filter (fuse_cuda.cpp:14-25, filter.cpp:12-18) and
+ * NeRFNGPNet.forward (models/networks/ngp.py:73-83).
+ * rays_o/rays_d [n][3], near/far [n] in the SMPL-root frame (after transform_rays_w2s); bg [n][3] or NULL (white).
+ * Outputs rgb [n][3], depth [n], alpha [n], counter [n] (occupied samples evaluated per ray).
+ * image_width: optional hint (>0: rays are a row-major image of that width -> 8x4 pixel warp tiles).
+ * workspace: >= 256 bytes, zeroed by the library on the stream.  stats: nullable. */
+int ia_render_fwd(const IaScene* scene /*[host]*/, const float* rays_o, const float* rays_d, const float* near,
+                  const float* far, int n_rays, const float* bg, int image_width, float* rgb, float* depth,
+                  float* alpha, float* counter, void* workspace, IaStats* stats, ia_stream_t stream);
+
+/* Point query: per point, max density over the valid canonical correspondences.  Replaces
+ * SNARFDeformer.__call__(pts, model, eval_mode) (deformers/snarf_deformer.py:126-165), used by
+ * DensityGrid.update / initialize (models/structures/density_grid.py:46-110).
+ * pts [n][3]; eval_mode != 0: invalid sigma = 0 and nan_to_num, else invalid sigma = -1e5.
+ * Outputs rgb [n][3], sigma [n]; xc_best [n][3] (nullable; canonical point of the arg-max candidate, 0 if none);
+ * best_init [n] int8 (nullable; index 0..12 of the winning initialisation, -1 if none valid). */
+int ia_deform_query(const IaScene* scene /*[host]*/, const float* pts, int n, int eval_mode, float* rgb, float* sigma,
+                    float* xc_best, int8_t* best_init, IaStats* stats, ia_stream_t stream);
+
+/* Fine-grained entry points (serve the legacy `model(pts)` callback path and the tinycudann-named shim):
+ * ia_broyden replaces fuse_kernel.fuse_broyden + filter_cuda.filter
+ *   (deformer_torch.py:100-116): xd [n][3] -> xc [n][13][3] (0 where invalid), valid [n][13] (after filter),
+ *   j_inv [n][13][9] (nullable).
+ * ia_ngp_forward replaces NeRFNGPNet.forward: x [n][3] canonical points -> sigma [n], rgb [n][3]. */
+int ia_broyden(const IaScene* scene /*[host]*/, const float* xd, int n, float* xc, uint8_t* valid, float* j_inv,
+               ia_stream_t stream);
+int ia_ngp_forward(const IaScene* scene /*[host]*/, const float* x, int n, float* sigma, float* rgb,
+                   ia_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IA_B200_H */

@@ -1,0 +1,86 @@
+"""ctypes binding of libia_b200.so (include/ia_b200.h).
+
+There is no CPU fallback: importing this module without the compiled sm_100a library raises, and every
+entry point requires CUDA tensors.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libia_b200.so")
+
+IA_MLP_HALFS = 11008
+IA_ENC_MLP_PARAMS = 3072
+IA_COL_MLP_PARAMS = 6144
+IA_NUM_INIT = 13
+IA_MAX_SAMPLES = 256
+
+SYMBOLS = [
+    "ia_abi_version", "ia_last_error", "ia_sm_count", "ia_hashgrid_layout", "ia_precompute", "ia_params_to_half",
+    "ia_pack_occupancy", "ia_render_fwd", "ia_deform_query", "ia_broyden", "ia_ngp_forward",
+]
+
+
+class IaScene(C.Structure):
+    _fields_ = [
+        ("field", C.c_void_p), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("offset_k", C.c_void_p), ("scale_k", C.c_void_p), ("tfs", C.c_void_p),
+        ("occ_bits", C.c_void_p), ("G", C.c_int32), ("occ_aabb", C.c_void_p),
+        ("table_h", C.c_void_p), ("mlp_h", C.c_void_p), ("net_center", C.c_void_p), ("net_scale", C.c_void_p),
+    ]
+
+
+class IaStats(C.Structure):
+    _fields_ = [("samples", C.c_ulonglong), ("gathers", C.c_ulonglong), ("net_evals", C.c_ulonglong),
+                ("rays_hit", C.c_ulonglong)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(instantavatar_b200 has no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.ia_last_error.restype = C.c_char_p
+        for s in SYMBOLS:
+            getattr(_lib, s)  # fail loudly on a stale library
+        if _lib.ia_abi_version() != 1:
+            raise RuntimeError("libia_b200.so ABI version mismatch")
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError(f"libia_b200: {lib().ia_last_error().decode()} (code {rc})")
+
+
+def ptr(t: torch.Tensor | None, dtype=None) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError("instantavatar_b200 kernels need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("tensor must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"expected {dtype}, got {t.dtype}")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def hashgrid_layout() -> dict:
+    res = (C.c_uint32 * 16)(); scale = (C.c_float * 16)(); size = (C.c_uint32 * 16)(); off = (C.c_uint32 * 16)()
+    tot = C.c_uint32(0)
+    check(lib().ia_hashgrid_layout(res, scale, size, off, C.byref(tot)))
+    return {"res": list(res), "scale": list(scale), "size": list(size), "offset": list(off), "total": int(tot.value)}

@@ -1,0 +1,677 @@
+// ia_kernels.cu -- sm_100a kernels + the extern "C" boundary of libia_b200.so (include/ia_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 -std=c++17 (see build.py).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "ia_warp_eval.cuh"
+
+using namespace ia;
+
+// ================================================================================================
+// error plumbing
+// ================================================================================================
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+#define IA_CHECK_CUDA(expr)                                                            \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) return set_err(IA_ECUDA, #expr ": %s", cudaGetErrorString(_e)); \
+    } while (0)
+#define IA_REQUIRE(cond)                                                    \
+    do {                                                                    \
+        if (!(cond)) return set_err(IA_EINVAL, "invalid argument: %s", #cond); \
+    } while (0)
+
+static const int kInitBones[kNumInit] = {0, 1, 2, 4, 5, 10, 11, 12, 15, 16, 17, 18, 19};  // deformer_torch.py:28
+__constant__ int c_init_bones[kNumInit] = {0, 1, 2, 4, 5, 10, 11, 12, 15, 16, 17, 18, 19};
+
+static void host_hash_levels(HashLevels& hl, uint32_t* total) {
+    uint32_t off = 0;
+    for (int l = 0; l < kLevels; l++) {
+        const float s = exp2f((float)l * log2f(1.5f)) * 16.0f - 1.0f;
+        const uint32_t r = (uint32_t)ceilf(s) + 1u;
+        uint64_t n = ((uint64_t)r * r * r + 7) / 8 * 8;
+        if (n > (1u << 19)) n = (1u << 19);
+        hl.scale[l] = s; hl.res[l] = r; hl.size[l] = (uint32_t)n; hl.offset[l] = off;
+        off += (uint32_t)n;
+    }
+    if (total) *total = off;
+}
+
+static float filter_threshold() {
+    const double c = 0.0001 * 0.0001;  // filter.cu:44 compares the float distance against this double
+    float cf = (float)c;
+    if ((double)cf < c) cf = nextafterf(cf, INFINITY);
+    return cf;
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+    if (!g_sm_count) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_sm_count;
+}
+
+// ================================================================================================
+// per-CTA prologue shared by the fused kernels: stage per-frame constants in shared memory
+// ================================================================================================
+struct SceneDev {
+    IaScene s;
+    HashLevels hl;
+    float filter_thr;
+};
+
+__device__ __forceinline__ void load_frame_const(FrameConst& fc, const SceneDev& sd) {
+    const int tid = threadIdx.x;
+    if (tid < kNumInit * 12) {
+        const int i = tid / 12, e = tid % 12;
+        fc.Tb[i][e] = sd.s.tfs[c_init_bones[i] * 16 + e];  // rows 0..2 of the 4x4
+    }
+    if (tid < 3) {
+        fc.bp.off[tid] = sd.s.offset_k[tid];
+        fc.bp.scl[tid] = sd.s.scale_k[tid];
+        fc.net_center[tid] = sd.s.net_center[tid];
+        fc.net_scale[tid] = sd.s.net_scale[tid];
+        if (sd.s.occ_aabb) {
+            const float mn = sd.s.occ_aabb[tid], mx = sd.s.occ_aabb[3 + tid];
+            fc.occ_min[tid] = mn;
+            fc.occ_s[tid] = (float)sd.s.G / (mx - mn);  // raymarcher.cu:37
+        }
+    }
+    if (tid == 0) {
+        const float cvg = 1e-5f, dvg = 1e-1f;  // deformer_torch.py:100
+        fc.bp.cvg2 = cvg * cvg;
+        fc.bp.dvg2 = dvg * dvg;
+        fc.filter_thr = sd.filter_thr;
+    }
+}
+
+// ================================================================================================
+// fused eval renderer
+// ================================================================================================
+struct RenderArgs {
+    SceneDev sd;
+    const float* rays_o; const float* rays_d; const float* near; const float* far; const float* bg;
+    int n_rays, image_width;
+    float* rgb; float* depth; float* alpha; float* counter;
+    int* tile_counter;
+    IaStats* stats;
+};
+
+struct RenderWarpExtra {
+    float qx[64], qy[64], qz[64], qt[64];
+    int qowner[64];
+    float bt[32];
+    int bo[32];
+};
+
+template <int kWarps>
+struct RenderSmem {
+    __align__(128) uint32_t occ[64 * 64 * 64 / 32];
+    __align__(16) __half W[kMlpHalfs];
+    FrameConst fc;
+    __align__(8) uint64_t mbar;
+    WarpScratch<false> ws[kWarps];
+    RenderWarpExtra wx[kWarps];
+};
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid_constant__ RenderArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    RenderSmem<kWarps>& sm = *reinterpret_cast<RenderSmem<kWarps>*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = a.sd.s.G;
+    // ---- prologue: TMA-engine bulk copies of the occupancy bitfield and the MLP weights -------------
+    const uint32_t occ_bytes = (uint32_t)(G * G * G / 8);
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.mbar, 1);
+        mbar_expect_tx(&sm.mbar, occ_bytes + kMlpHalfs * 2);
+        bulk_g2s(sm.occ, a.sd.s.occ_bits, occ_bytes, &sm.mbar);
+        bulk_g2s(sm.W, a.sd.s.mlp_h, kMlpHalfs * 2, &sm.mbar);
+    }
+    load_frame_const(sm.fc, a.sd);
+    __syncthreads();
+    mbar_wait(&sm.mbar, 0);
+
+    EvalCtx ctx;
+    ctx.field.data = reinterpret_cast<const float4*>(a.sd.s.field);
+    ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
+    ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
+    ctx.Wsm = sm.W;
+    ctx.fc = &sm.fc;
+    ctx.hl = &a.sd.hl;
+    WarpScratch<false>& ws = sm.ws[warp];
+    RenderWarpExtra& wx = sm.wx[warp];
+    const FrameConst& fc = sm.fc;
+
+    const bool tiled = a.image_width > 0 && (a.image_width % 8) == 0 && (a.n_rays % (a.image_width * 4)) == 0;
+    const int n_tiles = (a.n_rays + 31) / 32;
+    const int tiles_x = tiled ? a.image_width / 8 : 1;
+    unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_hit = 0;
+
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
+        tile = __shfl_sync(kFull, tile, 0);
+        if (tile >= n_tiles) break;
+        int ray;
+        if (tiled) {
+            const int ty = tile / tiles_x, tx = tile % tiles_x;
+            ray = (ty * 4 + (lane >> 3)) * a.image_width + tx * 8 + (lane & 7);
+        } else {
+            ray = tile * 32 + lane;
+        }
+        const bool has = ray < a.n_rays;
+        float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, t = 0, far = 0, dt = 0;
+        if (has) {
+            ox = a.rays_o[ray * 3]; oy = a.rays_o[ray * 3 + 1]; oz = a.rays_o[ray * 3 + 2];
+            dx = a.rays_d[ray * 3]; dy = a.rays_d[ray * 3 + 1]; dz = a.rays_d[ray * 3 + 2];
+            t = a.near[ray]; far = a.far[ray];
+            dt = (far - t) / (float)IA_MAX_SAMPLES;  // raymarcher_acc.py:102
+        }
+        float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Dp = 0.f;
+        int nocc = 0;
+        int qhead = 0, qcount = 0;
+        for (;;) {
+            // ---- scan: march until 32 occupied samples are queued (raymarcher.cu:13-73) ----
+            while (qcount < 32) {
+                const bool act = has && t < far && T > 1e-4f && nocc < IA_MAX_SAMPLES;
+                if (!__any_sync(kFull, act)) break;
+                bool occ = false;
+                float x = 0, y = 0, z = 0;
+                if (act) {
+                    x = __fmaf_rn(t, dx, ox); y = __fmaf_rn(t, dy, oy); z = __fmaf_rn(t, dz, oz);
+                    const int nx = (int)clampf((x - fc.occ_min[0]) * fc.occ_s[0], 0.0f, (float)G - 1.0f);
+                    const int ny = (int)clampf((y - fc.occ_min[1]) * fc.occ_s[1], 0.0f, (float)G - 1.0f);
+                    const int nz = (int)clampf((z - fc.occ_min[2]) * fc.occ_s[2], 0.0f, (float)G - 1.0f);
+                    const int bit = (nx * G + ny) * G + nz;
+                    occ = (sm.occ[bit >> 5] >> (bit & 31)) & 1u;
+                }
+                const unsigned m = __ballot_sync(kFull, occ);
+                if (occ) {
+                    const int slot = (qhead + qcount + __popc(m & ((1u << lane) - 1u))) & 63;
+                    wx.qx[slot] = x; wx.qy[slot] = y; wx.qz[slot] = z; wx.qt[slot] = t; wx.qowner[slot] = lane;
+                    nocc++;
+                }
+                qcount += __popc(m);
+                if (act) t += dt;
+            }
+            if (qcount == 0) break;
+            __syncwarp();
+            // ---- pop a batch of up to 32 samples ----
+            const int n = min(qcount, 32);
+            const bool sact = lane < n;
+            const int slot = (qhead + lane) & 63;
+            float sx = 0, sy = 0, sz = 0, stt = 0;
+            int sown = -1;
+            if (sact) { sx = wx.qx[slot]; sy = wx.qy[slot]; sz = wx.qz[slot]; stt = wx.qt[slot]; sown = wx.qowner[slot]; }
+            qhead = (qhead + n) & 63;
+            qcount -= n;
+            st_samples += sact ? 1u : 0u;
+            SampleOut so;
+            warp_eval_samples<false>(ctx, ws, sact, sx, sy, sz, true, lane, so, st_gather, st_roots);
+            // ---- composite in sample order (raymarcher.cu:200-235) ----
+            ws.res[lane][0] = so.sigma; ws.res[lane][1] = so.r; ws.res[lane][2] = so.g; ws.res[lane][3] = so.b;
+            wx.bt[lane] = stt; wx.bo[lane] = sown;
+            __syncwarp();
+            for (int i = 0; i < n; i++) {
+                if (wx.bo[i] == lane && T > 1e-4f) {
+                    const float tau = expf(-ws.res[i][0] * dt);
+                    const float al = 1.0f - tau;
+                    if (!(al < 0.01f)) {
+                        const float w = al * T;
+                        Cr = __fmaf_rn(w, ws.res[i][1], Cr);
+                        Cg = __fmaf_rn(w, ws.res[i][2], Cg);
+                        Cb = __fmaf_rn(w, ws.res[i][3], Cb);
+                        Dp = __fmaf_rn(w, wx.bt[i], Dp);
+                        T *= tau;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (has) {
+            float b0 = 1.f, b1 = 1.f, b2 = 1.f;  // raymarcher_acc.py:128-132
+            if (a.bg) { b0 = a.bg[ray * 3]; b1 = a.bg[ray * 3 + 1]; b2 = a.bg[ray * 3 + 2]; }
+            a.rgb[ray * 3 + 0] = Cr + T * b0;
+            a.rgb[ray * 3 + 1] = Cg + T * b1;
+            a.rgb[ray * 3 + 2] = Cb + T * b2;
+            a.depth[ray] = Dp;
+            a.alpha[ray] = 1.0f - T;
+            a.counter[ray] = (float)nocc;
+            st_hit += nocc > 0 ? 1u : 0u;
+        }
+    }
+    if (a.stats) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            st_gather += __shfl_xor_sync(kFull, st_gather, o);
+            st_roots += __shfl_xor_sync(kFull, st_roots, o);
+            st_samples += __shfl_xor_sync(kFull, st_samples, o);
+            st_hit += __shfl_xor_sync(kFull, st_hit, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.stats->gathers, (unsigned long long)st_gather);
+            atomicAdd(&a.stats->net_evals, (unsigned long long)st_roots);
+            atomicAdd(&a.stats->samples, (unsigned long long)st_samples);
+            atomicAdd(&a.stats->rays_hit, (unsigned long long)st_hit);
+        }
+    }
+}
+
+// ================================================================================================
+// point query (DensityGrid passes, legacy model(pts) path)
+// ================================================================================================
+struct QueryArgs {
+    SceneDev sd;
+    const float* pts; int n; int eval_mode;
+    float* rgb; float* sigma; float* xc_best; int8_t* best_init;
+    IaStats* stats;
+};
+
+template <int kWarps>
+struct QuerySmem {
+    __align__(16) __half W[kMlpHalfs];
+    FrameConst fc;
+    __align__(8) uint64_t mbar;
+    WarpScratch<true> ws[kWarps];
+};
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __grid_constant__ QueryArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    QuerySmem<kWarps>& sm = *reinterpret_cast<QuerySmem<kWarps>*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.mbar, 1);
+        mbar_expect_tx(&sm.mbar, kMlpHalfs * 2);
+        bulk_g2s(sm.W, a.sd.s.mlp_h, kMlpHalfs * 2, &sm.mbar);
+    }
+    load_frame_const(sm.fc, a.sd);
+    __syncthreads();
+    mbar_wait(&sm.mbar, 0);
+    EvalCtx ctx;
+    ctx.field.data = reinterpret_cast<const float4*>(a.sd.s.field);
+    ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
+    ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
+    ctx.Wsm = sm.W; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
+    unsigned st_gather = 0, st_roots = 0, st_samples = 0;
+    const int n_batches = (a.n + 31) / 32;
+    for (int bidx = blockIdx.x * kWarps + warp; bidx < n_batches; bidx += gridDim.x * kWarps) {
+        const int p = bidx * 32 + lane;
+        const bool act = p < a.n;
+        float x = 0, y = 0, z = 0;
+        if (act) { x = a.pts[p * 3]; y = a.pts[p * 3 + 1]; z = a.pts[p * 3 + 2]; }
+        SampleOut so;
+        warp_eval_samples<true>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots);
+        st_samples += act ? 1u : 0u;
+        if (act) {
+            a.sigma[p] = so.sigma;
+            a.rgb[p * 3] = so.r; a.rgb[p * 3 + 1] = so.g; a.rgb[p * 3 + 2] = so.b;
+            if (a.xc_best) { a.xc_best[p * 3] = so.xc[0]; a.xc_best[p * 3 + 1] = so.xc[1]; a.xc_best[p * 3 + 2] = so.xc[2]; }
+            if (a.best_init) a.best_init[p] = (int8_t)so.best;
+        }
+    }
+    if (a.stats) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            st_gather += __shfl_xor_sync(kFull, st_gather, o);
+            st_roots += __shfl_xor_sync(kFull, st_roots, o);
+            st_samples += __shfl_xor_sync(kFull, st_samples, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.stats->gathers, (unsigned long long)st_gather);
+            atomicAdd(&a.stats->net_evals, (unsigned long long)st_roots);
+            atomicAdd(&a.stats->samples, (unsigned long long)st_samples);
+        }
+    }
+}
+
+// ================================================================================================
+// fine-grained kernels: Broyden + filter, and hash-grid + MLP forward
+// ================================================================================================
+__global__ void __launch_bounds__(256) broyden_kernel(SceneDev sd, const float* __restrict__ xd, int n,
+                                                      float* __restrict__ xc, uint8_t* __restrict__ valid,
+                                                      float* __restrict__ jinv) {
+    __shared__ FrameConst fc;
+    load_frame_const(fc, sd);
+    __syncthreads();
+    FieldDesc f;
+    f.data = reinterpret_cast<const float4*>(sd.s.field); f.D = sd.s.D; f.H = sd.s.H; f.W = sd.s.W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float t0 = xd[p * 3], t1 = xd[p * 3 + 1], t2 = xd[p * 3 + 2];
+    float xs[kNumInit][3];
+    unsigned vmask = 0;
+#pragma unroll 1
+    for (int b = 0; b < kNumInit; b++) {
+        float J[9];
+        int ng = 0;
+        const bool ok = broyden_solve(f, fc.bp, fc.Tb[b], t0, t1, t2, xs[b], jinv ? J : nullptr, ng);
+        if (ok) vmask |= 1u << b;
+        if (jinv) {
+            for (int k = 0; k < 9; k++) jinv[((long)p * kNumInit + b) * 9 + k] = ok ? J[k] : 0.f;
+        }
+    }
+    unsigned kept = vmask;
+    for (int i = 0; i < kNumInit - 1; i++) {
+        if (!((vmask >> i) & 1)) continue;
+        for (int j = i + 1; j < kNumInit; j++) {
+            if (!((vmask >> j) & 1)) continue;
+            const float d0 = xs[i][0] - xs[j][0], d1 = xs[i][1] - xs[j][1], d2 = xs[i][2] - xs[j][2];
+            if (dot3f(d0, d0, d1, d1, d2, d2) < fc.filter_thr) { kept &= ~(1u << i); break; }
+        }
+    }
+    for (int b = 0; b < kNumInit; b++) {
+        const bool ok = (vmask >> b) & 1;  // xc is written where Broyden converged (before the filter), as the reference does
+        for (int k = 0; k < 3; k++) xc[((long)p * kNumInit + b) * 3 + k] = ok ? xs[b][k] : 0.f;
+        valid[(long)p * kNumInit + b] = (kept >> b) & 1;
+    }
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) ngp_forward_kernel(const __grid_constant__ SceneDev sd,
+                                                                  const float* __restrict__ x, int n,
+                                                                  float* __restrict__ sigma, float* __restrict__ rgb) {
+    __shared__ __align__(16) __half W[kMlpHalfs];
+    __shared__ __align__(16) __half At[kWarps][32][kW1Stride];
+    __shared__ float res[kWarps][32][4];
+    __shared__ float cs[6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kMlpHalfs / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(W)[i] = reinterpret_cast<const uint32_t*>(sd.s.mlp_h)[i];
+    if (threadIdx.x < 3) { cs[threadIdx.x] = sd.s.net_center[threadIdx.x]; cs[3 + threadIdx.x] = sd.s.net_scale[threadIdx.x]; }
+    __syncthreads();
+    const __half2* table = reinterpret_cast<const __half2*>(sd.s.table_h);
+    const int n_batches = (n + 31) / 32;
+    for (int bidx = blockIdx.x * kWarps + warp; bidx < n_batches; bidx += gridDim.x * kWarps) {
+        const int p = bidx * 32 + lane;
+        const bool has = p < n;
+        __half2* arow = reinterpret_cast<__half2*>(&At[warp][lane][0]);
+        if (has) {
+            const float n0 = fminf(fmaxf((x[p * 3] - cs[0]) / cs[3] + 0.5f, 0.f), 1.f);
+            const float n1 = fminf(fmaxf((x[p * 3 + 1] - cs[1]) / cs[4] + 0.5f, 0.f), 1.f);
+            const float n2 = fminf(fmaxf((x[p * 3 + 2] - cs[2]) / cs[5] + 0.5f, 0.f), 1.f);
+#pragma unroll 4
+            for (int l = 0; l < kLevels; l++) arow[l] = hash_encode_level(table, sd.hl, l, n0, n1, n2);
+        } else {
+            for (int l = 0; l < kLevels; l++) arow[l] = __floats2half2_rn(0.f, 0.f);
+        }
+        __syncwarp();
+        mlp_tile16(&At[warp][0][0], W, &res[warp][0], lane);
+        mlp_tile16(&At[warp][16][0], W, &res[warp][16], lane);
+        __syncwarp();
+        if (has) {
+            sigma[p] = res[warp][lane][0];
+            rgb[p * 3] = res[warp][lane][1]; rgb[p * 3 + 1] = res[warp][lane][2]; rgb[p * 3 + 2] = res[warp][lane][3];
+        }
+        __syncwarp();
+    }
+}
+
+// ================================================================================================
+// per-frame preparation
+// ================================================================================================
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+    // works for any sign: ordered-int trick
+    if (v >= 0) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+    if (v >= 0) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// precompute.cu:24-71 with a voxel-major output layout; one thread per voxel, weights read coalesced
+// (channel-major input), output written as 3 x float4.
+__global__ void __launch_bounds__(256) precompute_kernel(const float* __restrict__ voxel_w, const float* __restrict__ tfs,
+                                                         const float* __restrict__ offset_k,
+                                                         const float* __restrict__ scale_k, int D, int H, int W,
+                                                         float4* __restrict__ field, float* __restrict__ voxel_d,
+                                                         float* __restrict__ aabb) {
+    __shared__ float T[24][12];
+    __shared__ float red[6];
+    for (int i = threadIdx.x; i < 24 * 12; i += blockDim.x) T[i / 12][i % 12] = tfs[(i / 12) * 16 + (i % 12)];
+    if (threadIdx.x < 3) { red[threadIdx.x] = INFINITY; red[3 + threadIdx.x] = -INFINITY; }
+    __syncthreads();
+    const long V = (long)D * H * W;
+    const long index = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    float vd[3] = {INFINITY, INFINITY, INFINITY};
+    const bool act = index < V;
+    if (act) {
+        const int idx_d = (int)(index / ((long)H * W));
+        const int idx_h = (int)(index % ((long)H * W) / W);
+        const int idx_w = (int)(index % ((long)H * W) % W);
+        const float cx = (((float)idx_w) / (float)(W - 1) * 2.f - 1.f) / scale_k[0] - offset_k[0];
+        const float cy = (((float)idx_h) / (float)(H - 1) * 2.f - 1.f) / scale_k[1] - offset_k[1];
+        const float cz = (((float)idx_d) / (float)(D - 1) * 2.f - 1.f) / scale_k[2] - offset_k[2];
+        float J[12];
+#pragma unroll
+        for (int c = 0; c < 12; c++) J[c] = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < 24; j++) {
+            const float w = __ldg(voxel_w + (long)j * V + index);
+#pragma unroll
+            for (int c = 0; c < 12; c++) J[c] = __fmaf_rn(w, T[j][c], J[c]);
+        }
+        field[index * 3 + 0] = make_float4(J[0], J[1], J[2], J[3]);
+        field[index * 3 + 1] = make_float4(J[4], J[5], J[6], J[7]);
+        field[index * 3 + 2] = make_float4(J[8], J[9], J[10], J[11]);
+#pragma unroll
+        for (int i0 = 0; i0 < 3; i0++) {
+            vd[i0] = aff3f(J[i0 * 4 + 0], cx, J[i0 * 4 + 1], cy, J[i0 * 4 + 2], cz, J[i0 * 4 + 3]);
+            if (voxel_d) voxel_d[(long)i0 * V + index] = vd[i0];
+        }
+    }
+    if (aabb) {
+#pragma unroll
+        for (int i0 = 0; i0 < 3; i0++) {
+            float mn = act ? vd[i0] : INFINITY, mx = act ? vd[i0] : -INFINITY;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+            }
+            if ((threadIdx.x & 31) == 0) { atomic_min_f(&red[i0], mn); atomic_max_f(&red[3 + i0], mx); }
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) { atomic_min_f(&aabb[threadIdx.x], red[threadIdx.x]); atomic_max_f(&aabb[3 + threadIdx.x], red[3 + threadIdx.x]); }
+    }
+}
+
+__global__ void params_to_half_kernel(const float* __restrict__ enc, const float* __restrict__ col,
+                                      __half2* __restrict__ table, __half* __restrict__ mlp, uint32_t total_entries) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total_entries) {
+        const float2 v = *reinterpret_cast<const float2*>(enc + IA_ENC_MLP_PARAMS + 2 * i);
+        table[i] = __floats2half2_rn(v.x, v.y);
+    }
+    if (i < kMlpHalfs) {
+        // padded [out][in+8] blocks; pad columns are zero
+        float v = 0.f;
+        int o = (int)i;
+        if (o < kW2Off) { const int r = o / kW1Stride, c = o % kW1Stride; if (c < 32) v = enc[r * 32 + c]; }
+        else if (o < kW3Off) { o -= kW2Off; const int r = o / kW2Stride, c = o % kW2Stride; if (c < 64) v = enc[2048 + r * 64 + c]; }
+        else if (o < kW4Off) {
+            o -= kW3Off; const int r = o / kW3Stride, c = o % kW3Stride;
+            // column rotation: input column 0 carries the constant 1.0 (tcnn pad), columns 1..15 the features
+            if (c < 16) v = col[r * 16 + (c == 0 ? 15 : c - 1)];
+        }
+        else if (o < kW5Off) { o -= kW4Off; const int r = o / kW4Stride, c = o % kW4Stride; if (c < 64) v = col[1024 + r * 64 + c]; }
+        else { o -= kW5Off; const int r = o / kW5Stride, c = o % kW5Stride; if (c < 64) v = col[1024 + 4096 + r * 64 + c]; }
+        mlp[i] = __float2half_rn(v);
+    }
+}
+
+__global__ void pack_occupancy_kernel(const uint8_t* __restrict__ field, uint32_t* __restrict__ bits, int n_words) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t v = 0;
+    const uint8_t* p = field + (long)w * 32;
+#pragma unroll
+    for (int b = 0; b < 32; b++) v |= (p[b] ? 1u : 0u) << b;
+    bits[w] = v;
+}
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+static int make_scene_dev(const IaScene* s, SceneDev& sd, bool need_occ) {
+    IA_REQUIRE(s != nullptr);
+    IA_REQUIRE(s->field && s->offset_k && s->scale_k && s->tfs && s->table_h && s->mlp_h && s->net_center && s->net_scale);
+    IA_REQUIRE(s->D > 1 && s->H > 1 && s->W > 1);
+    if (need_occ) {
+        IA_REQUIRE(s->occ_bits && s->occ_aabb);
+        IA_REQUIRE(s->G == 64);
+    }
+    sd.s = *s;
+    host_hash_levels(sd.hl, nullptr);
+    sd.filter_thr = filter_threshold();
+    return IA_OK;
+}
+
+extern "C" {
+
+int ia_abi_version(void) { return IA_ABI_VERSION; }
+const char* ia_last_error(void) { return g_err; }
+int ia_sm_count(void) { return sm_count(); }
+
+int ia_hashgrid_layout(uint32_t res[IA_NUM_LEVELS], float scale[IA_NUM_LEVELS], uint32_t size[IA_NUM_LEVELS],
+                       uint32_t offset[IA_NUM_LEVELS], uint32_t* total_entries) {
+    HashLevels hl;
+    uint32_t tot;
+    host_hash_levels(hl, &tot);
+    for (int l = 0; l < kLevels; l++) {
+        if (res) res[l] = hl.res[l];
+        if (scale) scale[l] = hl.scale[l];
+        if (size) size[l] = hl.size[l];
+        if (offset) offset[l] = hl.offset[l];
+    }
+    if (total_entries) *total_entries = tot;
+    return IA_OK;
+}
+
+int ia_precompute(const float* voxel_w, const float* tfs, const float* offset_k, const float* scale_k, int D, int H,
+                  int W, float* field_out, float* voxel_d_out, float* aabb_out, ia_stream_t stream) {
+    IA_REQUIRE(voxel_w && tfs && offset_k && scale_k && field_out);
+    IA_REQUIRE(D > 1 && H > 1 && W > 1);
+    const long V = (long)D * H * W;
+    precompute_kernel<<<(unsigned)((V + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        voxel_w, tfs, offset_k, scale_k, D, H, W, reinterpret_cast<float4*>(field_out), voxel_d_out, aabb_out);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_params_to_half(const float* enc_params, const float* col_params, void* table_h, void* mlp_h, ia_stream_t stream) {
+    IA_REQUIRE(enc_params && col_params && table_h && mlp_h);
+    HashLevels hl;
+    uint32_t tot;
+    host_hash_levels(hl, &tot);
+    params_to_half_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        enc_params, col_params, reinterpret_cast<__half2*>(table_h), reinterpret_cast<__half*>(mlp_h), tot);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_pack_occupancy(const uint8_t* field_bool, uint32_t* bits, int G, ia_stream_t stream) {
+    IA_REQUIRE(field_bool && bits && G > 0 && (G * G * G) % 32 == 0);
+    const int n_words = G * G * G / 32;
+    pack_occupancy_kernel<<<(n_words + 255) / 256, 256, 0, (cudaStream_t)stream>>>(field_bool, bits, n_words);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+constexpr int kRenderWarps = 12;
+constexpr int kQueryWarps = 8;
+
+int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d, const float* near, const float* far,
+                  int n_rays, const float* bg, int image_width, float* rgb, float* depth, float* alpha, float* counter,
+                  void* workspace, IaStats* stats, ia_stream_t stream) {
+    IA_REQUIRE(rays_o && rays_d && near && far && rgb && depth && alpha && counter && workspace);
+    IA_REQUIRE(n_rays >= 0);
+    if (n_rays == 0) return IA_OK;
+    RenderArgs a;
+    int rc = make_scene_dev(scene, a.sd, true);
+    if (rc) return rc;
+    a.rays_o = rays_o; a.rays_d = rays_d; a.near = near; a.far = far; a.bg = bg;
+    a.n_rays = n_rays; a.image_width = image_width;
+    a.rgb = rgb; a.depth = depth; a.alpha = alpha; a.counter = counter;
+    a.tile_counter = reinterpret_cast<int*>(workspace);
+    a.stats = stats;
+    cudaStream_t st = (cudaStream_t)stream;
+    IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+    const size_t smem = sizeof(RenderSmem<kRenderWarps>);
+    static bool attr_set = false;
+    if (!attr_set) {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int n_tiles = (n_rays + 31) / 32;
+    int grid = sm_count();
+    if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    grid = min(grid, (n_tiles + kRenderWarps - 1) / kRenderWarps);
+    render_fwd_kernel<kRenderWarps><<<grid, kRenderWarps * 32, smem, st>>>(a);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode, float* rgb, float* sigma,
+                    float* xc_best, int8_t* best_init, IaStats* stats, ia_stream_t stream) {
+    IA_REQUIRE(pts && rgb && sigma && n >= 0);
+    if (n == 0) return IA_OK;
+    QueryArgs a;
+    int rc = make_scene_dev(scene, a.sd, false);
+    if (rc) return rc;
+    a.pts = pts; a.n = n; a.eval_mode = eval_mode; a.rgb = rgb; a.sigma = sigma; a.xc_best = xc_best;
+    a.best_init = best_init; a.stats = stats;
+    const size_t smem = sizeof(QuerySmem<kQueryWarps>);
+    static bool attr_set = false;
+    if (!attr_set) {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(deform_query_kernel<kQueryWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int n_batches = (n + 31) / 32;
+    int grid = sm_count() * 2;
+    if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    grid = min(grid, (n_batches + kQueryWarps - 1) / kQueryWarps);
+    deform_query_kernel<kQueryWarps><<<grid, kQueryWarps * 32, smem, (cudaStream_t)stream>>>(a);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_broyden(const IaScene* scene, const float* xd, int n, float* xc, uint8_t* valid, float* j_inv, ia_stream_t stream) {
+    IA_REQUIRE(xd && xc && valid && n >= 0);
+    if (n == 0) return IA_OK;
+    SceneDev sd;
+    int rc = make_scene_dev(scene, sd, false);
+    if (rc) return rc;
+    broyden_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sd, xd, n, xc, valid, j_inv);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_ngp_forward(const IaScene* scene, const float* x, int n, float* sigma, float* rgb, ia_stream_t stream) {
+    IA_REQUIRE(x && sigma && rgb && n >= 0);
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(scene && scene->table_h && scene->mlp_h && scene->net_center && scene->net_scale);
+    SceneDev sd;
+    sd.s = *scene;
+    host_hash_levels(sd.hl, nullptr);
+    sd.filter_thr = filter_threshold();
+    constexpr int kW = 8;
+    const int n_batches = (n + 31) / 32;
+    int grid = min(sm_count() * 4, (n_batches + kW - 1) / kW);
+    if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    ngp_forward_kernel<kW><<<grid, kW * 32, 0, (cudaStream_t)stream>>>(sd, x, n, sigma, rgb);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+"""Thin Python operators over the C ABI (include/ia_b200.h).  Each mirrors the reference operator it
+replaces; tensors in, tensors out, everything enqueued on torch's current CUDA stream, no host syncs."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field as dc_field
+
+import torch
+
+from . import _lib
+from ._lib import IaScene, IaStats, check, lib, ptr, stream
+
+f32 = torch.float32
+
+
+def precompute(voxel_w: torch.Tensor, tfs: torch.Tensor, offset_k: torch.Tensor, scale_k: torch.Tensor,
+               want_voxel_d: bool = True):
+    """precompute_cuda.precompute (deformer_torch.py:77-83).  voxel_w [1|,24,D,H,W]; tfs [1|,24,4,4].
+    Returns (field [D,H,W,12], voxel_d [3,D,H,W] | None, aabb [6])."""
+    voxel_w = voxel_w.reshape(24, *voxel_w.shape[-3:]).contiguous()
+    D, H, W = voxel_w.shape[-3:]
+    dev = voxel_w.device
+    fld = torch.empty((D, H, W, 12), device=dev, dtype=f32)
+    vd = torch.empty((3, D, H, W), device=dev, dtype=f32) if want_voxel_d else None
+    aabb = torch.tensor([float("inf")] * 3 + [float("-inf")] * 3, device=dev, dtype=f32)
+    check(lib().ia_precompute(ptr(voxel_w, f32), ptr(tfs.reshape(24, 4, 4).contiguous(), f32),
+                              ptr(offset_k.reshape(3).contiguous(), f32), ptr(scale_k.reshape(3).contiguous(), f32),
+                              C.c_int(D), C.c_int(H), C.c_int(W), ptr(fld), ptr(vd), ptr(aabb), stream()))
+    return fld, vd, aabb
+
+
+def params_to_half(enc_params: torch.Tensor, col_params: torch.Tensor, table_h=None, mlp_h=None):
+    total = _lib.hashgrid_layout()["total"]
+    assert enc_params.numel() == _lib.IA_ENC_MLP_PARAMS + 2 * total and col_params.numel() == _lib.IA_COL_MLP_PARAMS
+    dev = enc_params.device
+    if table_h is None:
+        table_h = torch.empty((total, 2), device=dev, dtype=torch.float16)
+    if mlp_h is None:
+        mlp_h = torch.empty(_lib.IA_MLP_HALFS, device=dev, dtype=torch.float16)
+    check(lib().ia_params_to_half(ptr(enc_params, f32), ptr(col_params, f32), ptr(table_h), ptr(mlp_h), stream()))
+    return table_h, mlp_h
+
+
+def pack_occupancy(field_bool: torch.Tensor, bits=None):
+    G = field_bool.shape[0]
+    fb = field_bool.contiguous().view(torch.uint8) if field_bool.dtype == torch.bool else field_bool.contiguous()
+    if bits is None:
+        bits = torch.empty(G * G * G // 32, device=fb.device, dtype=torch.int32)
+    check(lib().ia_pack_occupancy(ptr(fb), ptr(bits), C.c_int(G), stream()))
+    return bits
+
+
+@dataclass
+class Scene:
+    """Per-frame read-only state (IaScene) with the tensors that keep it alive."""
+    field: torch.Tensor            # [D,H,W,12]
+    offset_k: torch.Tensor         # [3]
+    scale_k: torch.Tensor          # [3]
+    tfs: torch.Tensor              # [24,4,4]
+    table_h: torch.Tensor
+    mlp_h: torch.Tensor
+    net_center: torch.Tensor
+    net_scale: torch.Tensor
+    occ_bits: torch.Tensor | None = None
+    occ_aabb: torch.Tensor | None = None   # [6]
+    G: int = 64
+    _keep: list = dc_field(default_factory=list)
+
+    def c_struct(self) -> IaScene:
+        D, H, W, _ = self.field.shape
+        s = IaScene()
+        s.field = ptr(self.field, f32).value; s.D, s.H, s.W = D, H, W
+        s.offset_k = ptr(self.offset_k, f32).value; s.scale_k = ptr(self.scale_k, f32).value
+        s.tfs = ptr(self.tfs, f32).value
+        s.occ_bits = ptr(self.occ_bits).value if self.occ_bits is not None else None
+        s.G = self.G
+        s.occ_aabb = ptr(self.occ_aabb, f32).value if self.occ_aabb is not None else None
+        s.table_h = ptr(self.table_h).value; s.mlp_h = ptr(self.mlp_h).value
+        s.net_center = ptr(self.net_center, f32).value; s.net_scale = ptr(self.net_scale, f32).value
+        return s
+
+
+def new_stats(device) -> torch.Tensor:
+    return torch.zeros(4, device=device, dtype=torch.int64)
+
+
+def stats_dict(t: torch.Tensor) -> dict:
+    v = t.tolist()
+    return {"samples": v[0], "gathers": v[1], "net_evals": v[2], "rays_hit": v[3]}
+
+
+def render_fwd(scene: Scene, rays_o, rays_d, near, far, bg=None, image_width: int = 0, stats: torch.Tensor | None = None,
+               out: dict | None = None, workspace: torch.Tensor | None = None):
+    """Fused Raymarcher.render_test (raymarcher_acc.py:82-138)."""
+    n = rays_o.numel() // 3
+    dev = rays_o.device
+    if out is None:
+        out = {"rgb": torch.empty((n, 3), device=dev, dtype=f32), "depth": torch.empty(n, device=dev, dtype=f32),
+               "alpha": torch.empty(n, device=dev, dtype=f32), "counter": torch.empty(n, device=dev, dtype=f32)}
+    if workspace is None:
+        workspace = torch.empty(64, device=dev, dtype=torch.int32)
+    s = scene.c_struct()
+    check(lib().ia_render_fwd(C.byref(s), ptr(rays_o, f32), ptr(rays_d, f32), ptr(near, f32), ptr(far, f32), C.c_int(n),
+                              ptr(bg), C.c_int(image_width), ptr(out["rgb"]), ptr(out["depth"]), ptr(out["alpha"]),
+                              ptr(out["counter"]), ptr(workspace), ptr(stats), stream()))
+    return out
+
+
+def deform_query(scene: Scene, pts, eval_mode=True, want_xc=False, stats=None):
+    """SNARFDeformer.__call__(pts, net, eval_mode) (snarf_deformer.py:126-165)."""
+    pts = pts.reshape(-1, 3).contiguous()
+    n = pts.shape[0]
+    dev = pts.device
+    rgb = torch.empty((n, 3), device=dev, dtype=f32); sigma = torch.empty(n, device=dev, dtype=f32)
+    xc = torch.empty((n, 3), device=dev, dtype=f32) if want_xc else None
+    best = torch.empty(n, device=dev, dtype=torch.int8) if want_xc else None
+    s = scene.c_struct()
+    check(lib().ia_deform_query(C.byref(s), ptr(pts, f32), C.c_int(n), C.c_int(1 if eval_mode else 0), ptr(rgb), ptr(sigma),
+                                ptr(xc), ptr(best), ptr(stats), stream()))
+    return (rgb, sigma, xc, best) if want_xc else (rgb, sigma)
+
+
+def broyden(scene: Scene, xd, want_jinv=False):
+    """fuse_kernel.fuse_broyden + filter_cuda.filter (deformer_torch.py:100-116)."""
+    xd = xd.reshape(-1, 3).contiguous()
+    n = xd.shape[0]
+    dev = xd.device
+    xc = torch.empty((n, 13, 3), device=dev, dtype=f32); valid = torch.empty((n, 13), device=dev, dtype=torch.uint8)
+    jinv = torch.empty((n, 13, 3, 3), device=dev, dtype=f32) if want_jinv else None
+    s = scene.c_struct()
+    check(lib().ia_broyden(C.byref(s), ptr(xd, f32), C.c_int(n), ptr(xc), ptr(valid), ptr(jinv), stream()))
+    return xc, valid.bool(), jinv
+
+
+def ngp_forward(scene: Scene, x):
+    """NeRFNGPNet.forward (ngp.py:73-83): canonical points -> (rgb, sigma)."""
+    x = x.reshape(-1, 3).contiguous()
+    n = x.shape[0]
+    sigma = torch.empty(n, device=x.device, dtype=f32); rgb = torch.empty((n, 3), device=x.device, dtype=f32)
+    s = scene.c_struct()
+    check(lib().ia_ngp_forward(C.byref(s), ptr(x, f32), C.c_int(n), ptr(sigma), ptr(rgb), stream()))
+    return rgb, sigma

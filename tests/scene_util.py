@@ -1,0 +1,43 @@
+"""Builds the synthetic scene with the ORACLE on the CPU and uploads it for the CUDA product
+(tests only: product code never imports oracle/)."""
+import numpy as np
+
+from oracle import render as orender
+from oracle import scene as oscene
+
+_CACHE = {}
+
+
+def oracle_scene(frame_idx=0, track="male-3-casual", sigma_in=100.0):
+    key = (frame_idx, track, sigma_in)
+    if key in _CACHE:
+        return _CACHE[key]
+    from instantavatar_b200 import synthetic
+    subj = oscene.build_subject(track=track)
+    pose = synthetic.load_pose(frame_idx, track)
+    fr = subj.prepare_frame(pose)
+    net = oscene.build_net(subj, sigma_in=sigma_in)
+    field, density, jit = oscene.build_occupancy(subj, fr, net)
+    sc = {"subj": subj, "pose": pose, "frame": fr, "net": net, "occ": field, "occ_density": density, "occ_jitter": jit}
+    _CACHE[key] = sc
+    return sc
+
+
+def upload(sc, device="cuda"):
+    """oracle scene -> instantavatar_b200.ops.Scene (same inputs on the device)."""
+    import torch
+    from instantavatar_b200 import ops
+    subj, fr, net = sc["subj"], sc["frame"], sc["net"]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    offset_k, scale_k, tfs = t(subj.offset_kernel), t(subj.scale_kernel), t(fr["tfs"])
+    fld, vd, aabb = ops.precompute(t(subj.lbs_voxel), tfs, offset_k, scale_k)
+    table_h, mlp_h = ops.params_to_half(t(net.enc), t(net.col))
+    occ_bits = ops.pack_occupancy(t(sc["occ"]))
+    scene = ops.Scene(field=fld, offset_k=offset_k, scale_k=scale_k, tfs=tfs, table_h=table_h, mlp_h=mlp_h,
+                      net_center=t(net.center), net_scale=t(net.scale), occ_bits=occ_bits,
+                      occ_aabb=t(fr["bbox_deformed"].reshape(6)))
+    return scene, {"voxel_d": vd, "aabb": aabb}
+
+
+def oracle_model(sc, eval_mode=True):
+    return lambda p: orender.deform_query(p, sc["frame"], sc["subj"], sc["net"], eval_mode)

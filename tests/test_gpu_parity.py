@@ -1,0 +1,181 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs."""
+import numpy as np
+import pytest
+
+from oracle import capi
+from oracle import frame as oframe
+from oracle import render as orender
+from oracle import scene as oscene
+from tests import scene_util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sc():
+    return scene_util.oracle_scene(0)
+
+
+@pytest.fixture(scope="module")
+def dev(sc):
+    import torch
+    assert torch.cuda.is_available()
+    scene, extra = scene_util.upload(sc)
+    torch.cuda.synchronize()
+    return scene, extra
+
+
+def sample_points(sc, n, seed=0):
+    rng = np.random.default_rng(seed)
+    bb = sc["frame"]["bbox_deformed"]
+    # 70% near the posed body, 30% uniform in the deformed bbox
+    v = sc["frame"]["vertices"]
+    a = v[rng.integers(0, len(v), int(n * 0.7))] + rng.normal(0, 0.03, (int(n * 0.7), 3)).astype(np.float32)
+    b = rng.uniform(bb[0], bb[1], (n - len(a), 3)).astype(np.float32)
+    return np.concatenate([a, b]).astype(np.float32)
+
+
+def test_precompute_bit_exact(sc, dev):
+    scene, extra = dev
+    vJ = sc["frame"]["voxel_J"]  # [12,D,H,W]
+    fld = scene.field.cpu().numpy()  # [D,H,W,12]
+    np.testing.assert_array_equal(fld, np.moveaxis(vJ, 0, -1))
+    np.testing.assert_array_equal(extra["voxel_d"].cpu().numpy(), sc["frame"]["voxel_d"])
+    np.testing.assert_array_equal(extra["aabb"].cpu().numpy(), sc["frame"]["bbox_deformed"].reshape(6))
+
+
+def test_hashgrid_layout_matches_oracle():
+    from instantavatar_b200 import _lib
+    a, b = _lib.hashgrid_layout(), capi.hashgrid_layout()
+    assert a["total"] == b["total"] == 6513496
+    for k in ("res", "size", "offset"):
+        assert list(a[k]) == [int(x) for x in b[k]]
+    assert list(np.float32(a["scale"])) == list(b["scale"])
+
+
+def test_broyden_bit_exact(sc, dev):
+    import torch
+    from instantavatar_b200 import ops
+    scene, _ = dev
+    pts = sample_points(sc, 20000)
+    xc_o, jinv_o, valid_raw, _ = capi.broyden(pts, sc["frame"]["voxel_J"], sc["frame"]["tfs"], oframe.INIT_BONES,
+                                              sc["subj"].offset_kernel, sc["subj"].scale_kernel)
+    mask_o = capi.filter_roots(xc_o, valid_raw)
+    xc, valid, jinv = ops.broyden(scene, torch.from_numpy(pts).cuda(), want_jinv=True)
+    xc, valid, jinv = xc.cpu().numpy(), valid.cpu().numpy(), jinv.cpu().numpy()
+    assert valid_raw.sum() > 1000
+    np.testing.assert_array_equal(valid, mask_o)
+    np.testing.assert_array_equal(xc, xc_o)
+    np.testing.assert_array_equal(jinv.reshape(jinv_o.shape), jinv_o)
+
+
+def test_ngp_forward_close(sc, dev):
+    import torch
+    from instantavatar_b200 import ops
+    scene, _ = dev
+    rng = np.random.default_rng(1)
+    bb = sc["subj"].bbox
+    x = rng.uniform(bb[0], bb[1], (65536, 3)).astype(np.float32)
+    # half of the points near the canonical body so that densities are non-trivial
+    v = sc["subj"].verts_cano
+    x[:32768] = v[rng.integers(0, len(v), 32768)] + rng.normal(0, 0.02, (32768, 3)).astype(np.float32)
+    s_o, c_o = sc["net"](x)
+    c, s = ops.ngp_forward(scene, torch.from_numpy(x).cuda())
+    c, s = c.cpu().numpy(), s.cpu().numpy()
+    # fp16 network: 1 fp16 ulp of |sigma| <= 128 is 0.0625; accumulation-order effects flip at most the last fp16 bit
+    assert np.abs(s - s_o).max() <= 0.13, np.abs(s - s_o).max()
+    assert np.mean(s == s_o) > 0.97
+    assert np.abs(c - c_o).max() <= 2e-3
+    assert (s_o > 10).sum() > 1000
+
+
+def test_deform_query_matches_oracle(sc, dev):
+    import torch
+    from instantavatar_b200 import ops
+    scene, _ = dev
+    pts = sample_points(sc, 30000, seed=3)
+    for eval_mode in (True, False):
+        rgb_o, sig_o, aux = orender.deform_query(pts, sc["frame"], sc["subj"], sc["net"], eval_mode, return_aux=True)
+        rgb, sig, xc, best = ops.deform_query(scene, torch.from_numpy(pts).cuda(), eval_mode, want_xc=True)
+        rgb, sig, xc, best = rgb.cpu().numpy(), sig.cpu().numpy(), xc.cpu().numpy(), best.cpu().numpy()
+        ok = np.abs(sig - sig_o) <= 0.13
+        assert ok.mean() > 0.9995, ok.mean()
+        assert np.mean(np.abs(rgb - rgb_o).max(-1) <= 2e-3) > 0.999
+        has = best >= 0
+        assert has.sum() > 1000
+        assert np.array_equal(has, aux["valid"].any(-1) & (np.take_along_axis(aux["valid"], aux["idx"][:, None], 1)[:, 0]))
+        same = best[has] == aux["idx"][has]
+        assert same.mean() > 0.999
+        xo = aux["xc"][np.arange(len(pts)), np.maximum(best, 0)]
+        np.testing.assert_array_equal(xc[has], xo[has])
+
+
+def _render_compare(sc, dev, idx, image_width):
+    import torch
+    from instantavatar_b200 import ops
+    scene, _ = dev
+    fr = sc["frame"]
+    o, d, near, far = oscene.camera_rays(fr, 512, 512)
+    o, d, near, far = o[idx], d[idx], near[idx], far[idx]
+    ref = orender.render_test(o, d, near, far, sc["occ"], fr["bbox_deformed"][0], fr["bbox_deformed"][1],
+                              scene_util.oracle_model(sc, True))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    stats = ops.new_stats("cuda")
+    out = ops.render_fwd(scene, t(o), t(d), t(near), t(far), None, image_width, stats)
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    return ref, got, ops.stats_dict(stats)
+
+
+def check_render(ref, got, n_hit_min):
+    err_rgb = np.abs(got["rgb"] - ref["rgb"]).max(-1)
+    err_a = np.abs(got["alpha"] - ref["alpha"])
+    bad = (err_rgb > 1e-3) | (err_a > 1e-3)
+    hit = ref["alpha"] > 0.5
+    assert hit.sum() >= n_hit_min
+    # The 1e-3 bound (BASELINE.json north_star) holds for all rays except those where a discrete decision of the
+    # reference algorithm (alpha < 0.01 skip, T <= 1e-4 stop, arg-max over candidates) sits within rounding
+    # distance of its threshold; those are bounded by the size of the skipped term.
+    assert bad.mean() <= 2e-4, (bad.sum(), bad.mean(), err_rgb.max(), err_a.max())
+    assert err_rgb.max() <= 3e-2 and err_a.max() <= 3e-2
+    dep = np.abs(got["depth"] - ref["depth"])
+    assert np.mean(dep > 5e-3) <= 2e-4
+
+
+def test_render_fwd_subsampled_image(sc, dev):
+    idx = (np.arange(0, 512, 4)[:, None] * 512 + np.arange(0, 512, 4)[None]).ravel()
+    ref, got, st = _render_compare(sc, dev, idx, 0)
+    check_render(ref, got, 300)
+    assert st["samples"] > 0 and st["net_evals"] > 0 and st["gathers"] > st["samples"] * 13
+
+
+def test_render_fwd_tiled_crop(sc, dev):
+    # a 128-wide x 192-tall crop around the body, tiled 8x4 path
+    ys, xs = np.arange(160, 352), np.arange(224, 352)
+    idx = (ys[:, None] * 512 + xs[None]).ravel()
+    ref, got, st = _render_compare(sc, dev, idx, 128)
+    check_render(ref, got, 3000)
+    # background rays: exactly white, alpha 0
+    miss = ref["counter"] == 0
+    assert np.array_equal(got["rgb"][miss], ref["rgb"][miss]) and np.array_equal(got["alpha"][miss], ref["alpha"][miss])
+
+
+def test_render_edge_cases(sc, dev):
+    import torch
+    from instantavatar_b200 import ops
+    scene, _ = dev
+    # empty input
+    e = torch.empty((0, 3), device="cuda")
+    out = ops.render_fwd(scene, e, e, torch.empty(0, device="cuda"), torch.empty(0, device="cuda"))
+    assert out["rgb"].shape == (0, 3)
+    # ragged count (not a multiple of 32), custom background
+    fr = sc["frame"]
+    o, d, near, far = oscene.camera_rays(fr, 512, 512)
+    idx = np.arange(512 * 250 + 200, 512 * 250 + 200 + 77)
+    bg = np.random.default_rng(0).random((77, 3)).astype(np.float32)
+    ref = orender.render_test(o[idx], d[idx], near[idx], far[idx], sc["occ"], fr["bbox_deformed"][0], fr["bbox_deformed"][1],
+                              scene_util.oracle_model(sc, True), bg_color=bg)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    out = ops.render_fwd(scene, t(o[idx]), t(d[idx]), t(near[idx]), t(far[idx]), t(bg))
+    assert np.abs(out["rgb"].cpu().numpy() - ref["rgb"]).max() <= 1e-3
+    assert np.abs(out["alpha"].cpu().numpy() - ref["alpha"]).max() <= 1e-3
