@@ -26,7 +26,6 @@ static int set_err(int code, const char* fmt, const char* detail = "") {
         if (!(cond)) return set_err(IA_EINVAL, "invalid argument: %s", #cond); \
     } while (0)
 
-static const int kInitBones[kNumInit] = {0, 1, 2, 4, 5, 10, 11, 12, 15, 16, 17, 18, 19};  // deformer_torch.py:28
 __constant__ int c_init_bones[kNumInit] = {0, 1, 2, 4, 5, 10, 11, 12, 15, 16, 17, 18, 19};
 
 static void host_hash_levels(HashLevels& hl, uint32_t* total) {
@@ -77,8 +76,10 @@ __device__ __forceinline__ void load_frame_const(FrameConst& fc, const SceneDev&
     if (tid < 3) {
         fc.bp.off[tid] = sd.s.offset_k[tid];
         fc.bp.scl[tid] = sd.s.scale_k[tid];
-        fc.net_center[tid] = sd.s.net_center[tid];
-        fc.net_scale[tid] = sd.s.net_scale[tid];
+        if (sd.s.net_center) {
+            fc.net_center[tid] = sd.s.net_center[tid];
+            fc.net_scale[tid] = sd.s.net_scale[tid];
+        }
         if (sd.s.occ_aabb) {
             const float mn = sd.s.occ_aabb[tid], mx = sd.s.occ_aabb[3 + tid];
             fc.occ_min[tid] = mn;
@@ -523,9 +524,10 @@ __global__ void pack_occupancy_kernel(const uint8_t* __restrict__ field, uint32_
 // ================================================================================================
 // extern "C"
 // ================================================================================================
-static int make_scene_dev(const IaScene* s, SceneDev& sd, bool need_occ) {
+static int make_scene_dev(const IaScene* s, SceneDev& sd, bool need_occ, bool need_net = true) {
     IA_REQUIRE(s != nullptr);
-    IA_REQUIRE(s->field && s->offset_k && s->scale_k && s->tfs && s->table_h && s->mlp_h && s->net_center && s->net_scale);
+    IA_REQUIRE(s->field && s->offset_k && s->scale_k && s->tfs);
+    if (need_net) IA_REQUIRE(s->table_h && s->mlp_h && s->net_center && s->net_scale);
     IA_REQUIRE(s->D > 1 && s->H > 1 && s->W > 1);
     if (need_occ) {
         IA_REQUIRE(s->occ_bits && s->occ_aabb);
@@ -594,9 +596,9 @@ constexpr int kQueryWarps = 8;
 int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d, const float* near, const float* far,
                   int n_rays, const float* bg, int image_width, float* rgb, float* depth, float* alpha, float* counter,
                   void* workspace, IaStats* stats, ia_stream_t stream) {
-    IA_REQUIRE(rays_o && rays_d && near && far && rgb && depth && alpha && counter && workspace);
     IA_REQUIRE(n_rays >= 0);
     if (n_rays == 0) return IA_OK;
+    IA_REQUIRE(rays_o && rays_d && near && far && rgb && depth && alpha && counter && workspace);
     RenderArgs a;
     int rc = make_scene_dev(scene, a.sd, true);
     if (rc) return rc;
@@ -624,8 +626,9 @@ int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d
 
 int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode, float* rgb, float* sigma,
                     float* xc_best, int8_t* best_init, IaStats* stats, ia_stream_t stream) {
-    IA_REQUIRE(pts && rgb && sigma && n >= 0);
+    IA_REQUIRE(n >= 0);
     if (n == 0) return IA_OK;
+    IA_REQUIRE(pts && rgb && sigma);
     QueryArgs a;
     int rc = make_scene_dev(scene, a.sd, false);
     if (rc) return rc;
@@ -647,10 +650,11 @@ int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode
 }
 
 int ia_broyden(const IaScene* scene, const float* xd, int n, float* xc, uint8_t* valid, float* j_inv, ia_stream_t stream) {
-    IA_REQUIRE(xd && xc && valid && n >= 0);
+    IA_REQUIRE(n >= 0);
     if (n == 0) return IA_OK;
+    IA_REQUIRE(xd && xc && valid);
     SceneDev sd;
-    int rc = make_scene_dev(scene, sd, false);
+    int rc = make_scene_dev(scene, sd, false, false);
     if (rc) return rc;
     broyden_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sd, xd, n, xc, valid, j_inv);
     IA_CHECK_CUDA(cudaPeekAtLastError());
@@ -658,8 +662,9 @@ int ia_broyden(const IaScene* scene, const float* xd, int n, float* xc, uint8_t*
 }
 
 int ia_ngp_forward(const IaScene* scene, const float* x, int n, float* sigma, float* rgb, ia_stream_t stream) {
-    IA_REQUIRE(x && sigma && rgb && n >= 0);
+    IA_REQUIRE(n >= 0);
     if (n == 0) return IA_OK;
+    IA_REQUIRE(x && sigma && rgb);
     IA_REQUIRE(scene && scene->table_h && scene->mlp_h && scene->net_center && scene->net_scale);
     SceneDev sd;
     sd.s = *scene;

@@ -1,0 +1,234 @@
+"""Host-side mirror of instant_avatar/deformers/snarf_deformer.py::SNARFDeformer and
+deformers/fast_snarf/deformer_torch.py::ForwardDeformer (same names, arguments and attributes), backed by
+libia_b200.so.  Per point, `deformer(pts, net, eval_mode)` runs the fused query kernel (13 Broyden root finds ->
+duplicate filter -> hash grid + MLPs -> max over candidates) when `net` is a NeRFNGPNet; any other callable is
+served through the fine-grained Broyden entry point + PyTorch glue (the reference's `model(pts)` contract).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from .. import ops
+from .smpl import SMPL
+
+INIT_BONES = [0, 1, 2, 4, 5, 10, 11, 12, 15, 16, 17, 18, 19]
+
+
+def _opt_get(opt, key, default=None):
+    if opt is None:
+        return default
+    if isinstance(opt, dict):
+        return opt.get(key, default)
+    return getattr(opt, key, default) if not hasattr(opt, "get") else opt.get(key, default)
+
+
+def get_predefined_rest_pose(cano_pose, device="cuda"):
+    """snarf_deformer.py:6-18"""
+    body_pose_t = torch.zeros((1, 69), device=device)
+    if cano_pose.lower() == "da_pose":
+        body_pose_t[:, 2] = torch.pi / 6
+        body_pose_t[:, 5] = -torch.pi / 6
+    elif cano_pose.lower() == "a_pose":
+        body_pose_t[:, 2] = 0.2
+        body_pose_t[:, 5] = -0.2
+        body_pose_t[:, 47] = -0.8
+        body_pose_t[:, 50] = 0.8
+    else:
+        raise ValueError("Unknown cano_pose: {}".format(cano_pose))
+    return body_pose_t
+
+
+def get_bbox_from_smpl(vs, factor=1.2):
+    """snarf_deformer.py:20-31"""
+    assert vs.shape[0] == 1
+    min_vert = vs.min(dim=1).values
+    max_vert = vs.max(dim=1).values
+    c = (max_vert + min_vert) / 2
+    s = (max_vert - min_vert) / 2
+    s = s.max(dim=-1).values * factor
+    return torch.cat([c - s[:, None], c + s[:, None]], dim=0)
+
+
+def knn_points(x: torch.Tensor, verts: torch.Tensor, K: int, chunk: int = 16384):
+    """brute-force K nearest vertices (squared distances), the contract of third_parties/pytorch3d/ops.py:123-206"""
+    d_all, i_all = [], []
+    v2 = (verts * verts).sum(-1)
+    for s in range(0, x.shape[0], chunk):
+        xs = x[s:s + chunk]
+        d2 = (xs * xs).sum(-1, keepdim=True) - 2.0 * xs @ verts.T + v2[None]
+        _, idx = torch.topk(d2, K, dim=1, largest=False)
+        diff = xs[:, None, :] - verts[idx]
+        d_all.append((diff * diff).sum(-1))
+        i_all.append(idx)
+    return torch.cat(d_all), torch.cat(i_all)
+
+
+def query_weights_smpl(x, smpl_verts, smpl_weights, resolution=128):
+    """deformer_torch.py:225-244: inverse-distance blend of the 30 nearest vertices' skinning weights followed by
+    30 Laplacian smoothing passes on the [24, res/4, res, res] grid."""
+    dist, idx = knn_points(x[0], smpl_verts[0], K=30)
+    dist = dist.sqrt().clamp_(0.0001, 1.0)
+    weights = smpl_weights[0, idx]
+    ws = 1.0 / dist
+    ws = ws / ws.sum(-1, keepdim=True)
+    weights = (ws[..., None] * weights).sum(-2)[None]
+    b, c, d, h, w = 1, 24, resolution // 4, resolution, resolution
+    weights = weights.permute(0, 2, 1).reshape(b, c, d, h, w).contiguous()
+    for _ in range(30):
+        mean = (weights[:, :, 2:, 1:-1, 1:-1] + weights[:, :, :-2, 1:-1, 1:-1] + weights[:, :, 1:-1, 2:, 1:-1]
+                + weights[:, :, 1:-1, :-2, 1:-1] + weights[:, :, 1:-1, 1:-1, 2:] + weights[:, :, 1:-1, 1:-1, :-2]) / 6.0
+        weights[:, :, 1:-1, 1:-1, 1:-1] = (weights[:, :, 1:-1, 1:-1, 1:-1] - mean) * 0.7 + mean
+        weights = weights / weights.sum(1, keepdim=True)
+    return weights.detach()
+
+
+class ForwardDeformer(torch.nn.Module):
+    """deformers/fast_snarf/deformer_torch.py::ForwardDeformer -- state holder for the voxelised skinning field."""
+
+    def __init__(self, opt=None, **kwargs):
+        super().__init__()
+        self.opt = opt
+        self.init_bones = INIT_BONES
+        self.global_scale = 1.2
+        self.version = _opt_get(opt, "version", 1)
+        self.field = None
+        self.voxel_d = None
+        self.aabb = None
+
+    def switch_to_explicit(self, resolution=32, smpl_verts=None, smpl_weights=None, use_smpl=True, lbs_voxel=None):
+        """deformer_torch.py:130-202"""
+        self.resolution = resolution
+        device = smpl_verts.device
+        d, h, w = resolution // 4, resolution, resolution
+        self.ratio = h / d
+        gt_bbox = torch.cat([smpl_verts.min(dim=1).values, smpl_verts.max(dim=1).values], dim=0)
+        offset = (gt_bbox[0] + gt_bbox[1])[None, None, :] * 0.5
+        scale = (gt_bbox[1] - gt_bbox[0]).max() / 2 * self.global_scale
+        corner = torch.ones_like(offset[0]) * scale
+        corner[0, 2] /= self.ratio
+        self.bbox = torch.cat([(offset - corner).reshape(1, 3), (offset + corner).reshape(1, 3)], dim=0)
+        self.register_buffer("scale", scale)
+        self.register_buffer("offset", offset)
+        self.register_buffer("offset_kernel", -offset)
+        scale_kernel = torch.zeros_like(offset)
+        scale_kernel[...] = 1.0 / scale
+        scale_kernel[:, :, -1] = scale_kernel[:, :, -1] * self.ratio
+        self.register_buffer("scale_kernel", scale_kernel)
+        if lbs_voxel is None:
+            xr = torch.linspace(-1, 1, steps=w, device=device).view(1, 1, 1, w).expand(1, d, h, w)
+            yr = torch.linspace(-1, 1, steps=h, device=device).view(1, 1, h, 1).expand(1, d, h, w)
+            zr = torch.linspace(-1, 1, steps=d, device=device).view(1, d, 1, 1).expand(1, d, h, w)
+            grid = torch.cat((xr, yr, zr), dim=0).reshape(1, 3, -1).permute(0, 2, 1)
+            g = grid.clone()
+            g[..., -1] /= self.ratio
+            g = g * scale + offset
+            lbs_voxel = query_weights_smpl(g, smpl_verts, smpl_weights, resolution)
+        self.register_buffer("lbs_voxel_final", lbs_voxel.reshape(1, 24, d, h, w).contiguous().float())
+
+    def precompute(self, tfs):
+        """deformer_torch.py:77-83 -> fused precompute kernel (voxel-major field + voxel_d + its AABB)."""
+        self.field, vd, self.aabb = ops.precompute(self.lbs_voxel_final, tfs, self.offset_kernel, self.scale_kernel)
+        self.voxel_d = vd[None]
+
+
+class SNARFDeformer:
+    def __init__(self, model_path=None, gender="neutral", opt=None, smpl_data: dict | None = None) -> None:
+        if smpl_data is None and model_path is not None:
+            model_path = os.path.abspath(model_path)
+        self.body_model = SMPL(model_path, gender=gender, data_struct=smpl_data)
+        self.deformer = ForwardDeformer(opt)
+        self.initialized = False
+        self.opt = opt
+        self.dtype = torch.float32
+
+    def initialize(self, betas, device, lbs_voxel=None):
+        """snarf_deformer.py:41-69"""
+        cano = _opt_get(self.opt, "cano_pose", "A_pose")
+        if isinstance(cano, str):
+            body_pose_t = get_predefined_rest_pose(cano, device=device)
+        else:
+            body_pose_t = torch.zeros((1, 69), device=device)
+            body_pose_t[:, 2] = cano[0]; body_pose_t[:, 5] = cano[1]; body_pose_t[:, 47] = cano[2]; body_pose_t[:, 50] = cano[3]
+        out = self.body_model(betas=betas[:1], body_pose=body_pose_t)
+        self.tfs_inv_t = torch.inverse(out.A.float().detach())
+        self.vs_template = out.vertices
+        self.joints_cano = out.joints
+        self.deformer.device = device
+        self.deformer.switch_to_explicit(resolution=_opt_get(self.opt, "resolution", 128),
+                                         smpl_verts=out.vertices.float().detach(),
+                                         smpl_weights=self.body_model.lbs_weights.clone()[None].detach(),
+                                         use_smpl=True, lbs_voxel=lbs_voxel)
+        self.bbox = get_bbox_from_smpl(out.vertices.detach())
+
+    def prepare_deformer(self, smpl_params):
+        """snarf_deformer.py:71-93"""
+        device = smpl_params["betas"].device
+        if self.body_model.v_template.device != device:
+            self.body_model = self.body_model.to(device)
+        if not self.initialized:
+            self.initialize(smpl_params["betas"], device)
+            self.initialized = True
+        out = self.body_model(betas=smpl_params["betas"], body_pose=smpl_params["body_pose"],
+                              global_orient=smpl_params["global_orient"], transl=smpl_params["transl"])
+        s2w = out.A[:, 0].float()
+        w2s = torch.inverse(s2w)
+        tfs = (w2s[:, None] @ out.A.float() @ self.tfs_inv_t).type(self.dtype)
+        self.deformer.precompute(tfs)
+        self.w2s = w2s
+        self.vertices = (out.vertices @ w2s[:, :3, :3].permute(0, 2, 1)) + w2s[:, None, :3, 3]
+        self.tfs = tfs
+        self.smpl_outputs = out
+        self.smpl_params = smpl_params
+
+    def transform_rays_w2s(self, rays):
+        """snarf_deformer.py:95-103"""
+        w2s = self.w2s
+        rays.o = (rays.o @ w2s[:, :3, :3].permute(0, 2, 1)) + w2s[:, None, :3, 3]
+        rays.d = (rays.d @ w2s[:, :3, :3].permute(0, 2, 1)).to(rays.d)
+        d = torch.norm(rays.o, dim=-1)
+        rays.near = d - 1
+        rays.far = d + 1
+
+    def get_bbox_deformed(self):
+        """snarf_deformer.py:105-107 (computed by the precompute kernel)"""
+        return [self.deformer.aabb[:3], self.deformer.aabb[3:]]
+
+    def scene(self, net, occ_bits=None, occ_aabb=None) -> ops.Scene:
+        """the per-frame read-only state handed to the fused kernels"""
+        table_h, mlp_h = net.half_params()
+        return ops.Scene(field=self.deformer.field, offset_k=self.deformer.offset_kernel.reshape(3).contiguous(),
+                         scale_k=self.deformer.scale_kernel.reshape(3).contiguous(), tfs=self.tfs.reshape(24, 4, 4).contiguous(),
+                         table_h=table_h, mlp_h=mlp_h, net_center=net.center.reshape(3).contiguous().float(),
+                         net_scale=net.scale.reshape(3).contiguous().float(), occ_bits=occ_bits, occ_aabb=occ_aabb)
+
+    def deform(self, pts, eval_mode):
+        """snarf_deformer.py:109-124 via the fine-grained Broyden entry point"""
+        sc = ops.Scene(field=self.deformer.field, offset_k=self.deformer.offset_kernel.reshape(3).contiguous(),
+                       scale_k=self.deformer.scale_kernel.reshape(3).contiguous(), tfs=self.tfs.reshape(24, 4, 4).contiguous())
+        xc, valid, _ = ops.broyden(sc, pts.reshape(-1, 3).float())
+        return xc, valid
+
+    def __call__(self, pts, model, eval_mode=True):
+        from ..models.networks.ngp import NeRFNGPNet
+        pts = pts.reshape(-1, 3).type(self.dtype).contiguous()
+        if isinstance(model, NeRFNGPNet):
+            model.initialize(self.bbox)
+            if eval_mode or not torch.is_grad_enabled() or not model.encoder.params.requires_grad:
+                rgb, sigma = ops.deform_query(self.scene(model), pts, eval_mode)
+                return rgb, sigma
+            from ..autograd import deform_query_train
+            return deform_query_train(self, model, pts)
+        # legacy contract: any callable model(x, d) -> (rgb, sigma)
+        xc, valid = self.deform(pts, eval_mode)
+        rgb_c = torch.zeros_like(xc)
+        sig_c = torch.zeros_like(xc[..., 0]) if eval_mode else -torch.ones_like(xc[..., 0]) * 1e5
+        if valid.any():
+            r, s = model(xc[valid], None)
+            if eval_mode:
+                s = torch.nan_to_num(s, 0, 0, 0); r = torch.nan_to_num(r, 0, 0, 0)
+            rgb_c[valid], sig_c[valid] = r.float(), s.float()
+        sig, idx = torch.max(sig_c, dim=-1)
+        rgb = torch.gather(rgb_c, 1, idx[:, None, None].repeat(1, 1, 3))
+        return rgb.reshape(-1, 3), sig.reshape(-1)

@@ -53,30 +53,32 @@ def pack_occupancy(field_bool: torch.Tensor, bits=None):
 @dataclass
 class Scene:
     """Per-frame read-only state (IaScene) with the tensors that keep it alive."""
-    field: torch.Tensor            # [D,H,W,12]
-    offset_k: torch.Tensor         # [3]
-    scale_k: torch.Tensor          # [3]
-    tfs: torch.Tensor              # [24,4,4]
-    table_h: torch.Tensor
-    mlp_h: torch.Tensor
-    net_center: torch.Tensor
-    net_scale: torch.Tensor
+    field: torch.Tensor | None = None     # [D,H,W,12]
+    offset_k: torch.Tensor | None = None  # [3]
+    scale_k: torch.Tensor | None = None   # [3]
+    tfs: torch.Tensor | None = None       # [24,4,4]
+    table_h: torch.Tensor | None = None
+    mlp_h: torch.Tensor | None = None
+    net_center: torch.Tensor | None = None
+    net_scale: torch.Tensor | None = None
     occ_bits: torch.Tensor | None = None
     occ_aabb: torch.Tensor | None = None   # [6]
     G: int = 64
     _keep: list = dc_field(default_factory=list)
 
     def c_struct(self) -> IaScene:
-        D, H, W, _ = self.field.shape
         s = IaScene()
-        s.field = ptr(self.field, f32).value; s.D, s.H, s.W = D, H, W
-        s.offset_k = ptr(self.offset_k, f32).value; s.scale_k = ptr(self.scale_k, f32).value
-        s.tfs = ptr(self.tfs, f32).value
+        if self.field is not None:
+            D, H, W, _ = self.field.shape
+            s.field = ptr(self.field, f32).value; s.D, s.H, s.W = D, H, W
+        o = lambda t: ptr(t, f32).value if t is not None else None
+        s.offset_k = o(self.offset_k); s.scale_k = o(self.scale_k); s.tfs = o(self.tfs)
         s.occ_bits = ptr(self.occ_bits).value if self.occ_bits is not None else None
         s.G = self.G
         s.occ_aabb = ptr(self.occ_aabb, f32).value if self.occ_aabb is not None else None
-        s.table_h = ptr(self.table_h).value; s.mlp_h = ptr(self.mlp_h).value
-        s.net_center = ptr(self.net_center, f32).value; s.net_scale = ptr(self.net_scale, f32).value
+        s.table_h = ptr(self.table_h).value if self.table_h is not None else None
+        s.mlp_h = ptr(self.mlp_h).value if self.mlp_h is not None else None
+        s.net_center = o(self.net_center); s.net_scale = o(self.net_scale)
         return s
 
 

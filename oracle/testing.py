@@ -1,9 +1,9 @@
 """Builds the synthetic scene with the ORACLE on the CPU and uploads it for the CUDA product
-(tests only: product code never imports oracle/)."""
+(test infrastructure: used by tests/, smoke() and bench.py only; product code never imports oracle/)."""
 import numpy as np
 
-from oracle import render as orender
-from oracle import scene as oscene
+from . import render as orender
+from . import scene as oscene
 
 _CACHE = {}
 

@@ -4,7 +4,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from instantavatar_b200 import ops
 from oracle import scene as oscene
-from tests import scene_util
+from oracle import testing as scene_util
 
 sc = scene_util.oracle_scene(0)
 scene, _ = scene_util.upload(sc)

@@ -6,7 +6,7 @@ from oracle import capi
 from oracle import frame as oframe
 from oracle import render as orender
 from oracle import scene as oscene
-from tests import scene_util
+from oracle import testing as scene_util
 
 pytestmark = pytest.mark.gpu
 
