@@ -39,7 +39,7 @@ typedef struct IaScene {
     const float* offset_k;   /* [3] ForwardDeformer.offset_kernel (deformer_torch.py:154) */
     const float* scale_k;    /* [3] ForwardDeformer.scale_kernel  (deformer_torch.py:155-158) */
     const float* tfs;        /* [24][4][4] bone transforms (snarf_deformer.py:86) */
-    const uint32_t* occ_bits;/* [G*G*G/32] occupancy bitfield, bit index (nx*G+ny)*G+nz (ia_pack_occupancy) */
+    const uint32_t* occ_bits;/* [G*G*G/32 + 8] occupancy bitfield, bit index (nx*G+ny)*G+nz (ia_pack_occupancy) */
     int32_t G;
     const float* occ_aabb;   /* [6] min xyz, max xyz of the occupancy grid (DensityGrid.min_corner/max_corner) */
     const void* table_h;     /* half2[total_entries] hash-grid features (ia_params_to_half) */
@@ -61,6 +61,9 @@ const char* ia_last_error(void);
 /* number of SMs of the current device (grid sizing is a multiple of this) [host result] */
 int ia_sm_count(void);
 
+/* tuning knobs (do not change results): "render_rays_per_warp" in {32,16,8,4} */
+int ia_set_option(const char* name, int value);
+
 /* tiny-cuda-nn HashGrid level table (models/networks/ngp.py:27-37 config). [host] outputs. */
 int ia_hashgrid_layout(uint32_t res[IA_NUM_LEVELS], float scale[IA_NUM_LEVELS], uint32_t size[IA_NUM_LEVELS],
                        uint32_t offset[IA_NUM_LEVELS], uint32_t* total_entries);
@@ -79,7 +82,8 @@ int ia_precompute(const float* voxel_w, const float* tfs, const float* offset_k,
 int ia_params_to_half(const float* enc_params, const float* col_params, void* table_h, void* mlp_h,
                       ia_stream_t stream);
 
-/* bool [G][G][G] (DensityGrid.density_field) -> bitfield */
+/* bool [G][G][G] (DensityGrid.density_field) -> bitfield.  bits must hold G*G*G/32 + 8 words: the 8 trailing
+ * words receive the bounding box of the occupied cells (used for exact empty-space skipping). */
 int ia_pack_occupancy(const uint8_t* field_bool, uint32_t* bits, int G, ia_stream_t stream);
 
 /* Fused eval renderer.  Replaces Raymarcher.render_test (renderers/raymarcher_acc.py:82-138) together with

@@ -20,7 +20,7 @@ IA_NUM_INIT = 13
 IA_MAX_SAMPLES = 256
 
 SYMBOLS = [
-    "ia_abi_version", "ia_last_error", "ia_sm_count", "ia_hashgrid_layout", "ia_precompute", "ia_params_to_half",
+    "ia_abi_version", "ia_last_error", "ia_sm_count", "ia_set_option", "ia_hashgrid_layout", "ia_precompute", "ia_params_to_half",
     "ia_pack_occupancy", "ia_render_fwd", "ia_deform_query", "ia_broyden", "ia_ngp_forward",
 ]
 

@@ -48,6 +48,7 @@ static float filter_threshold() {
     return cf;
 }
 
+static int g_render_rays = 8;  // rays per warp (32 / 16 / 8 / 4), tunable through ia_set_option
 static int g_sm_count = 0;
 static int sm_count() {
     if (!g_sm_count) {
@@ -123,8 +124,39 @@ struct RenderSmem {
     RenderWarpExtra wx[kWarps];
 };
 
-template <int kWarps>
+// Conservative parametric interval of the ray inside the bounding box of the OCCUPIED cells (cell box from
+// ia_pack_occupancy).  Samples are clamped into the grid (raymarcher.cu:49-51), so a bound only constrains the ray
+// when the occupied box does not touch that face of the grid.
+__device__ __forceinline__ void occupied_interval(const FrameConst& fc, const int* __restrict__ cbox, int G, float ox,
+                                                  float oy, float oz, float dx, float dy, float dz, float& t0, float& t1) {
+    t0 = -INFINITY; t1 = INFINITY;
+    const float o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float cell = 1.0f / fc.occ_s[a];
+        float lo = -INFINITY, hi = INFINITY;
+        if (cbox[a] > 0) lo = fc.occ_min[a] + ((float)cbox[a] - 0.5f) * cell;
+        if (cbox[3 + a] < G - 1) hi = fc.occ_min[a] + ((float)cbox[3 + a] + 1.5f) * cell;
+        if (fabsf(d[a]) < 1e-12f) {
+            if (o[a] < lo || o[a] > hi) { t0 = INFINITY; t1 = -INFINITY; }
+        } else {
+            const float inv = 1.0f / d[a];
+            float ta = (lo - o[a]) * inv, tb = (hi - o[a]) * inv;
+            if (ta > tb) { const float tmp = ta; ta = tb; tb = tmp; }
+            if (ta == ta) t0 = fmaxf(t0, ta);
+            if (tb == tb) t1 = fminf(t1, tb);
+        }
+    }
+}
+
+// kRays rays per warp, each marched kDepth = 32/kRays steps ahead (lane = depth * kRays + ray): the batch of 32
+// samples a warp evaluates stays spatially coherent (neighbouring pixels x consecutive steps) while the number of
+// independent work units grows by kDepth -- there are fewer hit rays in a 512^2 frame than resident lanes.
+template <int kWarps, int kRays>
 __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid_constant__ RenderArgs a) {
+    constexpr int kDepth = 32 / kRays;
+    constexpr int kTileW = kRays == 32 ? 8 : (kRays >= 8 ? 4 : 2);
+    constexpr int kTileH = kRays / kTileW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RenderSmem<kWarps>& sm = *reinterpret_cast<RenderSmem<kWarps>*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -151,10 +183,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
     WarpScratch<false>& ws = sm.ws[warp];
     RenderWarpExtra& wx = sm.wx[warp];
     const FrameConst& fc = sm.fc;
+    const int* cbox = reinterpret_cast<const int*>(a.sd.s.occ_bits + G * G * G / 32);  // occupied-cell box
 
-    const bool tiled = a.image_width > 0 && (a.image_width % 8) == 0 && (a.n_rays % (a.image_width * 4)) == 0;
-    const int n_tiles = (a.n_rays + 31) / 32;
-    const int tiles_x = tiled ? a.image_width / 8 : 1;
+    const bool tiled = a.image_width > 0 && (a.image_width % kTileW) == 0 && (a.n_rays % (a.image_width * kTileH)) == 0;
+    const int n_tiles = (a.n_rays + kRays - 1) / kRays;
+    const int tiles_x = tiled ? a.image_width / kTileW : 1;
+    const int rl = lane % kRays, jl = lane / kRays;
     unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_hit = 0;
 
     for (;;) {
@@ -165,25 +199,39 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
         int ray;
         if (tiled) {
             const int ty = tile / tiles_x, tx = tile % tiles_x;
-            ray = (ty * 4 + (lane >> 3)) * a.image_width + tx * 8 + (lane & 7);
+            ray = (ty * kTileH + rl / kTileW) * a.image_width + tx * kTileW + (rl % kTileW);
         } else {
-            ray = tile * 32 + lane;
+            ray = tile * kRays + rl;
         }
         const bool has = ray < a.n_rays;
         float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, t = 0, far = 0, dt = 0;
+        int k = jl, kend = -1;
         if (has) {
             ox = a.rays_o[ray * 3]; oy = a.rays_o[ray * 3 + 1]; oz = a.rays_o[ray * 3 + 2];
             dx = a.rays_d[ray * 3]; dy = a.rays_d[ray * 3 + 1]; dz = a.rays_d[ray * 3 + 2];
             t = a.near[ray]; far = a.far[ray];
             dt = (far - t) / (float)IA_MAX_SAMPLES;  // raymarcher_acc.py:102
+            // empty-space skip: steps outside [kbeg, kend] cannot hit an occupied cell
+            float t0, t1;
+            occupied_interval(fc, cbox, G, ox, oy, oz, dx, dy, dz, t0, t1);
+            if (cbox[6] != 0 && t0 <= t1 && dt > 0.f) {
+                const float k0f = floorf((fmaxf(t0, t) - t) / dt) - 2.f, k1f = ceilf((fminf(t1, far) - t) / dt) + 2.f;
+                int kbeg = (int)fminf(fmaxf(k0f, 0.f), 1024.f);
+                kend = (int)fminf(fmaxf(k1f, -1.f), 1024.f);
+                kbeg = (kbeg / kDepth) * kDepth;
+                k = kbeg + jl;
+            }
+            // t_k is the k-fold sequential sum near + dt + dt + ... exactly as the reference accumulates it
+            for (int i = 0; i < k; i++) t += dt;
         }
-        float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Dp = 0.f;
+        float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Dp = 0.f;  // ray state lives in lanes < kRays
         int nocc = 0;
         int qhead = 0, qcount = 0;
         for (;;) {
             // ---- scan: march until 32 occupied samples are queued (raymarcher.cu:13-73) ----
+            const bool dead = __shfl_sync(kFull, !(T > 1e-4f), rl);
             while (qcount < 32) {
-                const bool act = has && t < far && T > 1e-4f && nocc < IA_MAX_SAMPLES;
+                const bool act = has && !dead && k <= kend && t < far;
                 if (!__any_sync(kFull, act)) break;
                 bool occ = false;
                 float x = 0, y = 0, z = 0;
@@ -198,29 +246,35 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
                 const unsigned m = __ballot_sync(kFull, occ);
                 if (occ) {
                     const int slot = (qhead + qcount + __popc(m & ((1u << lane) - 1u))) & 63;
-                    wx.qx[slot] = x; wx.qy[slot] = y; wx.qz[slot] = z; wx.qt[slot] = t; wx.qowner[slot] = lane;
+                    wx.qx[slot] = x; wx.qy[slot] = y; wx.qz[slot] = z; wx.qt[slot] = t; wx.qowner[slot] = rl;
                     nocc++;
                 }
                 qcount += __popc(m);
-                if (act) t += dt;
+                if (act) {
+#pragma unroll
+                    for (int i = 0; i < kDepth; i++) t += dt;
+                    k += kDepth;
+                }
             }
             if (qcount == 0) break;
             __syncwarp();
-            // ---- pop a batch of up to 32 samples ----
+            // ---- pop a batch of up to 32 samples; entries of rays that terminated meanwhile are dropped ----
             const int n = min(qcount, 32);
-            const bool sact = lane < n;
             const int slot = (qhead + lane) & 63;
             float sx = 0, sy = 0, sz = 0, stt = 0;
-            int sown = -1;
-            if (sact) { sx = wx.qx[slot]; sy = wx.qy[slot]; sz = wx.qz[slot]; stt = wx.qt[slot]; sown = wx.qowner[slot]; }
+            int sown = 0;
+            if (lane < n) { sx = wx.qx[slot]; sy = wx.qy[slot]; sz = wx.qz[slot]; stt = wx.qt[slot]; sown = wx.qowner[slot]; }
+            const bool owner_dead = __shfl_sync(kFull, !(T > 1e-4f), sown);
+            const bool sact = lane < n && !owner_dead;
             qhead = (qhead + n) & 63;
             qcount -= n;
+            if (!__any_sync(kFull, sact)) continue;
             st_samples += sact ? 1u : 0u;
             SampleOut so;
             warp_eval_samples<false>(ctx, ws, sact, sx, sy, sz, true, lane, so, st_gather, st_roots);
             // ---- composite in sample order (raymarcher.cu:200-235) ----
             ws.res[lane][0] = so.sigma; ws.res[lane][1] = so.r; ws.res[lane][2] = so.g; ws.res[lane][3] = so.b;
-            wx.bt[lane] = stt; wx.bo[lane] = sown;
+            wx.bt[lane] = stt; wx.bo[lane] = sact ? sown : -1;
             __syncwarp();
             for (int i = 0; i < n; i++) {
                 if (wx.bo[i] == lane && T > 1e-4f) {
@@ -238,7 +292,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
             }
             __syncwarp();
         }
-        if (has) {
+        // samples marched per ray = sum over its kDepth lanes
+#pragma unroll
+        for (int o = kRays; o < 32; o <<= 1) nocc += __shfl_xor_sync(kFull, nocc, o);
+        if (has && jl == 0) {
             float b0 = 1.f, b1 = 1.f, b2 = 1.f;  // raymarcher_acc.py:128-132
             if (a.bg) { b0 = a.bg[ray * 3]; b1 = a.bg[ray * 3 + 1]; b2 = a.bg[ray * 3 + 2]; }
             a.rgb[ray * 3 + 0] = Cr + T * b0;
@@ -511,7 +568,9 @@ __global__ void params_to_half_kernel(const float* __restrict__ enc, const float
     }
 }
 
-__global__ void pack_occupancy_kernel(const uint8_t* __restrict__ field, uint32_t* __restrict__ bits, int n_words) {
+// bool [G][G][G] -> bit field (+ 8 trailing words: occupied-cell box min xyz, max xyz, any, pad; the caller
+// initialises them to {G,G,G,-1,-1,-1,0,0})
+__global__ void pack_occupancy_kernel(const uint8_t* __restrict__ field, uint32_t* __restrict__ bits, int n_words, int G) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     uint32_t v = 0;
@@ -519,6 +578,15 @@ __global__ void pack_occupancy_kernel(const uint8_t* __restrict__ field, uint32_
 #pragma unroll
     for (int b = 0; b < 32; b++) v |= (p[b] ? 1u : 0u) << b;
     bits[w] = v;
+    if (v) {
+        int* box = reinterpret_cast<int*>(bits + n_words);
+        const int cell0 = w * 32;
+        const int nx = cell0 / (G * G), ny = (cell0 / G) % G, nz0 = cell0 % G;
+        atomicMin(&box[0], nx); atomicMax(&box[3], nx);
+        atomicMin(&box[1], ny); atomicMax(&box[4], ny);
+        atomicMin(&box[2], nz0 + (__ffs(v) - 1)); atomicMax(&box[5], nz0 + (31 - __clz(v)));
+        box[6] = 1;
+    }
 }
 
 // ================================================================================================
@@ -544,6 +612,16 @@ extern "C" {
 int ia_abi_version(void) { return IA_ABI_VERSION; }
 const char* ia_last_error(void) { return g_err; }
 int ia_sm_count(void) { return sm_count(); }
+
+int ia_set_option(const char* name, int value) {
+    IA_REQUIRE(name != nullptr);
+    if (!strcmp(name, "render_rays_per_warp")) {
+        IA_REQUIRE(value == 32 || value == 16 || value == 8 || value == 4);
+        g_render_rays = value;
+        return IA_OK;
+    }
+    return set_err(IA_EINVAL, "unknown option: %s", name);
+}
 
 int ia_hashgrid_layout(uint32_t res[IA_NUM_LEVELS], float scale[IA_NUM_LEVELS], uint32_t size[IA_NUM_LEVELS],
                        uint32_t offset[IA_NUM_LEVELS], uint32_t* total_entries) {
@@ -583,9 +661,11 @@ int ia_params_to_half(const float* enc_params, const float* col_params, void* ta
 }
 
 int ia_pack_occupancy(const uint8_t* field_bool, uint32_t* bits, int G, ia_stream_t stream) {
-    IA_REQUIRE(field_bool && bits && G > 0 && (G * G * G) % 32 == 0);
+    IA_REQUIRE(field_bool && bits && G >= 32 && G % 32 == 0);
     const int n_words = G * G * G / 32;
-    pack_occupancy_kernel<<<(n_words + 255) / 256, 256, 0, (cudaStream_t)stream>>>(field_bool, bits, n_words);
+    const int init[8] = {G, G, G, -1, -1, -1, 0, 0};
+    IA_CHECK_CUDA(cudaMemcpyAsync(bits + n_words, init, sizeof(init), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    pack_occupancy_kernel<<<(n_words + 255) / 256, 256, 0, (cudaStream_t)stream>>>(field_bool, bits, n_words, G);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }
@@ -612,14 +692,23 @@ int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d
     const size_t smem = sizeof(RenderSmem<kRenderWarps>);
     static bool attr_set = false;
     if (!attr_set) {
-        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const int n_tiles = (n_rays + 31) / 32;
+    const int rpw = g_render_rays;
+    const int n_tiles = (n_rays + rpw - 1) / rpw;
     int grid = sm_count();
     if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
     grid = min(grid, (n_tiles + kRenderWarps - 1) / kRenderWarps);
-    render_fwd_kernel<kRenderWarps><<<grid, kRenderWarps * 32, smem, st>>>(a);
+    switch (rpw) {
+        case 32: render_fwd_kernel<kRenderWarps, 32><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
+        case 16: render_fwd_kernel<kRenderWarps, 16><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
+        case 4: render_fwd_kernel<kRenderWarps, 4><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
+        default: render_fwd_kernel<kRenderWarps, 8><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
+    }
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

@@ -45,7 +45,7 @@ def pack_occupancy(field_bool: torch.Tensor, bits=None):
     G = field_bool.shape[0]
     fb = field_bool.contiguous().view(torch.uint8) if field_bool.dtype == torch.bool else field_bool.contiguous()
     if bits is None:
-        bits = torch.empty(G * G * G // 32, device=fb.device, dtype=torch.int32)
+        bits = torch.empty(G * G * G // 32 + 8, device=fb.device, dtype=torch.int32)
     check(lib().ia_pack_occupancy(ptr(fb), ptr(bits), C.c_int(G), stream()))
     return bits
 
@@ -80,6 +80,10 @@ class Scene:
         s.mlp_h = ptr(self.mlp_h).value if self.mlp_h is not None else None
         s.net_center = o(self.net_center); s.net_scale = o(self.net_scale)
         return s
+
+
+def set_option(name: str, value: int):
+    check(lib().ia_set_option(name.encode(), C.c_int(value)))
 
 
 def new_stats(device) -> torch.Tensor:

@@ -1,0 +1,92 @@
+"""Host-side mirror of instant_avatar/renderers/raymarcher_acc.py::Raymarcher.
+
+Same constructor, `initialize(N)`, `__call__(rays, model, eval_mode, noise, bg_color)` and result dictionary as the
+reference.  When `model` is bound to a SNARFDeformer + NeRFNGPNet pair (a `BoundModel`, or the reference's
+`lambda x, _: self.deformer(x, self.net_coarse, eval_mode)` closure) the whole per-ray path -- occupancy-grid march,
+Broyden root finding, hash grid + MLPs, compositing -- runs as one fused kernel (`ia_render_fwd`, and the
+`ia_train_fwd/bwd` pair for training) instead of the reference's host-synchronous window loop.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from ..models.structures.density_grid import DensityGrid
+
+
+class BoundModel:
+    """`model(x, d)` callable carrying the deformer/network it is bound to (what DNeRFModel.forward builds)."""
+
+    def __init__(self, deformer, net, eval_mode=True):
+        self.deformer, self.net, self.eval_mode = deformer, net, eval_mode
+
+    def __call__(self, x, _=None):
+        return self.deformer(x, self.net, self.eval_mode)
+
+
+def _unwrap(model):
+    """find (deformer, net) behind a model callable; None if it is a foreign model"""
+    if hasattr(model, "deformer") and hasattr(model, "net"):
+        return model.deformer, model.net
+    for cell in getattr(model, "__closure__", None) or ():
+        obj = cell.cell_contents
+        if hasattr(obj, "deformer") and hasattr(obj, "net_coarse"):
+            return obj.deformer, obj.net_coarse
+    return None
+
+
+class Raymarcher(torch.nn.Module):
+    def __init__(self, MAX_SAMPLES: int = 256, MAX_BATCH_SIZE: int = 291600, smpl_init: bool = False, device="cuda") -> None:
+        super().__init__()
+        if MAX_SAMPLES != 256:
+            raise ValueError("the fused kernels are built for MAX_SAMPLES = 256 (confs/renderer/raymarcher_acc.yaml)")
+        self.MAX_SAMPLES = MAX_SAMPLES
+        self.MAX_BATCH_SIZE = MAX_BATCH_SIZE
+        self.aabb = torch.tensor([[-1.25, -1.55, -1.25], [1.25, 0.95, 1.25]]).float().to(device)
+        self.density_grid_test = DensityGrid(64, device=device)
+        self.smpl_init = smpl_init
+        self.idx = 0
+        self.image_width = 0  # optional hint: rays form a row-major image of this width
+
+    def initialize(self, N):
+        dev = self.aabb.device
+        self.density_grid_train_all = [DensityGrid(64, self.aabb, device=dev)]
+
+    @property
+    def density_grid_train(self):
+        return self.density_grid_train_all[min(self.idx, len(self.density_grid_train_all) - 1)]
+
+    def __call__(self, rays, model, eval_mode=True, noise=0, bg_color=None):
+        if eval_mode:
+            return self.render_test(rays, model, bg_color)
+        return self.render_train(rays, model, noise, bg_color)
+
+    @torch.no_grad()
+    def render_test(self, rays, model, bg_color, stats=None):
+        bound = _unwrap(model)
+        if bound is None:
+            raise NotImplementedError("Raymarcher.render_test: only SNARFDeformer + NeRFNGPNet models are fused")
+        deformer, net = bound
+        net.initialize(deformer.bbox)
+        grid = self.density_grid_test
+        scene = deformer.scene(net, grid.occupancy_bits(), grid.aabb6())
+        rays_o = rays.o.reshape(-1, 3).float().contiguous()
+        rays_d = rays.d.reshape(-1, 3).float().contiguous()
+        near = rays.near.reshape(-1).float().contiguous()
+        far = rays.far.reshape(-1).float().contiguous()
+        bg = bg_color.reshape(-1, 3).float().contiguous() if bg_color is not None else None
+        out = ops.render_fwd(scene, rays_o, rays_d, near, far, bg, self.image_width, stats)
+        return {
+            "rgb_coarse": out["rgb"].reshape(rays.o.shape),
+            "depth_coarse": out["depth"].reshape(rays.near.shape),
+            "alpha_coarse": out["alpha"].reshape(rays.near.shape),
+            "counter_coarse": out["counter"].reshape(rays.near.shape),
+        }
+
+    def render_train(self, rays, model, noise, bg_color, jitter=None, noise_tensor=None):
+        bound = _unwrap(model)
+        if bound is None:
+            raise NotImplementedError("Raymarcher.render_train: only SNARFDeformer + NeRFNGPNet models are fused")
+        from ..autograd import render_train_fused
+        deformer, net = bound
+        return render_train_fused(self, deformer, net, rays, noise, bg_color, jitter, noise_tensor)

@@ -13,7 +13,9 @@ o, d, near, far = oscene.camera_rays(fr, 512, 512)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 o, d, near, far = t(o), t(d), t(near), t(far)
 res = {}
-for width in (512, 0):
+for rpw in (32, 16, 8, 4):
+  ops.set_option("render_rays_per_warp", rpw)
+  for width in (512, 0):
     stats = ops.new_stats("cuda")
     out = ops.render_fwd(scene, o, d, near, far, None, width, stats)
     torch.cuda.synchronize()
@@ -23,8 +25,9 @@ for width in (512, 0):
     for i in range(20):
         ev0.record(); ops.render_fwd(scene, o, d, near, far, None, width, None, out); ev1.record(); torch.cuda.synchronize()
         ts.append(ev0.elapsed_time(ev1))
-    res[f"width{width}"] = {"ms_median": float(np.median(ts)), "ms_min": float(min(ts)), "stats": st,
-                            "rays_per_s": 262144 / (np.median(ts) * 1e-3), "alpha_sum": float(out["alpha"].sum())}
-    print(width, res[f"width{width}"])
+    key = f"rpw{rpw}_width{width}"
+    res[key] = {"ms_median": float(np.median(ts)), "ms_min": float(min(ts)), "stats": st,
+                "rays_per_s": 262144 / (np.median(ts) * 1e-3), "alpha_sum": float(out["alpha"].sum())}
+    print(key, res[key])
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/probe.json", "w"), indent=1)
