@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of a 512x512 avatar render (BASELINE.json metric) on N B200s.
+
+A "step" is one complete frame of the reference's `render_image_fast` (DNeRF.py:72-97) on the synthetic
+PeopleSnapshot-shaped scene: SMPL forward -> bone transforms -> skinning-transform field ->
+5-pass occupancy-grid initialisation (+ connected component) -> 262 144 rays through the fused march / Broyden /
+hash-grid / MLP / compositing kernel.
+
+  value : rays/s with the frame's inputs (rays, SMPL pose) resident in HBM.
+  e2e   : the same frame through the public API with HOST buffers: pinned rays + pose -> device, render, RGBA -> host.
+  --impl reference : the CPU oracle (C port of the reference's kernels + numpy host loop, all host threads) on the same
+                     frame -- the reference's own GPU path needs tiny-cuda-nn, which cannot be built.
+N > 1: one process per GPU (torchrun), each rank renders whole frames of different poses; no data-path collective
+("scaling": "weak").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 512
+N_RAYS = H * W
+FRAMES = [0, 20, 57, 100]
+METRIC = "rays/sec at 512x512 render"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rays-per-warp", type=int, default=0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# scene
+# ------------------------------------------------------------------------------------------------
+def host_batch(frame: int):
+    from instantavatar_b200 import synthetic
+    pose = synthetic.load_pose(frame)
+    o, d = synthetic.demo_camera_rays(H, W)
+    dist = np.linalg.norm(pose["transl"], axis=-1).astype(np.float32)
+    near = np.full((1, N_RAYS), dist[0] - 1, np.float32)  # peoplesnapshot dataset convention; overridden by w2s
+    far = np.full((1, N_RAYS), dist[0] + 1, np.float32)
+    return {"rays_o": o[None], "rays_d": d[None], "near": near, "far": far, **pose}
+
+
+def build_model(device, frame: int):
+    import torch
+    from instantavatar_b200 import synthetic
+    from instantavatar_b200.models.dnerf import DNeRFModel
+    model = DNeRFModel(smpl_data=synthetic.smpl_dict_cached(0), device=device).eval()
+    hb = host_batch(frame)
+    batch = {k: torch.from_numpy(v).to(device) for k, v in hb.items()}
+    model.deformer.prepare_deformer(batch)  # subject initialisation (KNN skinning-weight voxelisation etc.), untimed
+    model.net_coarse.initialize(model.deformer.bbox)
+    bbox = model.deformer.bbox.cpu().numpy().astype(np.float64)
+    c, s = (bbox[0] + bbox[1]) / 2, bbox[1] - bbox[0]
+    enc, col = synthetic.analytic_avatar_params(model.deformer.joints_cano[0].cpu().numpy(), c, s)
+    model.net_coarse.load_flat_params(torch.from_numpy(enc).to(device), torch.from_numpy(col).to(device))
+    return model, hb, batch
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle frame (cpu_baseline leg and --impl reference): the only place bench.py executes oracle/
+# ------------------------------------------------------------------------------------------------
+class CpuFrame:
+    def __init__(self, frame: int):
+        from oracle import capi, scene as oscene
+        from instantavatar_b200 import synthetic
+        self.capi = capi
+        self.subj = oscene.build_subject()
+        self.net = oscene.build_net(self.subj)
+        self.pose = synthetic.load_pose(frame)
+        self.threads = capi.num_threads()
+
+    def step(self):
+        from oracle import render as orender, scene as oscene
+        fr = self.subj.prepare_frame(self.pose)
+        occ, _, _ = oscene.build_occupancy(self.subj, fr, self.net)
+        o, d, near, far = oscene.camera_rays(fr, H, W)
+        out = orender.render_test(o, d, near, far, occ, fr["bbox_deformed"][0], fr["bbox_deformed"][1],
+                                  lambda p: orender.deform_query(p, fr, self.subj, self.net, True))
+        return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cf = CpuFrame(FRAMES[0])
+    for _ in range(min(args.warmup, 1)):
+        cf.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cf.step()
+    dt = time.perf_counter() - t0
+    v = N_RAYS * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "male-3-casual-shaped synthetic frame, 512x512 rays, full render_image_fast on host cores"},
+            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cf.threads, "kind": "port",
+                             "sample": "complete 512x512 frame per step (prep + 5-pass occupancy init + march), C oracle with OpenMP"},
+            "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from instantavatar_b200 import _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if args.rays_per_warp:
+        ops.set_option("render_rays_per_warp", args.rays_per_warp)
+
+    frame = FRAMES[rank % len(FRAMES)]
+    model, hb, batch = build_model(device, frame)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in hb.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    out_host = torch.empty((N_RAYS, 4), dtype=torch.float32).pin_memory()
+    d2h_bytes = out_host.numel() * 4
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def step_resident():
+        return model.render_image_fast(dict(batch), (H, W))
+
+    def step_e2e():
+        b = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
+        rgb, depth, alpha, counter = model.render_image_fast(b, (H, W))
+        out_host[:, :3].copy_(rgb.reshape(-1, 3), non_blocking=True)
+        out_host[:, 3].copy_(alpha.reshape(-1), non_blocking=True)
+        return rgb
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.zero_()  # L2 flush between timed iterations (outside the event bracket)
+            a.record(); fn(); b.record()
+        barrier()
+        ms = [a.elapsed_time(b) for a, b in ev]
+        tot = torch.tensor([sum(ms)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()), ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.LAUNCHES = 0
+    total_ms, per = timed(step_resident, args.steps, max(args.warmup, 3))
+    launches = getattr(_lib, "LAUNCHES", 0)
+    e2e_ms, _ = timed(step_e2e, args.steps, 3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- kernel-only timings + work counters for the roofline of the dominant kernel ----
+    rays = model.renderer
+    stats = ops.new_stats(device)
+    from instantavatar_b200.models.dnerf import Rays
+    from instantavatar_b200.renderers.raymarcher_acc import BoundModel
+    r = Rays(o=batch["rays_o"].clone(), d=batch["rays_d"].clone(), near=batch["near"].clone(), far=batch["far"].clone())
+    model.deformer.transform_rays_w2s(r)
+    bm = BoundModel(model.deformer, model.net_coarse, True)
+    rays.image_width = W
+    rays.render_test(r, bm, None, stats)
+    torch.cuda.synchronize()
+    st = ops.stats_dict(stats)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for a, b in kev:
+        flush.zero_()
+        a.record(); rays.render_test(r, bm, None); b.record()
+    torch.cuda.synchronize()
+    k_ms = float(np.median([a.elapsed_time(b) for a, b in kev]))
+    # occupancy-init point queries (5 x 64^3 points)
+    grid = rays.density_grid_test
+    qev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for a, b in qev:
+        flush.zero_()
+        a.record(); grid.initialize(model.deformer, model.net_coarse); b.record()
+    torch.cuda.synchronize()
+    occ_ms = float(np.median([a.elapsed_time(b) for a, b in qev]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    field_bytes = model.deformer.deformer.field.numel() * 4
+    table_bytes = 6513496 * 4
+    # R*(24+16) + gathers*384 + P*512 + one compulsory read of the tables
+    algo_bytes = N_RAYS * 40 + st["gathers"] * 384 + st["net_evals"] * 512 + field_bytes + table_bytes + 32768 + 22016
+    achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "render_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    value = world * N_RAYS * args.steps / (total_ms * 1e-3)
+    e2e = world * N_RAYS * args.steps / (e2e_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 geometry + f16 hash-grid/MLP (fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": "male-3-casual-shaped synthetic avatar, one 512x512 frame per step per GPU "
+                               "(SMPL prep + 5-pass occupancy init + fused render), frames of different poses per rank",
+                   "rays_per_step_per_gpu": N_RAYS, "l2_flush_between_steps": True,
+                   "breakdown_ms": {"fused_render_kernel": k_ms, "occupancy_init": occ_ms,
+                                    "frame_total": total_ms / args.steps},
+                   "work_per_frame": st},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "render_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
+                     "algorithmic_bytes_per_launch": algo_bytes,
+                     "note": "no-reuse gather model (SURVEY.md 8d): most gathers are served by L1/L2, so frac can exceed 1; "
+                             "traffic = measured DRAM bytes (ncu)"},
+    }
+    if not args.no_cpu_baseline:
+        cf = CpuFrame(frame)
+        cf.step()
+        t0 = time.perf_counter(); n = 2
+        for _ in range(n):
+            cf.step()
+        dt = (time.perf_counter() - t0) / n
+        line["cpu_baseline"] = {"value": N_RAYS / dt, "unit": "rays/s", "cores": cf.threads, "kind": "port",
+                                "sample": f"{n} complete 512x512 frames (prep + occupancy init + march) on the C/numpy oracle, OpenMP"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

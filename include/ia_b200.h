@@ -86,6 +86,13 @@ int ia_params_to_half(const float* enc_params, const float* col_params, void* ta
  * words receive the bounding box of the occupied cells (used for exact empty-space skipping). */
 int ia_pack_occupancy(const uint8_t* field_bool, uint32_t* bits, int G, ia_stream_t stream);
 
+/* Occupancy-grid post-processing on the device: density [G][G][G] (already EMA'd / max-merged by the caller) ->
+ * 1-exp(-0.01 d), 3x3x3 max-pool, > min(mean, 0.01), largest 26-connected component.  Replaces
+ * models/structures/density_grid.py:78-85 / :104-110 incl. max_connected_component (:118-125).
+ * field_out bool [G][G][G] (nullable), bits_out [G*G*G/32 + 8]; workspace >= 12*G^3 + 64 bytes. */
+int ia_occupancy_build(const float* density, int G, uint8_t* field_out, uint32_t* bits_out, void* workspace,
+                       size_t workspace_bytes, ia_stream_t stream);
+
 /* Fused eval renderer.  Replaces Raymarcher.render_test (renderers/raymarcher_acc.py:82-138) together with
  * raymarch_test / composite_test (renderers/cuda/raymarcher.cpp:16-29,65-75), SNARFDeformer.deform_test
  * (deformers/snarf_deformer.py:126-141), fuse_broyden + filter (fuse_cuda.cpp:14-25, filter.cpp:12-18) and

@@ -21,7 +21,7 @@ IA_MAX_SAMPLES = 256
 
 SYMBOLS = [
     "ia_abi_version", "ia_last_error", "ia_sm_count", "ia_set_option", "ia_hashgrid_layout", "ia_precompute", "ia_params_to_half",
-    "ia_pack_occupancy", "ia_render_fwd", "ia_deform_query", "ia_broyden", "ia_ngp_forward",
+    "ia_pack_occupancy", "ia_occupancy_build", "ia_render_fwd", "ia_deform_query", "ia_broyden", "ia_ngp_forward",
 ]
 
 
@@ -40,6 +40,12 @@ class IaStats(C.Structure):
 
 
 _lib = None
+LAUNCHES = 0  # kernels of libia_b200.so launched through ops.py (bench.py reports it)
+
+
+def count(n: int):
+    global LAUNCHES
+    LAUNCHES += n
 
 
 def lib():

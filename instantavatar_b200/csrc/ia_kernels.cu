@@ -8,23 +8,10 @@
 
 using namespace ia;
 
-// ================================================================================================
-// error plumbing
-// ================================================================================================
+#include "ia_host.h"
+
 static thread_local char g_err[512] = "";
-static int set_err(int code, const char* fmt, const char* detail = "") {
-    snprintf(g_err, sizeof(g_err), fmt, detail);
-    return code;
-}
-#define IA_CHECK_CUDA(expr)                                                            \
-    do {                                                                               \
-        cudaError_t _e = (expr);                                                       \
-        if (_e != cudaSuccess) return set_err(IA_ECUDA, #expr ": %s", cudaGetErrorString(_e)); \
-    } while (0)
-#define IA_REQUIRE(cond)                                                    \
-    do {                                                                    \
-        if (!(cond)) return set_err(IA_EINVAL, "invalid argument: %s", #cond); \
-    } while (0)
+char* ia_err_buf() { return g_err; }
 
 __constant__ int c_init_bones[kNumInit] = {0, 1, 2, 4, 5, 10, 11, 12, 15, 16, 17, 18, 19};
 
@@ -568,6 +555,11 @@ __global__ void params_to_half_kernel(const float* __restrict__ enc, const float
     }
 }
 
+__global__ void pack_init_box_kernel(uint32_t* bits, int n_words, int G) {
+    int* box = reinterpret_cast<int*>(bits + n_words);
+    if (threadIdx.x < 8) box[threadIdx.x] = threadIdx.x < 3 ? G : (threadIdx.x < 6 ? -1 : 0);
+}
+
 // bool [G][G][G] -> bit field (+ 8 trailing words: occupied-cell box min xyz, max xyz, any, pad; the caller
 // initialises them to {G,G,G,-1,-1,-1,0,0})
 __global__ void pack_occupancy_kernel(const uint8_t* __restrict__ field, uint32_t* __restrict__ bits, int n_words, int G) {
@@ -663,8 +655,7 @@ int ia_params_to_half(const float* enc_params, const float* col_params, void* ta
 int ia_pack_occupancy(const uint8_t* field_bool, uint32_t* bits, int G, ia_stream_t stream) {
     IA_REQUIRE(field_bool && bits && G >= 32 && G % 32 == 0);
     const int n_words = G * G * G / 32;
-    const int init[8] = {G, G, G, -1, -1, -1, 0, 0};
-    IA_CHECK_CUDA(cudaMemcpyAsync(bits + n_words, init, sizeof(init), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    pack_init_box_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(bits, n_words, G);
     pack_occupancy_kernel<<<(n_words + 255) / 256, 256, 0, (cudaStream_t)stream>>>(field_bool, bits, n_words, G);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;

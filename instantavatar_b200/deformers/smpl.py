@@ -62,8 +62,13 @@ class SMPL(nn.Module):
         self.register_buffer("parents", torch.tensor(parents))
         self.register_buffer("lbs_weights", torch.tensor(g("weights"), dtype=dtype))
         self.register_buffer("faces_tensor", torch.tensor(g("f").astype(np.int64)))
-        self._levels = _chain_levels(parents)
-        self._parents_np = parents
+        # kinematic-chain levels as device index tensors (no per-frame host->device index uploads)
+        self._n_levels = 0
+        for lv in _chain_levels(parents):
+            self.register_buffer(f"_lvl_idx{self._n_levels}", torch.tensor(lv), persistent=False)
+            self.register_buffer(f"_lvl_par{self._n_levels}", torch.tensor(parents[lv]), persistent=False)
+            self._n_levels += 1
+        self.register_buffer("_par1", torch.tensor(parents[1:]), persistent=False)
 
     @staticmethod
     def rodrigues(rot_vecs: torch.Tensor) -> torch.Tensor:
@@ -91,15 +96,16 @@ class SMPL(nn.Module):
         v_posed = v_shaped + torch.matmul(pose_feature, self.posedirs).view(B, -1, 3)
         # kinematic chain, level by level
         rel = J.clone()
-        rel[:, 1:] = J[:, 1:] - J[:, self._parents_np[1:]]
+        rel[:, 1:] = J[:, 1:] - J[:, self._par1]
         tm = torch.zeros((B, 24, 4, 4), device=dev, dtype=dt)
         tm[:, :, :3, :3] = rot
         tm[:, :, :3, 3] = rel
         tm[:, :, 3, 3] = 1
         chain = torch.empty_like(tm)
         chain[:, 0] = tm[:, 0]
-        for idx in self._levels:
-            chain[:, idx] = torch.matmul(chain[:, self._parents_np[idx]], tm[:, idx])
+        for l in range(self._n_levels):
+            idx, par = getattr(self, f"_lvl_idx{l}"), getattr(self, f"_lvl_par{l}")
+            chain[:, idx] = torch.matmul(chain[:, par], tm[:, idx])
         posed_joints = chain[:, :, :3, 3]
         jh = torch.cat([J, torch.zeros((B, 24, 1), device=dev, dtype=dt)], dim=2)[..., None]
         A = chain.clone()

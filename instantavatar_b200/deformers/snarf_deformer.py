@@ -173,7 +173,7 @@ class SNARFDeformer:
         out = self.body_model(betas=smpl_params["betas"], body_pose=smpl_params["body_pose"],
                               global_orient=smpl_params["global_orient"], transl=smpl_params["transl"])
         s2w = out.A[:, 0].float()
-        w2s = torch.inverse(s2w)
+        w2s = torch.linalg.inv_ex(s2w).inverse  # torch.inverse without the host-synchronising error check
         tfs = (w2s[:, None] @ out.A.float() @ self.tfs_inv_t).type(self.dtype)
         self.deformer.precompute(tfs)
         self.w2s = w2s

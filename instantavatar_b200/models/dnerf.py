@@ -1,0 +1,61 @@
+"""Host-side mirror of instant_avatar/models/DNeRF.py::DNeRFModel without the PyTorch-Lightning / Hydra shell
+(control plane, out of scope): the same sub-modules (`net_coarse`, `deformer`, `renderer`, `loss_fn`), the same
+`forward`, `render_image_fast`, `update_density_grid` and `training_step` logic, driving the fused kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from ..deformers.snarf_deformer import SNARFDeformer
+from ..renderers.raymarcher_acc import BoundModel, Raymarcher
+from .networks.ngp import NeRFNGPNet
+
+
+@dataclass
+class Rays:  # models/structures/utils.py:5-11
+    o: torch.Tensor
+    d: torch.Tensor
+    near: torch.Tensor = None
+    far: torch.Tensor = None
+
+
+class DNeRFModel(torch.nn.Module):
+    def __init__(self, smpl_data=None, model_path=None, gender="male", n_train_frames=1, device="cuda", net_seed=1337,
+                 deformer_opt=None):
+        super().__init__()
+        self.net_coarse = NeRFNGPNet(None, seed=net_seed).to(device)
+        self.deformer = SNARFDeformer(model_path, gender, deformer_opt or {"cano_pose": "A_pose", "resolution": 128},
+                                      smpl_data=smpl_data)
+        self.deformer.body_model = self.deformer.body_model.to(device)
+        self.renderer = Raymarcher(256, 291600, device=device)
+        self.renderer.initialize(n_train_frames)
+        self.global_step = 0
+        self.image_width = 0
+
+    def forward(self, batch, eval_mode=None, jitter=None, noise_tensor=None):
+        """DNeRF.py:61-70"""
+        eval_mode = (not self.training) if eval_mode is None else eval_mode
+        rays = Rays(o=batch["rays_o"], d=batch["rays_d"], near=batch["near"], far=batch["far"])
+        self.deformer.transform_rays_w2s(rays)
+        use_noise = self.global_step < 1000 and not eval_mode
+        model = BoundModel(self.deformer, self.net_coarse, eval_mode)
+        self.renderer.image_width = self.image_width
+        if eval_mode:
+            return self.renderer(rays, model, eval_mode=True, noise=0, bg_color=batch.get("bg_color", None))
+        return self.renderer.render_train(rays, model, 1 if use_noise else 0, batch.get("bg_color", None), jitter, noise_tensor)
+
+    @torch.no_grad()
+    def render_image_fast(self, batch, img_size, jitters=None):
+        """DNeRF.py:72-97: per-frame preparation, test occupancy grid, fused render."""
+        self.deformer.prepare_deformer(batch)
+        self.net_coarse.initialize(self.deformer.bbox)
+        self.renderer.density_grid_test.initialize(self.deformer, self.net_coarse, jitters=jitters)
+        self.image_width = img_size[1]
+        d = self.forward(batch, eval_mode=True)
+        rgb = d["rgb_coarse"].reshape(-1, *img_size, 3)
+        depth = d["depth_coarse"].reshape(-1, *img_size)
+        alpha = d["alpha_coarse"].reshape(-1, *img_size)
+        counter = d["counter_coarse"].reshape(-1, *img_size)
+        return rgb, depth, alpha, counter

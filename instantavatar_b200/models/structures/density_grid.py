@@ -27,13 +27,11 @@ def max_connected_component(grid):
     return comp.squeeze(0).squeeze(0)
 
 
-def field_from_density(density):
-    """density_grid.py:78-85 / :104-110"""
+def field_from_density_torch(density):
+    """density_grid.py:78-85 / :104-110 with the PyTorch ops the reference uses (kept for cross-checking)"""
     field = 1 - torch.exp(0.01 * -density)
     field = F.max_pool3d(field[None, None], kernel_size=3, stride=1, padding=1)[0, 0]
     field = field > torch.clamp(field.mean(), max=0.01)
-    if hasattr(ops, "largest_component"):
-        return ops.largest_component(field)
     mcc = max_connected_component(field)
     label = torch.mode(mcc[field], 0).values
     return mcc == label
@@ -80,6 +78,13 @@ class DensityGrid(torch.nn.Module):
         self.density_field = field
         self._version += 1
 
+    def build_from_density(self, density):
+        """density -> density_field + bit field in one pass of the occupancy kernels"""
+        field, self._bits = ops.occupancy_build(density, self._bits)
+        self.density_field = field
+        self._version += 1
+        self._bits_version = self._version
+
     def update(self, deformer, net, step, jitter=None):
         """density_grid.py:46-92 (train-time refresh; returns the regulariser inputs)."""
         if jitter is None:
@@ -90,7 +95,7 @@ class DensityGrid(torch.nn.Module):
         density = density.clip(min=0).reshape(coords.shape[:-1])
         old = self.density_field
         self.density_cached = torch.maximum(self.density_cached * 0.8, density.detach())
-        self.set_field(field_from_density(self.density_cached))
+        self.build_from_density(self.density_cached)
         density = 1 - torch.exp(0.01 * -F.relu(density))
         valid = self.density_field if step < 500 else old
         return density, valid
@@ -105,4 +110,4 @@ class DensityGrid(torch.nn.Module):
             coords = denormalize(self.coords + j / self.grid_size, self.aabb)
             _, d = deformer(coords.reshape(-1, 3), net)
             density = torch.maximum(density, d.reshape(density.shape))
-        self.set_field(field_from_density(density))
+        self.build_from_density(density)

@@ -23,7 +23,7 @@ def precompute(voxel_w: torch.Tensor, tfs: torch.Tensor, offset_k: torch.Tensor,
     fld = torch.empty((D, H, W, 12), device=dev, dtype=f32)
     vd = torch.empty((3, D, H, W), device=dev, dtype=f32) if want_voxel_d else None
     aabb = torch.tensor([float("inf")] * 3 + [float("-inf")] * 3, device=dev, dtype=f32)
-    check(lib().ia_precompute(ptr(voxel_w, f32), ptr(tfs.reshape(24, 4, 4).contiguous(), f32),
+    _lib.count(1); check(lib().ia_precompute(ptr(voxel_w, f32), ptr(tfs.reshape(24, 4, 4).contiguous(), f32),
                               ptr(offset_k.reshape(3).contiguous(), f32), ptr(scale_k.reshape(3).contiguous(), f32),
                               C.c_int(D), C.c_int(H), C.c_int(W), ptr(fld), ptr(vd), ptr(aabb), stream()))
     return fld, vd, aabb
@@ -37,7 +37,7 @@ def params_to_half(enc_params: torch.Tensor, col_params: torch.Tensor, table_h=N
         table_h = torch.empty((total, 2), device=dev, dtype=torch.float16)
     if mlp_h is None:
         mlp_h = torch.empty(_lib.IA_MLP_HALFS, device=dev, dtype=torch.float16)
-    check(lib().ia_params_to_half(ptr(enc_params, f32), ptr(col_params, f32), ptr(table_h), ptr(mlp_h), stream()))
+    _lib.count(1); check(lib().ia_params_to_half(ptr(enc_params, f32), ptr(col_params, f32), ptr(table_h), ptr(mlp_h), stream()))
     return table_h, mlp_h
 
 
@@ -46,8 +46,23 @@ def pack_occupancy(field_bool: torch.Tensor, bits=None):
     fb = field_bool.contiguous().view(torch.uint8) if field_bool.dtype == torch.bool else field_bool.contiguous()
     if bits is None:
         bits = torch.empty(G * G * G // 32 + 8, device=fb.device, dtype=torch.int32)
-    check(lib().ia_pack_occupancy(ptr(fb), ptr(bits), C.c_int(G), stream()))
+    _lib.count(2); check(lib().ia_pack_occupancy(ptr(fb), ptr(bits), C.c_int(G), stream()))
     return bits
+
+
+def occupancy_build(density: torch.Tensor, bits=None, want_field=True, workspace=None):
+    """density [G,G,G] -> (density_field bool [G,G,G] | None, occupancy bit field) -- density_grid.py:78-85,118-125"""
+    G = density.shape[0]
+    dev = density.device
+    density = density.contiguous().float()
+    field = torch.empty((G, G, G), device=dev, dtype=torch.bool) if want_field else None
+    if bits is None:
+        bits = torch.empty(G * G * G // 32 + 8, device=dev, dtype=torch.int32)
+    nbytes = 12 * G * G * G + 64
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    _lib.count(7); check(lib().ia_occupancy_build(ptr(density, f32), C.c_int(G), ptr(field), ptr(bits), ptr(workspace), C.c_size_t(nbytes), stream()))
+    return field, bits
 
 
 @dataclass
@@ -106,7 +121,7 @@ def render_fwd(scene: Scene, rays_o, rays_d, near, far, bg=None, image_width: in
     if workspace is None:
         workspace = torch.empty(64, device=dev, dtype=torch.int32)
     s = scene.c_struct()
-    check(lib().ia_render_fwd(C.byref(s), ptr(rays_o, f32), ptr(rays_d, f32), ptr(near, f32), ptr(far, f32), C.c_int(n),
+    _lib.count(1); check(lib().ia_render_fwd(C.byref(s), ptr(rays_o, f32), ptr(rays_d, f32), ptr(near, f32), ptr(far, f32), C.c_int(n),
                               ptr(bg), C.c_int(image_width), ptr(out["rgb"]), ptr(out["depth"]), ptr(out["alpha"]),
                               ptr(out["counter"]), ptr(workspace), ptr(stats), stream()))
     return out
@@ -121,7 +136,7 @@ def deform_query(scene: Scene, pts, eval_mode=True, want_xc=False, stats=None):
     xc = torch.empty((n, 3), device=dev, dtype=f32) if want_xc else None
     best = torch.empty(n, device=dev, dtype=torch.int8) if want_xc else None
     s = scene.c_struct()
-    check(lib().ia_deform_query(C.byref(s), ptr(pts, f32), C.c_int(n), C.c_int(1 if eval_mode else 0), ptr(rgb), ptr(sigma),
+    _lib.count(1); check(lib().ia_deform_query(C.byref(s), ptr(pts, f32), C.c_int(n), C.c_int(1 if eval_mode else 0), ptr(rgb), ptr(sigma),
                                 ptr(xc), ptr(best), ptr(stats), stream()))
     return (rgb, sigma, xc, best) if want_xc else (rgb, sigma)
 
@@ -134,7 +149,7 @@ def broyden(scene: Scene, xd, want_jinv=False):
     xc = torch.empty((n, 13, 3), device=dev, dtype=f32); valid = torch.empty((n, 13), device=dev, dtype=torch.uint8)
     jinv = torch.empty((n, 13, 3, 3), device=dev, dtype=f32) if want_jinv else None
     s = scene.c_struct()
-    check(lib().ia_broyden(C.byref(s), ptr(xd, f32), C.c_int(n), ptr(xc), ptr(valid), ptr(jinv), stream()))
+    _lib.count(1); check(lib().ia_broyden(C.byref(s), ptr(xd, f32), C.c_int(n), ptr(xc), ptr(valid), ptr(jinv), stream()))
     return xc, valid.bool(), jinv
 
 
@@ -144,5 +159,5 @@ def ngp_forward(scene: Scene, x):
     n = x.shape[0]
     sigma = torch.empty(n, device=x.device, dtype=f32); rgb = torch.empty((n, 3), device=x.device, dtype=f32)
     s = scene.c_struct()
-    check(lib().ia_ngp_forward(C.byref(s), ptr(x, f32), C.c_int(n), ptr(sigma), ptr(rgb), stream()))
+    _lib.count(1); check(lib().ia_ngp_forward(C.byref(s), ptr(x, f32), C.c_int(n), ptr(sigma), ptr(rgb), stream()))
     return rgb, sigma
