@@ -21,7 +21,7 @@ extern "C" {
 #define IA_ABI_VERSION 1
 #define IA_NUM_INIT 13      /* deformers/fast_snarf/deformer_torch.py:28 */
 #define IA_NUM_LEVELS 16    /* models/networks/ngp.py:30 */
-#define IA_MLP_HALFS 11008  /* padded fp16 weight block, see ia_params_to_half */
+#define IA_MLP_HALFS 22144  /* padded fp16 weight block (forward + transposed copies), see ia_params_to_half */
 #define IA_ENC_MLP_PARAMS 3072
 #define IA_COL_MLP_PARAMS 6144
 #define IA_MAX_SAMPLES 256  /* confs/renderer/raymarcher_acc.yaml:2 */
@@ -123,6 +123,46 @@ int ia_broyden(const IaScene* scene /*[host]*/, const float* xd, int n, float* x
                ia_stream_t stream);
 int ia_ngp_forward(const IaScene* scene /*[host]*/, const float* x, int n, float* sigma, float* rgb,
                    ia_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Training path
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* Fused training forward.  Replaces Raymarcher.render_train (renderers/raymarcher_acc.py:140-186) together with
+ * raymarch_train (raymarcher.cpp:41-53), SNARFDeformer.deform_train (snarf_deformer.py:143-159) and the network.
+ * jitter [n][256] (U(0,1), replaces torch.rand_like, :158) and noise [n][256] (already scaled, replaces
+ * noise*randn_like, :167) are nullable.  Outputs rgb [n][3], depth [n], alpha [n], weights [n][256] and the dense
+ * per-sample state the backward needs: s_sigma/s_z [n][256], s_rgb/s_xc [n][256][3], s_best [n][256] (int8, -1 =
+ * no valid root), s_count [n].  workspace >= 256 bytes. */
+int ia_train_fwd(const IaScene* scene /*[host]*/, const float* rays_o, const float* rays_d, const float* near,
+                 const float* far, int n_rays, const float* bg, const float* jitter, const float* noise, float* rgb,
+                 float* depth, float* alpha, float* weights, float* s_sigma, float* s_rgb, float* s_xc, float* s_z,
+                 int* s_count, int8_t* s_best, void* workspace, IaStats* stats, ia_stream_t stream);
+
+/* Compositing backward (autograd of raymarcher_acc.py:25-36,166-186): upstream grads (nullable) of rgb [n][3],
+ * depth [n], alpha [n], weights [n][256] -> compact list of (canonical point, d sigma, d rgb) of the samples that
+ * reached the network; l_* arrays hold up to n*256 entries, l_count [1] must be zeroed by the caller. */
+int ia_composite_bwd(int n_rays, const float* near, const float* far, const float* bg, const float* noise,
+                     const float* s_sigma, const float* s_rgb, const float* s_xc, const float* s_z, const int* s_count,
+                     const int8_t* s_best, const float* g_rgb, const float* g_depth, const float* g_alpha,
+                     const float* g_weights, float* l_xc, float* l_dsigma, float* l_drgb, int* l_count,
+                     ia_stream_t stream);
+
+/* Network backward (tiny-cuda-nn's autograd through HashGrid + FullyFusedMLPs, ngp.py:73-83): for the first
+ * min(*count, capacity) list entries accumulates (+=) d loss / d encoder.params into grad_enc [3072 + 2*total] and
+ * d loss / d color_net.params into grad_col [6144] (fp32, tcnn parameter order).  grad_scale: internal loss scale of
+ * the fp16 dgrad chain (results are un-scaled).  scratch >= ia_ngp_backward_scratch_bytes(capacity). */
+size_t ia_ngp_backward_scratch_bytes(int capacity);
+int ia_ngp_backward(const IaScene* scene /*[host]*/, const float* xc, const float* dsigma, const float* drgb,
+                    const int* count, int capacity, float grad_scale, float* grad_enc, float* grad_col, void* scratch,
+                    ia_stream_t stream);
+
+/* Fused dense Adam (torch.optim.Adam semantics, models/DNeRF.py:46-50) on a flat fp32 tensor; gradients are
+ * multiplied by inv_grad_scale (GradScaler unscale, DNeRF.py:157-158); if found_inf (device, nullable) is non-zero
+ * the step is skipped.  ia_grad_check_finite sets *found_inf = 1 when any gradient is non-finite. */
+int ia_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1,
+                 float beta2, float eps, int step, float inv_grad_scale, const float* found_inf, ia_stream_t stream);
+int ia_grad_check_finite(const float* grads, long n, float* found_inf, ia_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libia_b200.so")
 
-IA_MLP_HALFS = 11008
+IA_MLP_HALFS = 22144
 IA_ENC_MLP_PARAMS = 3072
 IA_COL_MLP_PARAMS = 6144
 IA_NUM_INIT = 13
@@ -21,7 +21,8 @@ IA_MAX_SAMPLES = 256
 
 SYMBOLS = [
     "ia_abi_version", "ia_last_error", "ia_sm_count", "ia_set_option", "ia_hashgrid_layout", "ia_precompute", "ia_params_to_half",
-    "ia_pack_occupancy", "ia_occupancy_build", "ia_render_fwd", "ia_deform_query", "ia_broyden", "ia_ngp_forward",
+    "ia_pack_occupancy", "ia_occupancy_build", "ia_train_fwd", "ia_composite_bwd", "ia_ngp_backward",
+    "ia_ngp_backward_scratch_bytes", "ia_adam_step", "ia_grad_check_finite", "ia_render_fwd", "ia_deform_query", "ia_broyden", "ia_ngp_forward",
 ]
 
 
@@ -57,6 +58,7 @@ def lib():
                 "(instantavatar_b200 has no CPU fallback)")
         _lib = C.CDLL(LIB_PATH)
         _lib.ia_last_error.restype = C.c_char_p
+        _lib.ia_ngp_backward_scratch_bytes.restype = C.c_size_t
         for s in SYMBOLS:
             getattr(_lib, s)  # fail loudly on a stale library
         if _lib.ia_abi_version() != 1:

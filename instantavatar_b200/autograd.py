@@ -1,0 +1,88 @@
+"""torch.autograd glue for the fused training kernels.
+
+The reference differentiates ~20 ATen ops + two tiny-cuda-nn modules; here one custom Function wraps
+`ia_train_fwd` (forward) and `ia_composite_bwd` + `ia_ngp_backward` (backward): it returns the per-ray outputs the
+loss consumes (rgb, depth, alpha and the dense per-sample weights) and produces gradients for the two flat parameter
+tensors `encoder.params` / `color_net.params`.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+GRAD_SCALE = 128.0  # internal loss scale of the fp16 dgrad chain (tiny-cuda-nn uses the same default)
+
+
+class _RenderTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enc_params, col_params, scene, rays_o, rays_d, near, far, bg, jitter, noise, stats):
+        out, saved = ops.train_fwd(scene, rays_o, rays_d, near, far, bg, jitter, noise, stats)
+        ctx.scene, ctx.saved, ctx.misc = scene, saved, (near, far, bg, noise)
+        ctx.shapes = (enc_params.shape, col_params.shape)
+        ctx.mark_non_differentiable(out["depth"]) if False else None
+        return out["rgb"], out["depth"], out["alpha"], out["weights"]
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_alpha, g_weights):
+        near, far, bg, noise = ctx.misc
+        l_xc, l_ds, l_dc, l_count = ops.composite_bwd(near, far, bg, noise, ctx.saved, g_rgb, g_depth, g_alpha, g_weights)
+        dev = near.device
+        g_enc = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32)
+        g_col = torch.zeros(ctx.shapes[1], device=dev, dtype=torch.float32)
+        ops.ngp_backward(ctx.scene, l_xc, l_ds, l_dc, l_count, g_enc, g_col, GRAD_SCALE)
+        return g_enc, g_col, None, None, None, None, None, None, None, None, None
+
+
+def render_train_fused(renderer, deformer, net, rays, noise, bg_color, jitter=None, noise_tensor=None, stats=None):
+    """Raymarcher.render_train (raymarcher_acc.py:140-186) on the fused kernels."""
+    net.initialize(deformer.bbox)
+    grid = renderer.density_grid_train
+    scene = deformer.scene(net, grid.occupancy_bits(), grid.aabb6())
+    rays_o = rays.o.reshape(-1, 3).float().contiguous()
+    rays_d = rays.d.reshape(-1, 3).float().contiguous()
+    near = rays.near.reshape(-1).float().contiguous()
+    far = rays.far.reshape(-1).float().contiguous()
+    n = near.numel()
+    if jitter is None:
+        jitter = torch.rand((n, 256), device=near.device)
+    if noise_tensor is None and noise > 0:
+        noise_tensor = noise * torch.randn((n, 256), device=near.device)
+    bg = bg_color.reshape(-1, 3).float().contiguous() if bg_color is not None else None
+    rgb, depth, alpha, weights = _RenderTrain.apply(net.encoder.params, net.color_net.params, scene, rays_o, rays_d, near, far, bg,
+                                                    jitter.contiguous(), noise_tensor.contiguous() if noise_tensor is not None else None, stats)
+    return {
+        "rgb_coarse": rgb.reshape(rays.o.shape),
+        "depth_coarse": depth.reshape(rays.near.shape),
+        "alpha_coarse": alpha.reshape(rays.near.shape),
+        "weight_coarse": weights.reshape(*rays.near.shape, -1),
+    }
+
+
+class _DeformQueryTrain(torch.autograd.Function):
+    """deformer(pts, net, eval_mode=False) with gradients w.r.t. the network parameters (DensityGrid.update regulariser)."""
+
+    @staticmethod
+    def forward(ctx, enc_params, col_params, scene, pts):
+        rgb, sigma, xc, best = ops.deform_query(scene, pts, eval_mode=False, want_xc=True)
+        ctx.scene, ctx.saved = scene, (xc, best)
+        ctx.shapes = (enc_params.shape, col_params.shape)
+        return rgb, sigma
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_sigma):
+        xc, best = ctx.saved
+        dev = xc.device
+        valid = best >= 0
+        g_sigma = torch.where(valid, g_sigma.contiguous().float(), torch.zeros_like(g_sigma)) if g_sigma is not None else torch.zeros(xc.shape[0], device=dev)
+        g_rgb = (g_rgb.contiguous().float() * valid[:, None]) if g_rgb is not None else torch.zeros_like(xc)
+        count = torch.full((1,), xc.shape[0], device=dev, dtype=torch.int32)
+        g_enc = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32)
+        g_col = torch.zeros(ctx.shapes[1], device=dev, dtype=torch.float32)
+        ops.ngp_backward(ctx.scene, xc, g_sigma.contiguous(), g_rgb.contiguous(), count, g_enc, g_col, GRAD_SCALE)
+        return g_enc, g_col, None, None
+
+
+def deform_query_train(deformer, net, pts):
+    scene = deformer.scene(net)
+    return _DeformQueryTrain.apply(net.encoder.params, net.color_net.params, scene, pts)

@@ -8,79 +8,13 @@
 
 using namespace ia;
 
+static int g_render_rays = 8;  // rays per warp (32 / 16 / 8 / 4), tunable through ia_set_option
+
 #include "ia_host.h"
+#include "ia_scene.cuh"
 
 static thread_local char g_err[512] = "";
 char* ia_err_buf() { return g_err; }
-
-__constant__ int c_init_bones[kNumInit] = {0, 1, 2, 4, 5, 10, 11, 12, 15, 16, 17, 18, 19};
-
-static void host_hash_levels(HashLevels& hl, uint32_t* total) {
-    uint32_t off = 0;
-    for (int l = 0; l < kLevels; l++) {
-        const float s = exp2f((float)l * log2f(1.5f)) * 16.0f - 1.0f;
-        const uint32_t r = (uint32_t)ceilf(s) + 1u;
-        uint64_t n = ((uint64_t)r * r * r + 7) / 8 * 8;
-        if (n > (1u << 19)) n = (1u << 19);
-        hl.scale[l] = s; hl.res[l] = r; hl.size[l] = (uint32_t)n; hl.offset[l] = off;
-        off += (uint32_t)n;
-    }
-    if (total) *total = off;
-}
-
-static float filter_threshold() {
-    const double c = 0.0001 * 0.0001;  // filter.cu:44 compares the float distance against this double
-    float cf = (float)c;
-    if ((double)cf < c) cf = nextafterf(cf, INFINITY);
-    return cf;
-}
-
-static int g_render_rays = 8;  // rays per warp (32 / 16 / 8 / 4), tunable through ia_set_option
-static int g_sm_count = 0;
-static int sm_count() {
-    if (!g_sm_count) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return g_sm_count;
-}
-
-// ================================================================================================
-// per-CTA prologue shared by the fused kernels: stage per-frame constants in shared memory
-// ================================================================================================
-struct SceneDev {
-    IaScene s;
-    HashLevels hl;
-    float filter_thr;
-};
-
-__device__ __forceinline__ void load_frame_const(FrameConst& fc, const SceneDev& sd) {
-    const int tid = threadIdx.x;
-    if (tid < kNumInit * 12) {
-        const int i = tid / 12, e = tid % 12;
-        fc.Tb[i][e] = sd.s.tfs[c_init_bones[i] * 16 + e];  // rows 0..2 of the 4x4
-    }
-    if (tid < 3) {
-        fc.bp.off[tid] = sd.s.offset_k[tid];
-        fc.bp.scl[tid] = sd.s.scale_k[tid];
-        if (sd.s.net_center) {
-            fc.net_center[tid] = sd.s.net_center[tid];
-            fc.net_scale[tid] = sd.s.net_scale[tid];
-        }
-        if (sd.s.occ_aabb) {
-            const float mn = sd.s.occ_aabb[tid], mx = sd.s.occ_aabb[3 + tid];
-            fc.occ_min[tid] = mn;
-            fc.occ_s[tid] = (float)sd.s.G / (mx - mn);  // raymarcher.cu:37
-        }
-    }
-    if (tid == 0) {
-        const float cvg = 1e-5f, dvg = 1e-1f;  // deformer_torch.py:100
-        fc.bp.cvg2 = cvg * cvg;
-        fc.bp.dvg2 = dvg * dvg;
-        fc.filter_thr = sd.filter_thr;
-    }
-}
 
 // ================================================================================================
 // fused eval renderer
@@ -538,19 +472,23 @@ __global__ void params_to_half_kernel(const float* __restrict__ enc, const float
         const float2 v = *reinterpret_cast<const float2*>(enc + IA_ENC_MLP_PARAMS + 2 * i);
         table[i] = __floats2half2_rn(v.x, v.y);
     }
-    if (i < kMlpHalfs) {
-        // padded [out][in+8] blocks; pad columns are zero
+    if (i < kMlpAllHalfs) {
+        // padded [out][in+8] blocks (forward) followed by padded transposed [in][out+8] blocks (backward);
+        // pad columns are zero.  W3 is stored column-rotated: input column 0 carries the constant 1.0 (tcnn pad),
+        // columns 1..15 the 15 geometry features.
         float v = 0.f;
         int o = (int)i;
+        auto W3r = [&](int r, int c) { return col[r * 16 + (c == 0 ? 15 : c - 1)]; };
         if (o < kW2Off) { const int r = o / kW1Stride, c = o % kW1Stride; if (c < 32) v = enc[r * 32 + c]; }
         else if (o < kW3Off) { o -= kW2Off; const int r = o / kW2Stride, c = o % kW2Stride; if (c < 64) v = enc[2048 + r * 64 + c]; }
-        else if (o < kW4Off) {
-            o -= kW3Off; const int r = o / kW3Stride, c = o % kW3Stride;
-            // column rotation: input column 0 carries the constant 1.0 (tcnn pad), columns 1..15 the features
-            if (c < 16) v = col[r * 16 + (c == 0 ? 15 : c - 1)];
-        }
+        else if (o < kW4Off) { o -= kW3Off; const int r = o / kW3Stride, c = o % kW3Stride; if (c < 16) v = W3r(r, c); }
         else if (o < kW5Off) { o -= kW4Off; const int r = o / kW4Stride, c = o % kW4Stride; if (c < 64) v = col[1024 + r * 64 + c]; }
-        else { o -= kW5Off; const int r = o / kW5Stride, c = o % kW5Stride; if (c < 64) v = col[1024 + 4096 + r * 64 + c]; }
+        else if (o < kW5TOff) { o -= kW5Off; const int r = o / kW5Stride, c = o % kW5Stride; if (c < 64) v = col[1024 + 4096 + r * 64 + c]; }
+        else if (o < kW4TOff) { o -= kW5TOff; const int r = o / kW5TStride, c = o % kW5TStride; if (c < 16) v = col[1024 + 4096 + c * 64 + r]; }
+        else if (o < kW3TOff) { o -= kW4TOff; const int r = o / kW4TStride, c = o % kW4TStride; if (c < 64) v = col[1024 + c * 64 + r]; }
+        else if (o < kW2TOff) { o -= kW3TOff; const int r = o / kW3TStride, c = o % kW3TStride; if (c < 64) v = W3r(c, r); }
+        else if (o < kW1TOff) { o -= kW2TOff; const int r = o / kW2TStride, c = o % kW2TStride; if (c < 16) v = enc[2048 + c * 64 + r]; }
+        else { o -= kW1TOff; const int r = o / kW1TStride, c = o % kW1TStride; if (c < 64) v = enc[c * 32 + r]; }
         mlp[i] = __float2half_rn(v);
     }
 }
@@ -584,21 +522,6 @@ __global__ void pack_occupancy_kernel(const uint8_t* __restrict__ field, uint32_
 // ================================================================================================
 // extern "C"
 // ================================================================================================
-static int make_scene_dev(const IaScene* s, SceneDev& sd, bool need_occ, bool need_net = true) {
-    IA_REQUIRE(s != nullptr);
-    IA_REQUIRE(s->field && s->offset_k && s->scale_k && s->tfs);
-    if (need_net) IA_REQUIRE(s->table_h && s->mlp_h && s->net_center && s->net_scale);
-    IA_REQUIRE(s->D > 1 && s->H > 1 && s->W > 1);
-    if (need_occ) {
-        IA_REQUIRE(s->occ_bits && s->occ_aabb);
-        IA_REQUIRE(s->G == 64);
-    }
-    sd.s = *s;
-    host_hash_levels(sd.hl, nullptr);
-    sd.filter_thr = filter_threshold();
-    return IA_OK;
-}
-
 extern "C" {
 
 int ia_abi_version(void) { return IA_ABI_VERSION; }

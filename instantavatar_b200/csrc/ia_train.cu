@@ -1,0 +1,724 @@
+// ia_train.cu -- training path: fused forward (march + jitter + Broyden + network + cumprod compositing), compositing
+// backward, network backward (MLP dgrad on tensor cores, hash-grid gradient scatter, weight gradients) and the fused
+// dense Adam step.  Same numerics contract as ia_kernels.cu (-fmad=false, explicit fma).
+#include <math.h>
+#include <stdint.h>
+
+#include "ia_scene.cuh"
+
+namespace {
+
+constexpr int kRowHalfs = 456;  // per-sample scratch row for the weight-gradient pass (see ngp_backward_kernel)
+constexpr int kOffD5 = 0, kOffH3 = 8, kOffD4 = 72, kOffH2 = 136, kOffD3 = 200, kOffC3 = 264, kOffD2 = 280, kOffH1 = 296,
+              kOffD1 = 360, kOffEnc = 424;
+
+// ================================================================================================
+// training forward: Raymarcher.render_train (raymarcher_acc.py:140-186) + SNARFDeformer.deform_train
+// ================================================================================================
+struct TrainFwdArgs {
+    SceneDev sd;
+    const float* rays_o; const float* rays_d; const float* near; const float* far;
+    const float* bg; const float* jitter; const float* noise;
+    int n_rays;
+    float* rgb; float* depth; float* alpha; float* weights;  // outputs; weights [n,256]
+    // saved for backward, dense slot-indexed [n,256(,3)]
+    float* s_sigma; float* s_rgb; float* s_xc; float* s_z; int* s_count; int8_t* s_best;
+    int* tile_counter;
+    IaStats* stats;
+};
+
+struct TrainWarpExtra {
+    float qx[64], qy[64], qz[64], qt[64];
+    int qowner[64];
+    short qslot[64];
+    float bt[32];
+    int bo[32];
+    short bs[32];
+};
+
+template <int kWarps>
+struct TrainSmem {
+    __align__(128) uint32_t occ[64 * 64 * 64 / 32];
+    __align__(16) __half W[kMlpHalfs];
+    FrameConst fc;
+    __align__(8) uint64_t mbar;
+    WarpScratch<true> ws[kWarps];
+    TrainWarpExtra wx[kWarps];
+};
+
+template <int kWarps, int kRays>
+__global__ void __launch_bounds__(kWarps * 32, 1) train_fwd_kernel(const __grid_constant__ TrainFwdArgs a) {
+    constexpr int kDepth = 32 / kRays;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TrainSmem<kWarps>& sm = *reinterpret_cast<TrainSmem<kWarps>*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = a.sd.s.G;
+    const uint32_t occ_bytes = (uint32_t)(G * G * G / 8);
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.mbar, 1);
+        mbar_expect_tx(&sm.mbar, occ_bytes + kMlpHalfs * 2);
+        bulk_g2s(sm.occ, a.sd.s.occ_bits, occ_bytes, &sm.mbar);
+        bulk_g2s(sm.W, a.sd.s.mlp_h, kMlpHalfs * 2, &sm.mbar);
+    }
+    load_frame_const(sm.fc, a.sd);
+    __syncthreads();
+    mbar_wait(&sm.mbar, 0);
+
+    EvalCtx ctx;
+    ctx.field.data = reinterpret_cast<const float4*>(a.sd.s.field);
+    ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
+    ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
+    ctx.Wsm = sm.W; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
+    WarpScratch<true>& ws = sm.ws[warp];
+    TrainWarpExtra& wx = sm.wx[warp];
+    const FrameConst& fc = sm.fc;
+
+    const int n_tiles = (a.n_rays + kRays - 1) / kRays;
+    const int rl = lane % kRays, jl = lane / kRays;
+    unsigned ray_mask = 0;
+#pragma unroll
+    for (int j = 0; j < kDepth; j++) ray_mask |= 1u << (rl + j * kRays);
+    unsigned st_gather = 0, st_roots = 0, st_samples = 0;
+
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
+        tile = __shfl_sync(kFull, tile, 0);
+        if (tile >= n_tiles) break;
+        const int ray = tile * kRays + rl;
+        const bool has = ray < a.n_rays;
+        float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, t = 0, far = 0, dt = 0;
+        if (has) {
+            ox = a.rays_o[ray * 3]; oy = a.rays_o[ray * 3 + 1]; oz = a.rays_o[ray * 3 + 2];
+            dx = a.rays_d[ray * 3]; dy = a.rays_d[ray * 3 + 1]; dz = a.rays_d[ray * 3 + 2];
+            t = a.near[ray]; far = a.far[ray];
+            dt = (far - t) / (float)IA_MAX_SAMPLES;  // raymarcher_acc.py:147
+            for (int i = 0; i < jl; i++) t += dt;
+        }
+        // zero this ray's dense rows (empty slots: weight 0, raymarcher_acc.py:161-171)
+        if (has) {
+            for (int s = jl; s < IA_MAX_SAMPLES; s += kDepth) {
+                a.weights[(long)ray * IA_MAX_SAMPLES + s] = 0.f;
+                a.s_best[(long)ray * IA_MAX_SAMPLES + s] = -1;
+            }
+        }
+        float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Dp = 0.f, Wsum = 0.f;  // owner lanes (jl == 0)
+        int ray_count = 0;  // occupied samples of this ray so far (kept consistent across the ray's lanes)
+        int qhead = 0, qcount = 0;
+        for (;;) {
+            while (qcount < 32) {
+                const bool act = has && t < far && ray_count < IA_MAX_SAMPLES;
+                if (!__any_sync(kFull, act)) break;
+                bool occ = false;
+                if (act) {  // occupancy test on the un-jittered position, raymarcher.cu:140-152
+                    const float x = __fmaf_rn(t, dx, ox), y = __fmaf_rn(t, dy, oy), z = __fmaf_rn(t, dz, oz);
+                    const int nx = (int)clampf((x - fc.occ_min[0]) * fc.occ_s[0], 0.0f, (float)G - 1.0f);
+                    const int ny = (int)clampf((y - fc.occ_min[1]) * fc.occ_s[1], 0.0f, (float)G - 1.0f);
+                    const int nz = (int)clampf((z - fc.occ_min[2]) * fc.occ_s[2], 0.0f, (float)G - 1.0f);
+                    const int bit = (nx * G + ny) * G + nz;
+                    occ = (sm.occ[bit >> 5] >> (bit & 31)) & 1u;
+                }
+                const unsigned m = __ballot_sync(kFull, occ);
+                const unsigned msame = m & ray_mask;
+                const int slot_s = ray_count + __popc(msame & ((1u << lane) - 1u));
+                if (occ && slot_s < IA_MAX_SAMPLES) {
+                    // raymarcher_acc.py:158-159: z = t + U*step ; pts = z * d + o  (separate mul/add as in torch)
+                    const float jit = a.jitter ? a.jitter[(long)ray * IA_MAX_SAMPLES + slot_s] : 0.f;
+                    const float z = t + jit * dt;
+                    const int slot = (qhead + qcount + __popc(m & ((1u << lane) - 1u))) & 63;
+                    wx.qx[slot] = z * dx + ox; wx.qy[slot] = z * dy + oy; wx.qz[slot] = z * dz + oz;
+                    wx.qt[slot] = z; wx.qowner[slot] = rl; wx.qslot[slot] = (short)slot_s;
+                }
+                // (slots beyond 255 cannot occur: at most 256 steps fit between near and far)
+                qcount += __popc(m);
+                ray_count += __popc(msame);
+                if (act) {
+#pragma unroll
+                    for (int i = 0; i < kDepth; i++) t += dt;
+                }
+            }
+            if (qcount == 0) break;
+            __syncwarp();
+            const int n = min(qcount, 32);
+            const int slot = (qhead + lane) & 63;
+            float sx = 0, sy = 0, sz = 0, sz_t = 0;
+            int sown = 0, sslot = 0;
+            const bool sact = lane < n;
+            if (sact) { sx = wx.qx[slot]; sy = wx.qy[slot]; sz = wx.qz[slot]; sz_t = wx.qt[slot]; sown = wx.qowner[slot]; sslot = wx.qslot[slot]; }
+            qhead = (qhead + n) & 63;
+            qcount -= n;
+            st_samples += sact ? 1u : 0u;
+            SampleOut so;
+            warp_eval_samples<true>(ctx, ws, sact, sx, sy, sz, false, lane, so, st_gather, st_roots);
+            // save per-sample state for the backward pass
+            const int sray = tile * kRays + sown;
+            if (sact) {
+                const long o = (long)sray * IA_MAX_SAMPLES + sslot;
+                a.s_sigma[o] = so.sigma;
+                a.s_rgb[o * 3] = so.r; a.s_rgb[o * 3 + 1] = so.g; a.s_rgb[o * 3 + 2] = so.b;
+                a.s_xc[o * 3] = so.xc[0]; a.s_xc[o * 3 + 1] = so.xc[1]; a.s_xc[o * 3 + 2] = so.xc[2];
+                a.s_z[o] = sz_t;
+                a.s_best[o] = (int8_t)so.best;
+            }
+            // ---- composite (raymarcher_acc.py:25-36, :166-180) in slot order ----
+            float sig = so.sigma;
+            if (sact && a.noise) sig = sig + a.noise[(long)sray * IA_MAX_SAMPLES + sslot];
+            ws.res[lane][0] = sig; ws.res[lane][1] = so.r; ws.res[lane][2] = so.g; ws.res[lane][3] = so.b;
+            wx.bt[lane] = sz_t; wx.bo[lane] = sact ? sown : -1; wx.bs[lane] = (short)sslot;
+            __syncwarp();
+            for (int i = 0; i < n; i++) {
+                if (wx.bo[i] == lane) {
+                    const float tau = fmaxf(ws.res[i][0], 0.f) * dt;
+                    const float al = 1.0f - expf(-tau);
+                    const float w = al * T;
+                    a.weights[(long)ray * IA_MAX_SAMPLES + wx.bs[i]] = w;
+                    Cr += w * ws.res[i][1]; Cg += w * ws.res[i][2]; Cb += w * ws.res[i][3];
+                    Dp += w * wx.bt[i];
+                    Wsum += w;
+                    T = T * ((1.0f - al) + 1e-10f);
+                }
+            }
+            __syncwarp();
+        }
+        if (has && jl == 0) {
+            float b0 = 1.f, b1 = 1.f, b2 = 1.f;
+            if (a.bg) { b0 = a.bg[ray * 3]; b1 = a.bg[ray * 3 + 1]; b2 = a.bg[ray * 3 + 2]; }
+            a.rgb[ray * 3 + 0] = Cr + T * b0;
+            a.rgb[ray * 3 + 1] = Cg + T * b1;
+            a.rgb[ray * 3 + 2] = Cb + T * b2;
+            a.depth[ray] = Dp;
+            a.alpha[ray] = Wsum;
+            a.s_count[ray] = min(ray_count, IA_MAX_SAMPLES);
+        }
+    }
+    if (a.stats) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            st_gather += __shfl_xor_sync(kFull, st_gather, o);
+            st_roots += __shfl_xor_sync(kFull, st_roots, o);
+            st_samples += __shfl_xor_sync(kFull, st_samples, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.stats->gathers, (unsigned long long)st_gather);
+            atomicAdd(&a.stats->net_evals, (unsigned long long)st_roots);
+            atomicAdd(&a.stats->samples, (unsigned long long)st_samples);
+        }
+    }
+}
+
+// ================================================================================================
+// compositing backward: per ray, upstream grads of (rgb, depth, alpha, weights) -> per-sample (d sigma, d rgb),
+// compacted into the sample list the network backward consumes
+// ================================================================================================
+struct CompBwdArgs {
+    int n_rays;
+    const float* near; const float* far; const float* bg; const float* noise;
+    const float* s_sigma; const float* s_rgb; const float* s_xc; const float* s_z; const int* s_count; const int8_t* s_best;
+    const float* g_rgb; const float* g_depth; const float* g_alpha; const float* g_weights;  // upstream (nullable)
+    float* l_xc; float* l_dsigma; float* l_drgb; int* l_count;  // compact output list
+};
+
+__global__ void __launch_bounds__(128) composite_bwd_kernel(CompBwdArgs a) {
+    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= a.n_rays) return;
+    const int cnt = a.s_count[ray];
+    if (cnt == 0) return;
+    const float dt = (a.far[ray] - a.near[ray]) / (float)IA_MAX_SAMPLES;
+    const long base = (long)ray * IA_MAX_SAMPLES;
+    float gc[3] = {0, 0, 0}, gd = 0, ga = 0;
+    if (a.g_rgb) { gc[0] = a.g_rgb[ray * 3]; gc[1] = a.g_rgb[ray * 3 + 1]; gc[2] = a.g_rgb[ray * 3 + 2]; }
+    if (a.g_depth) gd = a.g_depth[ray];
+    if (a.g_alpha) ga = a.g_alpha[ray];
+    float b[3] = {1.f, 1.f, 1.f};
+    if (a.bg) { b[0] = a.bg[ray * 3]; b[1] = a.bg[ray * 3 + 1]; b[2] = a.bg[ray * 3 + 2]; }
+    // forward sweep for T_end, then backward sweep; T_s recomputed by division-free re-multiplication:
+    // keep the running products in a small local array (cnt <= 256) -> recompute instead: two passes
+    float T = 1.f;
+    int nvalid = 0;
+    for (int s = 0; s < cnt; s++) {
+        float sig = a.s_sigma[base + s];
+        if (a.noise) sig = sig + a.noise[base + s];
+        const float al = 1.0f - expf(-fmaxf(sig, 0.f) * dt);
+        T = T * ((1.0f - al) + 1e-10f);
+        nvalid += a.s_best[base + s] >= 0 ? 1 : 0;
+    }
+    if (nvalid == 0) return;
+    int pos = atomicAdd(a.l_count, nvalid) + nvalid;  // fill this ray's block back to front
+    // S = dL/dT entering the next sample; start with the background term
+    float S = gc[0] * b[0] + gc[1] * b[1] + gc[2] * b[2];
+    float Tn = T;  // T after sample s
+    for (int s = cnt - 1; s >= 0; s--) {
+        float sig = a.s_sigma[base + s];
+        if (a.noise) sig = sig + a.noise[base + s];
+        const float pre = fmaxf(sig, 0.f);
+        const float e = expf(-pre * dt);
+        const float al = 1.0f - e;
+        const float f = (1.0f - al) + 1e-10f;
+        const float Tb = Tn / f;  // T before sample s
+        const float c0 = a.s_rgb[(base + s) * 3], c1 = a.s_rgb[(base + s) * 3 + 1], c2 = a.s_rgb[(base + s) * 3 + 2];
+        float Gs = gc[0] * c0 + gc[1] * c1 + gc[2] * c2 + gd * a.s_z[base + s] + ga;
+        if (a.g_weights) Gs += a.g_weights[base + s];
+        const float dLdf = S * Tb;
+        const float dLdal = Gs * Tb - dLdf;
+        S = S * f + Gs * al;
+        Tn = Tb;
+        if (a.s_best[base + s] >= 0) {
+            const float dsig = sig > 0.f ? dLdal * e * dt : 0.f;  // d alpha / d sigma = exp(-tau) * dt through the relu
+            const float w = al * Tb;
+            pos--;
+            a.l_xc[pos * 3] = a.s_xc[(base + s) * 3]; a.l_xc[pos * 3 + 1] = a.s_xc[(base + s) * 3 + 1]; a.l_xc[pos * 3 + 2] = a.s_xc[(base + s) * 3 + 2];
+            a.l_dsigma[pos] = dsig;
+            a.l_drgb[pos * 3] = w * gc[0]; a.l_drgb[pos * 3 + 1] = w * gc[1]; a.l_drgb[pos * 3 + 2] = w * gc[2];
+        }
+    }
+}
+
+// ================================================================================================
+// network backward on a list of canonical points with upstream (d sigma, d rgb)
+// ================================================================================================
+struct NgpBwdArgs {
+    SceneDev sd;
+    const float* xc; const float* dsigma; const float* drgb; const int* count; int capacity;
+    float grad_scale;       // upstream grads are multiplied by this before the fp16 dgrad chain
+    float* grad_enc;        // [3072 + 2*total] fp32, accumulated (+=)
+    __half* scratch;        // [capacity][kRowHalfs]
+};
+
+__device__ __forceinline__ float mask_pos(float v, uint32_t packed, bool high) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&packed);
+    const float a = high ? __high2float(h) : __low2float(h);
+    return a > 0.f ? v : 0.f;
+}
+// dZ = dH (.) (h > 0), packed as the A fragments of the next dgrad MMA; h given as the forward A fragments
+__device__ __forceinline__ void mask_chain(float acc[8][4], const uint32_t h[4][4], uint32_t out[4][4]) {
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+        acc[2 * kt][0] = mask_pos(acc[2 * kt][0], h[kt][0], false); acc[2 * kt][1] = mask_pos(acc[2 * kt][1], h[kt][0], true);
+        acc[2 * kt][2] = mask_pos(acc[2 * kt][2], h[kt][1], false); acc[2 * kt][3] = mask_pos(acc[2 * kt][3], h[kt][1], true);
+        acc[2 * kt + 1][0] = mask_pos(acc[2 * kt + 1][0], h[kt][2], false); acc[2 * kt + 1][1] = mask_pos(acc[2 * kt + 1][1], h[kt][2], true);
+        acc[2 * kt + 1][2] = mask_pos(acc[2 * kt + 1][2], h[kt][3], false); acc[2 * kt + 1][3] = mask_pos(acc[2 * kt + 1][3], h[kt][3], true);
+        out[kt][0] = pack_h2(acc[2 * kt][0], acc[2 * kt][1]);
+        out[kt][1] = pack_h2(acc[2 * kt][2], acc[2 * kt][3]);
+        out[kt][2] = pack_h2(acc[2 * kt + 1][0], acc[2 * kt + 1][1]);
+        out[kt][3] = pack_h2(acc[2 * kt + 1][2], acc[2 * kt + 1][3]);
+    }
+}
+
+constexpr int kBwdWarps = 8;
+
+struct BwdWarpSmem {
+    __align__(16) __half At[32][kW1Stride];
+    float dEnc[32][33];
+};
+struct BwdSmem {
+    __align__(16) __half W[kMlpAllHalfs];
+    float cs[8];
+    BwdWarpSmem w[kBwdWarps];
+};
+
+// one 16-row tile: forward recompute (keeping fragments), dgrad chain, scratch rows, dEnc to shared memory
+__device__ __forceinline__ void mlp_bwd_tile16(const __half* __restrict__ At, const __half* __restrict__ Wsm, int lane, int mt,
+                                               float dsig_lane, float dr_lane, float dg_lane, float db_lane, float gscale,
+                                               __half* __restrict__ scratch, long row0, int nrows, float (*dEnc)[33]) {
+    const int g = lane >> 2, t = lane & 3;
+    // ---------------- forward recompute ----------------
+    uint32_t a1[2][4];
+#pragma unroll
+    for (int kt = 0; kt < 2; kt++) {
+        const __half* p0 = At + g * kW1Stride + kt * 16 + 2 * t;
+        const __half* p1 = At + (g + 8) * kW1Stride + kt * 16 + 2 * t;
+        a1[kt][0] = *reinterpret_cast<const uint32_t*>(p0);
+        a1[kt][1] = *reinterpret_cast<const uint32_t*>(p1);
+        a1[kt][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+        a1[kt][3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
+    }
+    float acc[8][4];
+    uint32_t aH1[4][4], aH2[4][4], aH3[4][4], c3[1][4];
+    layer_n64<2>(Wsm + kW1Off, kW1Stride, a1, g, t, acc);
+    chain_relu(acc, aH1);
+    float o[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+        o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < 4; kt++) {
+            uint32_t b0, b1;
+            load_b(Wsm + kW2Off, kW2Stride, nt, kt, g, t, b0, b1);
+            mma16816(o[nt], aH1[kt], b0, b1);
+        }
+    }
+    {
+        __half2 h00 = __floats2half2_rn(o[0][0], o[0][1]);
+        __half2 h01 = __floats2half2_rn(o[0][2], o[0][3]);
+        if (t == 0) {
+            h00 = __halves2half2(__float2half_rn(1.0f), __high2half(h00));
+            h01 = __halves2half2(__float2half_rn(1.0f), __high2half(h01));
+        }
+        c3[0][0] = *reinterpret_cast<uint32_t*>(&h00);
+        c3[0][1] = *reinterpret_cast<uint32_t*>(&h01);
+        c3[0][2] = pack_h2(o[1][0], o[1][1]);
+        c3[0][3] = pack_h2(o[1][2], o[1][3]);
+    }
+    layer_n64<1>(Wsm + kW3Off, kW3Stride, c3, g, t, acc);
+    chain_relu(acc, aH2);
+    layer_n64<4>(Wsm + kW4Off, kW4Stride, aH2, g, t, acc);
+    chain_relu(acc, aH3);
+    float c5[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+        uint32_t b0, b1;
+        load_b(Wsm + kW5Off, kW5Stride, 0, kt, g, t, b0, b1);
+        mma16816(c5, aH3[kt], b0, b1);
+    }
+    // ---------------- upstream grads into fragment layout ----------------
+    const int rA = 16 * mt + g, rB = rA + 8;
+    const float dsA = __shfl_sync(kFull, dsig_lane, rA) * gscale, dsB = __shfl_sync(kFull, dsig_lane, rB) * gscale;
+    const float drA = __shfl_sync(kFull, dr_lane, rA), drB = __shfl_sync(kFull, dr_lane, rB);
+    const float dgA = __shfl_sync(kFull, dg_lane, rA), dgB = __shfl_sync(kFull, dg_lane, rB);
+    const float dbA = __shfl_sync(kFull, db_lane, rA), dbB = __shfl_sync(kFull, db_lane, rB);
+    float d5[4] = {0.f, 0.f, 0.f, 0.f};  // (row g: cols 2t,2t+1), (row g+8: ...)
+    {
+        auto dsgm = [](float x) { const float s = 1.0f / (1.0f + expf(-x)); return s * (1.0f - s); };
+        if (t == 0) {
+            d5[0] = drA * dsgm(c5[0]) * gscale; d5[1] = dgA * dsgm(c5[1]) * gscale;
+            d5[2] = drB * dsgm(c5[2]) * gscale; d5[3] = dgB * dsgm(c5[3]) * gscale;
+        } else if (t == 1) {
+            d5[0] = dbA * dsgm(c5[0]) * gscale; d5[2] = dbB * dsgm(c5[2]) * gscale;
+        }
+    }
+    const bool okA = rA < nrows, okB = rB < nrows;
+    __half* rowA = scratch + (row0 + 16 * mt + g) * kRowHalfs;
+    __half* rowB = scratch + (row0 + 16 * mt + g + 8) * kRowHalfs;
+    uint32_t aD[4][4];
+    // ---------------- layer 5: dH3 = dO5 . W5 ----------------
+    uint32_t a5[1][4] = {{pack_h2(d5[0], d5[1]), pack_h2(d5[2], d5[3]), 0u, 0u}};
+    if (okA) *reinterpret_cast<uint32_t*>(rowA + kOffD5 + 2 * t) = a5[0][0];
+    if (okB) *reinterpret_cast<uint32_t*>(rowB + kOffD5 + 2 * t) = a5[0][1];
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+        if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffH3 + kt * 16 + 2 * t) = aH3[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffH3 + kt * 16 + 8 + 2 * t) = aH3[kt][2]; }
+        if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffH3 + kt * 16 + 2 * t) = aH3[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffH3 + kt * 16 + 8 + 2 * t) = aH3[kt][3]; }
+    }
+    layer_n64<1>(Wsm + kW5TOff, kW5TStride, a5, g, t, acc);
+    mask_chain(acc, aH3, aD);  // dZ3
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+        if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffD4 + kt * 16 + 2 * t) = aD[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffD4 + kt * 16 + 8 + 2 * t) = aD[kt][2]; }
+        if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffD4 + kt * 16 + 2 * t) = aD[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffD4 + kt * 16 + 8 + 2 * t) = aD[kt][3]; }
+        if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffH2 + kt * 16 + 2 * t) = aH2[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffH2 + kt * 16 + 8 + 2 * t) = aH2[kt][2]; }
+        if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffH2 + kt * 16 + 2 * t) = aH2[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffH2 + kt * 16 + 8 + 2 * t) = aH2[kt][3]; }
+    }
+    // ---------------- layer 4: dH2 = dZ3 . W4 ----------------
+    layer_n64<4>(Wsm + kW4TOff, kW4TStride, aD, g, t, acc);
+    mask_chain(acc, aH2, aD);  // dZ2'
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+        if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffD3 + kt * 16 + 2 * t) = aD[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffD3 + kt * 16 + 8 + 2 * t) = aD[kt][2]; }
+        if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffD3 + kt * 16 + 2 * t) = aD[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffD3 + kt * 16 + 8 + 2 * t) = aD[kt][3]; }
+    }
+    if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffC3 + 2 * t) = c3[0][0]; *reinterpret_cast<uint32_t*>(rowA + kOffC3 + 8 + 2 * t) = c3[0][2]; }
+    if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffC3 + 2 * t) = c3[0][1]; *reinterpret_cast<uint32_t*>(rowB + kOffC3 + 8 + 2 * t) = c3[0][3]; }
+    // ---------------- layer 3: d(out16) = dZ2' . W3'   (N = 16) ----------------
+    float d2[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+        d2[nt][0] = d2[nt][1] = d2[nt][2] = d2[nt][3] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < 4; kt++) {
+            uint32_t b0, b1;
+            load_b(Wsm + kW3TOff, kW3TStride, nt, kt, g, t, b0, b1);
+            mma16816(d2[nt], aD[kt], b0, b1);
+        }
+    }
+    if (t == 0) { d2[0][0] = dsA; d2[0][2] = dsB; }  // column 0 of the density-net output is sigma
+    uint32_t a2[1][4] = {{pack_h2(d2[0][0], d2[0][1]), pack_h2(d2[0][2], d2[0][3]), pack_h2(d2[1][0], d2[1][1]), pack_h2(d2[1][2], d2[1][3])}};
+    if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffD2 + 2 * t) = a2[0][0]; *reinterpret_cast<uint32_t*>(rowA + kOffD2 + 8 + 2 * t) = a2[0][2]; }
+    if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffD2 + 2 * t) = a2[0][1]; *reinterpret_cast<uint32_t*>(rowB + kOffD2 + 8 + 2 * t) = a2[0][3]; }
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+        if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffH1 + kt * 16 + 2 * t) = aH1[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffH1 + kt * 16 + 8 + 2 * t) = aH1[kt][2]; }
+        if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffH1 + kt * 16 + 2 * t) = aH1[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffH1 + kt * 16 + 8 + 2 * t) = aH1[kt][3]; }
+    }
+    // ---------------- layer 2: dH1 = d(out16) . W2 ----------------
+    layer_n64<1>(Wsm + kW2TOff, kW2TStride, a2, g, t, acc);
+    mask_chain(acc, aH1, aD);  // dZ1
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+        if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffD1 + kt * 16 + 2 * t) = aD[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffD1 + kt * 16 + 8 + 2 * t) = aD[kt][2]; }
+        if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffD1 + kt * 16 + 2 * t) = aD[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffD1 + kt * 16 + 8 + 2 * t) = aD[kt][3]; }
+    }
+#pragma unroll
+    for (int kt = 0; kt < 2; kt++) {
+        if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffEnc + kt * 16 + 2 * t) = a1[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffEnc + kt * 16 + 8 + 2 * t) = a1[kt][2]; }
+        if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffEnc + kt * 16 + 2 * t) = a1[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffEnc + kt * 16 + 8 + 2 * t) = a1[kt][3]; }
+    }
+    // ---------------- layer 1: dEnc = dZ1 . W1   (N = 32) ----------------
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kt = 0; kt < 4; kt++) {
+            uint32_t b0, b1;
+            load_b(Wsm + kW1TOff, kW1TStride, nt, kt, g, t, b0, b1);
+            mma16816(e, aD[kt], b0, b1);
+        }
+        dEnc[16 * mt + g][nt * 8 + 2 * t] = e[0]; dEnc[16 * mt + g][nt * 8 + 2 * t + 1] = e[1];
+        dEnc[16 * mt + g + 8][nt * 8 + 2 * t] = e[2]; dEnc[16 * mt + g + 8][nt * 8 + 2 * t + 1] = e[3];
+    }
+}
+
+__global__ void __launch_bounds__(kBwdWarps * 32, 1) ngp_backward_kernel(const __grid_constant__ NgpBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kMlpAllHalfs / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(sm.W)[i] = reinterpret_cast<const uint32_t*>(a.sd.s.mlp_h)[i];
+    if (threadIdx.x < 3) { sm.cs[threadIdx.x] = a.sd.s.net_center[threadIdx.x]; sm.cs[3 + threadIdx.x] = a.sd.s.net_scale[threadIdx.x]; }
+    __syncthreads();
+    const int count = min(*a.count, a.capacity);
+    const __half2* table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
+    BwdWarpSmem& ws = sm.w[warp];
+    const float inv_scale = 1.0f / a.grad_scale;
+    float* ggrid = a.grad_enc + IA_ENC_MLP_PARAMS;
+    const int n_tiles = (count + 31) / 32;
+    for (int tile = blockIdx.x * kBwdWarps + warp; tile < n_tiles; tile += gridDim.x * kBwdWarps) {
+        const int p = tile * 32 + lane;
+        const bool has = p < count;
+        const int nrows = min(32, count - tile * 32);
+        float n0 = 0, n1 = 0, n2 = 0, dsig = 0, dr = 0, dg = 0, db = 0;
+        __half2* arow = reinterpret_cast<__half2*>(&ws.At[lane][0]);
+        if (has) {
+            n0 = fminf(fmaxf((a.xc[p * 3] - sm.cs[0]) / sm.cs[3] + 0.5f, 0.f), 1.f);
+            n1 = fminf(fmaxf((a.xc[p * 3 + 1] - sm.cs[1]) / sm.cs[4] + 0.5f, 0.f), 1.f);
+            n2 = fminf(fmaxf((a.xc[p * 3 + 2] - sm.cs[2]) / sm.cs[5] + 0.5f, 0.f), 1.f);
+            dsig = a.dsigma[p]; dr = a.drgb[p * 3]; dg = a.drgb[p * 3 + 1]; db = a.drgb[p * 3 + 2];
+#pragma unroll 4
+            for (int l = 0; l < kLevels; l++) arow[l] = hash_encode_level(table, a.sd.hl, l, n0, n1, n2);
+        } else {
+#pragma unroll
+            for (int l = 0; l < kLevels; l++) arow[l] = __floats2half2_rn(0.f, 0.f);
+        }
+        __syncwarp();
+        mlp_bwd_tile16(&ws.At[0][0], sm.W, lane, 0, dsig, dr, dg, db, a.grad_scale, a.scratch, (long)tile * 32, nrows, ws.dEnc);
+        mlp_bwd_tile16(&ws.At[16][0], sm.W, lane, 1, dsig, dr, dg, db, a.grad_scale, a.scratch, (long)tile * 32, nrows, ws.dEnc);
+        __syncwarp();
+        // ---- hash-grid gradient scatter (lane = sample); samples without upstream gradient contribute nothing ----
+        if (has && (dsig != 0.f || dr != 0.f || dg != 0.f || db != 0.f)) {
+#pragma unroll 1
+            for (int l = 0; l < kLevels; l++) {
+                const float s = a.sd.hl.scale[l];
+                const float px = __fmaf_rn(n0, s, 0.5f), py = __fmaf_rn(n1, s, 0.5f), pz = __fmaf_rn(n2, s, 0.5f);
+                const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
+                const uint32_t cx = (uint32_t)flx, cy = (uint32_t)fly, cz = (uint32_t)flz;
+                const float wx = px - flx, wy = py - fly, wz = pz - flz;
+                const uint32_t res = a.sd.hl.res[l], hs = a.sd.hl.size[l];
+                const float g0 = ws.dEnc[lane][2 * l] * inv_scale, g1 = ws.dEnc[lane][2 * l + 1] * inv_scale;
+                float2* tb = reinterpret_cast<float2*>(ggrid) + a.sd.hl.offset[l];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float wt = (((k & 1) ? wx : 1.f - wx) * ((k & 2) ? wy : 1.f - wy)) * ((k & 4) ? wz : 1.f - wz);
+                    const uint32_t idx = grid_index(cx + (k & 1), cy + ((k >> 1) & 1), cz + (k >> 2), res, hs);
+                    atomicAdd(tb + idx, make_float2(wt * g0, wt * g1));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// weight gradients: dW_l[o][i] += sum_rows dZ_l[row][o] * In_l[row][i] from the scratch rows
+__global__ void __launch_bounds__(256) wgrad_kernel(const __half* __restrict__ scratch, const int* __restrict__ count_p, int capacity,
+                                                    float inv_scale, float* __restrict__ grad_enc, float* __restrict__ grad_col) {
+    constexpr int kChunk = 32;
+    __shared__ __align__(16) __half rows[kChunk][kRowHalfs];
+    const int t = threadIdx.x;
+    const int count = min(*count_p, capacity);
+    float a4[16], a1[8], a2[4], a3[4], a5[2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a4[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a1[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { a2[i] = 0.f; a3[i] = 0.f; }
+    a5[0] = a5[1] = 0.f;
+    const int o4 = t / 4, i4 = (t % 4) * 16;   // W4 [64][64]
+    const int o1 = t / 4, i1 = (t % 4) * 8;    // W1 [64][32]
+    const int o2 = t / 16, i2 = (t % 16) * 4;  // W2 [16][64]
+    const int o3 = t / 4, i3 = (t % 4) * 4;    // W3' [64][16]
+    const int o5 = t / 32, i5 = (t % 32) * 2;  // W5 [8][64]
+    for (int base = blockIdx.x * kChunk; base < count; base += gridDim.x * kChunk) {
+        const int n = min(kChunk, count - base);
+        __syncthreads();
+        const uint4* src = reinterpret_cast<const uint4*>(scratch + (long)base * kRowHalfs);
+        uint4* dst = reinterpret_cast<uint4*>(&rows[0][0]);
+        for (int i = t; i < n * (kRowHalfs / 8); i += 256) dst[i] = src[i];
+        __syncthreads();
+        for (int r = 0; r < n; r++) {
+            const __half* row = rows[r];
+            const float d4 = __half2float(row[kOffD4 + o4]);
+#pragma unroll
+            for (int i = 0; i < 16; i++) a4[i] = __fmaf_rn(d4, __half2float(row[kOffH2 + i4 + i]), a4[i]);
+            const float d1 = __half2float(row[kOffD1 + o1]);
+#pragma unroll
+            for (int i = 0; i < 8; i++) a1[i] = __fmaf_rn(d1, __half2float(row[kOffEnc + i1 + i]), a1[i]);
+            const float d2 = __half2float(row[kOffD2 + o2]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) a2[i] = __fmaf_rn(d2, __half2float(row[kOffH1 + i2 + i]), a2[i]);
+            const float d3 = __half2float(row[kOffD3 + o3]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) a3[i] = __fmaf_rn(d3, __half2float(row[kOffC3 + i3 + i]), a3[i]);
+            const float d5 = __half2float(row[kOffD5 + o5]);
+#pragma unroll
+            for (int i = 0; i < 2; i++) a5[i] = __fmaf_rn(d5, __half2float(row[kOffH3 + i5 + i]), a5[i]);
+        }
+    }
+    // flush (tcnn parameter order; W3 column un-rotation: column 0 of W3' is the pad column 15 of W3)
+#pragma unroll
+    for (int i = 0; i < 16; i++) atomicAdd(&grad_col[1024 + o4 * 64 + i4 + i], a4[i] * inv_scale);
+#pragma unroll
+    for (int i = 0; i < 8; i++) atomicAdd(&grad_enc[o1 * 32 + i1 + i], a1[i] * inv_scale);
+#pragma unroll
+    for (int i = 0; i < 4; i++) atomicAdd(&grad_enc[2048 + o2 * 64 + i2 + i], a2[i] * inv_scale);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int c = i3 + i;
+        atomicAdd(&grad_col[o3 * 16 + (c == 0 ? 15 : c - 1)], a3[i] * inv_scale);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) atomicAdd(&grad_col[1024 + 4096 + o5 * 64 + i5 + i], a5[i] * inv_scale);
+}
+
+// ================================================================================================
+// fused dense Adam (torch.optim.Adam semantics, DNeRF.py:46-50) + fp16 working-copy refresh
+// ================================================================================================
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long n, float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
+                            float inv_grad_scale, const float* __restrict__ found_inf) {
+    if (found_inf && *found_inf != 0.f) return;  // GradScaler: skip the step on inf/NaN gradients
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * inv_grad_scale;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - (lr / bc1) * (mi / denom);
+}
+
+__global__ void grad_finite_kernel(const float* __restrict__ g, long n, float* __restrict__ found_inf) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    for (long j = i; j < n; j += (long)gridDim.x * blockDim.x) bad |= !isfinite(g[j]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *found_inf = 1.f;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int ia_train_fwd(const IaScene* scene, const float* rays_o, const float* rays_d, const float* near, const float* far,
+                 int n_rays, const float* bg, const float* jitter, const float* noise, float* rgb, float* depth,
+                 float* alpha, float* weights, float* s_sigma, float* s_rgb, float* s_xc, float* s_z, int* s_count,
+                 int8_t* s_best, void* workspace, IaStats* stats, ia_stream_t stream) {
+    IA_REQUIRE(n_rays >= 0);
+    if (n_rays == 0) return IA_OK;
+    IA_REQUIRE(rays_o && rays_d && near && far && rgb && depth && alpha && weights && workspace);
+    IA_REQUIRE(s_sigma && s_rgb && s_xc && s_z && s_count && s_best);
+    TrainFwdArgs a;
+    int rc = make_scene_dev(scene, a.sd, true);
+    if (rc) return rc;
+    a.rays_o = rays_o; a.rays_d = rays_d; a.near = near; a.far = far; a.bg = bg; a.jitter = jitter; a.noise = noise;
+    a.n_rays = n_rays; a.rgb = rgb; a.depth = depth; a.alpha = alpha; a.weights = weights;
+    a.s_sigma = s_sigma; a.s_rgb = s_rgb; a.s_xc = s_xc; a.s_z = s_z; a.s_count = s_count; a.s_best = s_best;
+    a.tile_counter = reinterpret_cast<int*>(workspace);
+    a.stats = stats;
+    cudaStream_t st = (cudaStream_t)stream;
+    IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+    constexpr int kW = 8, kR = 4;
+    const size_t smem = sizeof(TrainSmem<kW>);
+    static bool attr_set = false;
+    if (!attr_set) {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(train_fwd_kernel<kW, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int n_tiles = (n_rays + kR - 1) / kR;
+    int grid = sm_count();
+    if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    grid = min(grid, (n_tiles + kW - 1) / kW);
+    train_fwd_kernel<kW, kR><<<grid, kW * 32, smem, st>>>(a);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_composite_bwd(int n_rays, const float* near, const float* far, const float* bg, const float* noise,
+                     const float* s_sigma, const float* s_rgb, const float* s_xc, const float* s_z, const int* s_count,
+                     const int8_t* s_best, const float* g_rgb, const float* g_depth, const float* g_alpha,
+                     const float* g_weights, float* l_xc, float* l_dsigma, float* l_drgb, int* l_count,
+                     ia_stream_t stream) {
+    IA_REQUIRE(n_rays >= 0);
+    if (n_rays == 0) return IA_OK;
+    IA_REQUIRE(near && far && s_sigma && s_rgb && s_xc && s_z && s_count && s_best && l_xc && l_dsigma && l_drgb && l_count);
+    CompBwdArgs a;
+    a.n_rays = n_rays; a.near = near; a.far = far; a.bg = bg; a.noise = noise;
+    a.s_sigma = s_sigma; a.s_rgb = s_rgb; a.s_xc = s_xc; a.s_z = s_z; a.s_count = s_count; a.s_best = s_best;
+    a.g_rgb = g_rgb; a.g_depth = g_depth; a.g_alpha = g_alpha; a.g_weights = g_weights;
+    a.l_xc = l_xc; a.l_dsigma = l_dsigma; a.l_drgb = l_drgb; a.l_count = l_count;
+    composite_bwd_kernel<<<(n_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+size_t ia_ngp_backward_scratch_bytes(int capacity) { return (size_t)capacity * kRowHalfs * sizeof(__half); }
+
+int ia_ngp_backward(const IaScene* scene, const float* xc, const float* dsigma, const float* drgb, const int* count,
+                    int capacity, float grad_scale, float* grad_enc, float* grad_col, void* scratch, ia_stream_t stream) {
+    IA_REQUIRE(capacity >= 0);
+    if (capacity == 0) return IA_OK;
+    IA_REQUIRE(xc && dsigma && drgb && count && grad_enc && grad_col && scratch && grad_scale > 0.f);
+    IA_REQUIRE(scene && scene->table_h && scene->mlp_h && scene->net_center && scene->net_scale);
+    NgpBwdArgs a;
+    a.sd.s = *scene;
+    host_hash_levels(a.sd.hl, nullptr);
+    a.sd.filter_thr = 0.f;
+    a.xc = xc; a.dsigma = dsigma; a.drgb = drgb; a.count = count; a.capacity = capacity; a.grad_scale = grad_scale;
+    a.grad_enc = grad_enc; a.scratch = reinterpret_cast<__half*>(scratch);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sizeof(BwdSmem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(ngp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int sms = sm_count();
+    if (sms <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    const int n_tiles = (capacity + 31) / 32;
+    ngp_backward_kernel<<<min(sms, (n_tiles + kBwdWarps - 1) / kBwdWarps), kBwdWarps * 32, smem, st>>>(a);
+    wgrad_kernel<<<min(sms * 2, (capacity + 31) / 32), 256, 0, st>>>(a.scratch, count, capacity, 1.0f / grad_scale, grad_enc, grad_col);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1,
+                 float beta2, float eps, int step, float inv_grad_scale, const float* found_inf, ia_stream_t stream) {
+    IA_REQUIRE(n >= 0 && step >= 1);
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(params && grads && exp_avg && exp_avg_sq);
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                              beta2, eps, bc1, bc2_sqrt, inv_grad_scale, found_inf);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_grad_check_finite(const float* grads, long n, float* found_inf, ia_stream_t stream) {
+    IA_REQUIRE(n >= 0 && found_inf);
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(grads != nullptr);
+    grad_finite_kernel<<<sm_count() > 0 ? sm_count() * 8 : 1024, 256, 0, (cudaStream_t)stream>>>(grads, n, found_inf);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+}  // extern "C"

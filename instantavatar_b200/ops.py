@@ -161,3 +161,68 @@ def ngp_forward(scene: Scene, x):
     s = scene.c_struct()
     _lib.count(1); check(lib().ia_ngp_forward(C.byref(s), ptr(x, f32), C.c_int(n), ptr(sigma), ptr(rgb), stream()))
     return rgb, sigma
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# training path
+# ------------------------------------------------------------------------------------------------------------------
+def train_fwd(scene: Scene, rays_o, rays_d, near, far, bg=None, jitter=None, noise=None, stats=None, workspace=None):
+    """Fused Raymarcher.render_train (raymarcher_acc.py:140-186).  Returns (outputs, saved-for-backward)."""
+    n = rays_o.numel() // 3
+    dev = rays_o.device
+    S = _lib.IA_MAX_SAMPLES
+    out = {"rgb": torch.empty((n, 3), device=dev, dtype=f32), "depth": torch.empty(n, device=dev, dtype=f32),
+           "alpha": torch.empty(n, device=dev, dtype=f32), "weights": torch.empty((n, S), device=dev, dtype=f32)}
+    saved = {"sigma": torch.empty((n, S), device=dev, dtype=f32), "rgb": torch.empty((n, S, 3), device=dev, dtype=f32),
+             "xc": torch.empty((n, S, 3), device=dev, dtype=f32), "z": torch.empty((n, S), device=dev, dtype=f32),
+             "count": torch.empty(n, device=dev, dtype=torch.int32), "best": torch.empty((n, S), device=dev, dtype=torch.int8)}
+    if workspace is None:
+        workspace = torch.empty(64, device=dev, dtype=torch.int32)
+    s = scene.c_struct()
+    _lib.count(1); check(lib().ia_train_fwd(C.byref(s), ptr(rays_o, f32), ptr(rays_d, f32), ptr(near, f32), ptr(far, f32), C.c_int(n),
+                                            ptr(bg), ptr(jitter), ptr(noise), ptr(out["rgb"]), ptr(out["depth"]), ptr(out["alpha"]),
+                                            ptr(out["weights"]), ptr(saved["sigma"]), ptr(saved["rgb"]), ptr(saved["xc"]), ptr(saved["z"]),
+                                            ptr(saved["count"]), ptr(saved["best"]), ptr(workspace), ptr(stats), stream()))
+    return out, saved
+
+
+def composite_bwd(near, far, bg, noise, saved, g_rgb=None, g_depth=None, g_alpha=None, g_weights=None):
+    """autograd of the training compositing -> compact (xc, d sigma, d rgb) list + device count"""
+    n = near.numel()
+    dev = near.device
+    cap = n * _lib.IA_MAX_SAMPLES
+    l_xc = torch.empty((cap, 3), device=dev, dtype=f32); l_ds = torch.empty(cap, device=dev, dtype=f32)
+    l_dc = torch.empty((cap, 3), device=dev, dtype=f32); l_count = torch.zeros(1, device=dev, dtype=torch.int32)
+    c = lambda t: t.contiguous().float() if t is not None else None
+    g_rgb, g_depth, g_alpha, g_weights = c(g_rgb), c(g_depth), c(g_alpha), c(g_weights)
+    _lib.count(1); check(lib().ia_composite_bwd(C.c_int(n), ptr(near, f32), ptr(far, f32), ptr(bg), ptr(noise), ptr(saved["sigma"]),
+                                                ptr(saved["rgb"]), ptr(saved["xc"]), ptr(saved["z"]), ptr(saved["count"]), ptr(saved["best"]),
+                                                ptr(g_rgb), ptr(g_depth), ptr(g_alpha), ptr(g_weights), ptr(l_xc), ptr(l_ds), ptr(l_dc),
+                                                ptr(l_count), stream()))
+    return l_xc, l_ds, l_dc, l_count
+
+
+_SCRATCH = {}
+
+
+def ngp_backward(scene: Scene, xc, dsigma, drgb, count, grad_enc, grad_col, grad_scale=128.0):
+    """accumulate d loss / d (encoder.params, color_net.params) for a list of canonical points"""
+    cap = xc.shape[0]
+    dev = xc.device
+    nbytes = int(lib().ia_ngp_backward_scratch_bytes(C.c_int(cap)))
+    key = (dev.index, )
+    if key not in _SCRATCH or _SCRATCH[key].numel() < nbytes:
+        _SCRATCH[key] = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    s = scene.c_struct()
+    _lib.count(2); check(lib().ia_ngp_backward(C.byref(s), ptr(xc, f32), ptr(dsigma, f32), ptr(drgb, f32), ptr(count), C.c_int(cap),
+                                               C.c_float(grad_scale), ptr(grad_enc, f32), ptr(grad_col, f32), ptr(_SCRATCH[key]), stream()))
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, betas, eps, step, inv_grad_scale=1.0, found_inf=None):
+    _lib.count(1); check(lib().ia_adam_step(ptr(params, f32), ptr(grads, f32), ptr(exp_avg, f32), ptr(exp_avg_sq, f32),
+                                            C.c_long(params.numel()), C.c_float(lr), C.c_float(betas[0]), C.c_float(betas[1]),
+                                            C.c_float(eps), C.c_int(step), C.c_float(inv_grad_scale), ptr(found_inf), stream()))
+
+
+def grad_check_finite(grads, found_inf):
+    _lib.count(1); check(lib().ia_grad_check_finite(ptr(grads, f32), C.c_long(grads.numel()), ptr(found_inf, f32), stream()))

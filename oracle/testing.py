@@ -41,3 +41,10 @@ def upload(sc, device="cuda"):
 
 def oracle_model(sc, eval_mode=True):
     return lambda p: orender.deform_query(p, sc["frame"], sc["subj"], sc["net"], eval_mode)
+
+
+def oracle_model_aux(sc, eval_mode=False):
+    """model callable for oracle.render.render_train(return_aux=True)"""
+    def f(p, want_aux=False):
+        return orender.deform_query(p, sc["frame"], sc["subj"], sc["net"], eval_mode, return_aux=want_aux)
+    return f
