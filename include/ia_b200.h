@@ -161,7 +161,8 @@ int ia_ngp_backward(const IaScene* scene /*[host]*/, const float* xc, const floa
  * multiplied by inv_grad_scale (GradScaler unscale, DNeRF.py:157-158); if found_inf (device, nullable) is non-zero
  * the step is skipped.  ia_grad_check_finite sets *found_inf = 1 when any gradient is non-finite. */
 int ia_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1,
-                 float beta2, float eps, int step, float inv_grad_scale, const float* found_inf, ia_stream_t stream);
+                 float beta2, float eps, int step, float inv_grad_scale, const float* grad_scale_dev /*nullable: divides*/,
+                 const float* found_inf, ia_stream_t stream);
 int ia_grad_check_finite(const float* grads, long n, float* found_inf, ia_stream_t stream);
 
 #ifdef __cplusplus

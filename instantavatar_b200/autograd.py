@@ -16,11 +16,11 @@ GRAD_SCALE = 128.0  # internal loss scale of the fp16 dgrad chain (tiny-cuda-nn 
 
 class _RenderTrain(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, enc_params, col_params, scene, rays_o, rays_d, near, far, bg, jitter, noise, stats):
+    def forward(ctx, enc_params, col_params, scene, rays_o, rays_d, near, far, bg, jitter, noise, stats, accum=None):
         out, saved = ops.train_fwd(scene, rays_o, rays_d, near, far, bg, jitter, noise, stats)
         ctx.scene, ctx.saved, ctx.misc = scene, saved, (near, far, bg, noise)
         ctx.shapes = (enc_params.shape, col_params.shape)
-        ctx.mark_non_differentiable(out["depth"]) if False else None
+        ctx.accum = accum  # optional persistent (grad_enc, grad_col) buffers to accumulate into
         return out["rgb"], out["depth"], out["alpha"], out["weights"]
 
     @staticmethod
@@ -28,10 +28,13 @@ class _RenderTrain(torch.autograd.Function):
         near, far, bg, noise = ctx.misc
         l_xc, l_ds, l_dc, l_count = ops.composite_bwd(near, far, bg, noise, ctx.saved, g_rgb, g_depth, g_alpha, g_weights)
         dev = near.device
+        if ctx.accum is not None:
+            ops.ngp_backward(ctx.scene, l_xc, l_ds, l_dc, l_count, ctx.accum[0], ctx.accum[1], GRAD_SCALE)
+            return (None,) * 12
         g_enc = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32)
         g_col = torch.zeros(ctx.shapes[1], device=dev, dtype=torch.float32)
         ops.ngp_backward(ctx.scene, l_xc, l_ds, l_dc, l_count, g_enc, g_col, GRAD_SCALE)
-        return g_enc, g_col, None, None, None, None, None, None, None, None, None
+        return (g_enc, g_col) + (None,) * 10
 
 
 def render_train_fused(renderer, deformer, net, rays, noise, bg_color, jitter=None, noise_tensor=None, stats=None):
@@ -50,7 +53,8 @@ def render_train_fused(renderer, deformer, net, rays, noise, bg_color, jitter=No
         noise_tensor = noise * torch.randn((n, 256), device=near.device)
     bg = bg_color.reshape(-1, 3).float().contiguous() if bg_color is not None else None
     rgb, depth, alpha, weights = _RenderTrain.apply(net.encoder.params, net.color_net.params, scene, rays_o, rays_d, near, far, bg,
-                                                    jitter.contiguous(), noise_tensor.contiguous() if noise_tensor is not None else None, stats)
+                                                    jitter.contiguous(), noise_tensor.contiguous() if noise_tensor is not None else None, stats,
+                                                    net.grad_buffers())
     return {
         "rgb_coarse": rgb.reshape(rays.o.shape),
         "depth_coarse": depth.reshape(rays.near.shape),
@@ -63,10 +67,11 @@ class _DeformQueryTrain(torch.autograd.Function):
     """deformer(pts, net, eval_mode=False) with gradients w.r.t. the network parameters (DensityGrid.update regulariser)."""
 
     @staticmethod
-    def forward(ctx, enc_params, col_params, scene, pts):
+    def forward(ctx, enc_params, col_params, scene, pts, accum=None):
         rgb, sigma, xc, best = ops.deform_query(scene, pts, eval_mode=False, want_xc=True)
         ctx.scene, ctx.saved = scene, (xc, best)
         ctx.shapes = (enc_params.shape, col_params.shape)
+        ctx.accum = accum
         return rgb, sigma
 
     @staticmethod
@@ -77,12 +82,15 @@ class _DeformQueryTrain(torch.autograd.Function):
         g_sigma = torch.where(valid, g_sigma.contiguous().float(), torch.zeros_like(g_sigma)) if g_sigma is not None else torch.zeros(xc.shape[0], device=dev)
         g_rgb = (g_rgb.contiguous().float() * valid[:, None]) if g_rgb is not None else torch.zeros_like(xc)
         count = torch.full((1,), xc.shape[0], device=dev, dtype=torch.int32)
+        if ctx.accum is not None:
+            ops.ngp_backward(ctx.scene, xc, g_sigma.contiguous(), g_rgb.contiguous(), count, ctx.accum[0], ctx.accum[1], GRAD_SCALE)
+            return (None,) * 5
         g_enc = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32)
         g_col = torch.zeros(ctx.shapes[1], device=dev, dtype=torch.float32)
         ops.ngp_backward(ctx.scene, xc, g_sigma.contiguous(), g_rgb.contiguous(), count, g_enc, g_col, GRAD_SCALE)
-        return g_enc, g_col, None, None
+        return g_enc, g_col, None, None, None
 
 
 def deform_query_train(deformer, net, pts):
     scene = deformer.scene(net)
-    return _DeformQueryTrain.apply(net.encoder.params, net.color_net.params, scene, pts)
+    return _DeformQueryTrain.apply(net.encoder.params, net.color_net.params, scene, pts, net.grad_buffers())

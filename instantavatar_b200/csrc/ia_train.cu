@@ -593,10 +593,11 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const __half* __restrict__ s
 // ================================================================================================
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long n, float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
-                            float inv_grad_scale, const float* __restrict__ found_inf) {
+                            float inv_grad_scale, const float* __restrict__ grad_scale_dev, const float* __restrict__ found_inf) {
     if (found_inf && *found_inf != 0.f) return;  // GradScaler: skip the step on inf/NaN gradients
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (grad_scale_dev) inv_grad_scale = inv_grad_scale / *grad_scale_dev;
     const float gi = g[i] * inv_grad_scale;
     const float mi = beta1 * m[i] + (1.f - beta1) * gi;
     const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
@@ -700,14 +701,15 @@ int ia_ngp_backward(const IaScene* scene, const float* xc, const float* dsigma, 
 }
 
 int ia_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1,
-                 float beta2, float eps, int step, float inv_grad_scale, const float* found_inf, ia_stream_t stream) {
+                 float beta2, float eps, int step, float inv_grad_scale, const float* grad_scale_dev, const float* found_inf,
+                 ia_stream_t stream) {
     IA_REQUIRE(n >= 0 && step >= 1);
     if (n == 0) return IA_OK;
     IA_REQUIRE(params && grads && exp_avg && exp_avg_sq);
     const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
-                                                                              beta2, eps, bc1, bc2_sqrt, inv_grad_scale, found_inf);
+                                                                              beta2, eps, bc1, bc2_sqrt, inv_grad_scale, grad_scale_dev, found_inf);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

@@ -33,6 +33,12 @@ class DNeRFModel(torch.nn.Module):
         self.renderer.initialize(n_train_frames)
         self.global_step = 0
         self.image_width = 0
+        from ..optim import FusedAdam, GradScaler
+        from ..utils_loss import NeRFLoss
+        self.loss_fn = NeRFLoss()
+        self.optimizer = FusedAdam(self.net_coarse, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, max_epochs=30)
+        self.scaler = GradScaler(device)
+        self.world_size = 1
 
     def forward(self, batch, eval_mode=None, jitter=None, noise_tensor=None):
         """DNeRF.py:61-70"""
@@ -59,3 +65,41 @@ class DNeRFModel(torch.nn.Module):
         alpha = d["alpha_coarse"].reshape(-1, *img_size)
         counter = d["counter_coarse"].reshape(-1, *img_size)
         return rgb, depth, alpha, counter
+
+    def update_density_grid(self, jitter=None):
+        """DNeRF.py:99-110: every 20 steps refresh the train occupancy grid and return the density regulariser."""
+        N = 20
+        if self.global_step % N != 0:
+            return None
+        density, valid = self.renderer.density_grid_train.update(self.deformer, self.net_coarse, self.global_step, jitter)
+        inv = (~valid).float()
+        reg = N * (density * inv).sum() / inv.sum()  # == N * density[~valid].mean(), without the host-syncing mask index
+        if self.global_step < 500:
+            reg = reg + 0.5 * density.mean()
+        return reg
+
+    def training_step(self, batch, jitter=None, noise_tensor=None, grid_jitter=None):
+        """DNeRF.py:112-161 (manual optimisation: zero_grad, scaled backward, Adam step, scaler update).
+        With world_size > 1 the rays of `batch` are this rank's shard and gradients are all-reduced (sum) before
+        the step, which divides by world_size."""
+        self.train()
+        self.renderer.idx = int(batch.get("idx", 0)) if not torch.is_tensor(batch.get("idx", 0)) else 0
+        self.deformer.prepare_deformer(batch)
+        self.net_coarse.initialize(self.deformer.bbox)
+        self.optimizer.zero_grad()
+        reg = self.update_density_grid(grid_jitter)
+        predicts = self.forward(batch, eval_mode=False, jitter=jitter, noise_tensor=noise_tensor)
+        losses = self.loss_fn(predicts, batch)
+        loss = losses["loss"]
+        if reg is not None:
+            losses["reg"] = reg
+            loss = loss + reg
+        self.scaler.scale(loss).backward()
+        if self.world_size > 1:
+            import torch.distributed as dist
+            for g in self.net_coarse.grad_buffers():
+                dist.all_reduce(g)
+        self.optimizer.step(self.scaler, self.world_size)
+        self.scaler.update()
+        self.global_step += 1
+        return losses

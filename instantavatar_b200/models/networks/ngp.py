@@ -72,6 +72,15 @@ class NeRFNGPNet(nn.Module):
     def mark_dirty(self):
         self._dirty = True
 
+    def grad_buffers(self):
+        """persistent flat fp32 gradient buffers the fused backward accumulates into (aliased as `.grad`)"""
+        p, c = self.encoder.params, self.color_net.params
+        if p.grad is None or p.grad.device != p.device:
+            p.grad = torch.zeros_like(p)
+        if c.grad is None or c.grad.device != c.device:
+            c.grad = torch.zeros_like(c)
+        return p.grad, c.grad
+
     def load_flat_params(self, enc, col):
         with torch.no_grad():
             self.encoder.params.copy_(torch.as_tensor(enc, dtype=torch.float32))

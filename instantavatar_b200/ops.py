@@ -218,10 +218,10 @@ def ngp_backward(scene: Scene, xc, dsigma, drgb, count, grad_enc, grad_col, grad
                                                C.c_float(grad_scale), ptr(grad_enc, f32), ptr(grad_col, f32), ptr(_SCRATCH[key]), stream()))
 
 
-def adam_step(params, grads, exp_avg, exp_avg_sq, lr, betas, eps, step, inv_grad_scale=1.0, found_inf=None):
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, betas, eps, step, inv_grad_scale=1.0, found_inf=None, grad_scale_dev=None):
     _lib.count(1); check(lib().ia_adam_step(ptr(params, f32), ptr(grads, f32), ptr(exp_avg, f32), ptr(exp_avg_sq, f32),
                                             C.c_long(params.numel()), C.c_float(lr), C.c_float(betas[0]), C.c_float(betas[1]),
-                                            C.c_float(eps), C.c_int(step), C.c_float(inv_grad_scale), ptr(found_inf), stream()))
+                                            C.c_float(eps), C.c_int(step), C.c_float(inv_grad_scale), ptr(grad_scale_dev), ptr(found_inf), stream()))
 
 
 def grad_check_finite(grads, found_inf):

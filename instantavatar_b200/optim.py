@@ -1,0 +1,61 @@
+"""Fused dense Adam + device-side GradScaler for the two flat parameter tensors of NeRFNGPNet.
+
+Mirrors DNeRFModel.configure_optimizers (models/DNeRF.py:32-59): one torch.optim.Adam with lr 1e-2, betas (0.9, 0.99),
+eps 1e-15 (confs/SNARF_NGP.yaml:28-31), LambdaLR (1 - epoch/max_epochs)^1.5, and a manual GradScaler(init_scale=1024).
+Dense semantics are kept (momentum of untouched hash-grid entries keeps decaying); the step, the unscale and the
+inf/NaN skip run in one kernel per tensor with no host synchronisation.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class GradScaler:
+    """torch.cuda.amp.GradScaler semantics (growth 2x every 2000 clean steps, backoff 0.5) kept on the device"""
+
+    def __init__(self, device, init_scale=1024.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+        self.scale_t = torch.full((1,), init_scale, device=device, dtype=torch.float32)
+        self.growth_tracker = torch.zeros(1, device=device, dtype=torch.int32)
+        self.found_inf = torch.zeros(1, device=device, dtype=torch.float32)
+        self.gf, self.bf, self.gi = growth_factor, backoff_factor, growth_interval
+
+    def scale(self, loss):
+        return loss * self.scale_t
+
+    def update(self):
+        torch._amp_update_scale_(self.scale_t, self.growth_tracker, self.found_inf, self.gf, self.bf, self.gi)
+        self.found_inf.zero_()
+
+
+class FusedAdam:
+    def __init__(self, net, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, max_epochs=30):
+        self.net = net
+        self.base_lr, self.betas, self.eps = lr, betas, eps
+        self.max_epochs, self.epoch = max_epochs, 0
+        self.params = [net.encoder.params, net.color_net.params]
+        self.state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in self.params]
+        self.step_count = 0
+
+    @property
+    def lr(self):  # LambdaLR of DNeRF.py:52-55, stepped in on_validation_epoch_end only
+        return self.base_lr * (1 - self.epoch / self.max_epochs) ** 1.5
+
+    def scheduler_step(self):
+        self.epoch += 1
+
+    def zero_grad(self):
+        for g in self.net.grad_buffers():
+            g.zero_()
+
+    def step(self, scaler: GradScaler | None = None, world_size: int = 1):
+        self.step_count += 1
+        grads = self.net.grad_buffers()
+        if scaler is not None:
+            for g in grads:
+                ops.grad_check_finite(g, scaler.found_inf)
+        for p, g, (m, v) in zip(self.params, grads, self.state):
+            ops.adam_step(p.data, g, m, v, self.lr, self.betas, self.eps, self.step_count, 1.0 / world_size,
+                          scaler.found_inf if scaler is not None else None, scaler.scale_t if scaler is not None else None)
+        self.net.mark_dirty()

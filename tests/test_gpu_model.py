@@ -1,0 +1,94 @@
+"""GPU: the host-side mirror classes end to end (SMPL -> bone transforms -> field -> occupancy grid -> fused render,
+and a short training run)."""
+import numpy as np
+import pytest
+
+from oracle import render as orender
+from oracle import scene as oscene
+from oracle import testing as scene_util
+
+pytestmark = pytest.mark.gpu
+
+H = W = 128  # subsampled demo camera (every 4th pixel of the 512x512 frame)
+
+
+def make_model(frame=0):
+    import torch
+    from instantavatar_b200 import synthetic
+    from instantavatar_b200.models.dnerf import DNeRFModel
+    model = DNeRFModel(smpl_data=synthetic.smpl_dict_cached(0), device="cuda")
+    pose = synthetic.load_pose(frame)
+    o, d = synthetic.demo_camera_rays(512, 512)
+    idx = (np.arange(0, 512, 4)[:, None] * 512 + np.arange(0, 512, 4)[None]).ravel()
+    batch = {"rays_o": torch.from_numpy(o[idx][None]).cuda(), "rays_d": torch.from_numpy(d[idx][None]).cuda(),
+             "near": torch.zeros((1, len(idx)), device="cuda"), "far": torch.ones((1, len(idx)), device="cuda")}
+    batch.update({k: torch.from_numpy(v).cuda() for k, v in pose.items()})
+    return model, batch, idx
+
+
+def test_prepare_and_render_image_matches_oracle_pipeline():
+    import torch
+    from instantavatar_b200 import synthetic
+    sc = scene_util.oracle_scene(0)
+    model, batch, idx = make_model(0)
+    model.eval()
+    # feed the oracle's skinning-weight voxelisation so both sides start from the same subject state
+    model.deformer.initialize(batch["betas"], batch["betas"].device, lbs_voxel=torch.from_numpy(sc["subj"].lbs_voxel).cuda())
+    model.deformer.initialized = True
+    model.net_coarse.initialize(model.deformer.bbox)
+    model.net_coarse.load_flat_params(torch.from_numpy(sc["net"].enc).cuda(), torch.from_numpy(sc["net"].col).cuda())
+    jit = torch.from_numpy(sc["occ_jitter"]).cuda()
+    rgb, depth, alpha, counter = model.render_image_fast(dict(batch), (H, W), jitters=jit)
+    torch.cuda.synchronize()
+    # per-frame state vs the oracle (different BLAS / op order in the SMPL forward: ~1e-6)
+    np.testing.assert_allclose(model.deformer.tfs[0].cpu().numpy(), sc["frame"]["tfs"], atol=5e-6)
+    np.testing.assert_allclose(model.deformer.bbox.cpu().numpy(), sc["subj"].bbox, atol=1e-5)
+    np.testing.assert_allclose(torch.stack(model.deformer.get_bbox_deformed()).cpu().numpy(), sc["frame"]["bbox_deformed"], atol=1e-5)
+    occ = model.renderer.density_grid_test.density_field.cpu().numpy()
+    assert (occ != sc["occ"]).mean() < 2e-3  # a few boundary cells may flip under the 1e-6 input perturbation
+    fr = sc["frame"]
+    o, d, near, far = oscene.camera_rays(fr, 512, 512)
+    ref = orender.render_test(o[idx], d[idx], near[idx], far[idx], sc["occ"], fr["bbox_deformed"][0], fr["bbox_deformed"][1],
+                              scene_util.oracle_model(sc, True))
+    a, r = alpha.reshape(-1).cpu().numpy(), rgb.reshape(-1, 3).cpu().numpy()
+    assert np.mean(np.abs(a - ref["alpha"]) > 2e-2) < 5e-3
+    assert np.mean(np.abs(r - ref["rgb"]).max(-1) > 2e-2) < 5e-3
+    assert np.abs(a - ref["alpha"]).mean() < 1e-3
+
+
+def test_short_training_run_reduces_loss():
+    """200-iteration config of BASELINE.json in miniature: train the randomly initialised network against renders of
+    the analytic avatar; the loss must fall and stay finite (exercises grid updates, noise, GradScaler, Adam)."""
+    import torch
+    from instantavatar_b200 import synthetic
+    torch.manual_seed(0)
+    gt, batch, idx = make_model(0)
+    gt.eval()
+    gt.deformer.prepare_deformer(batch)
+    gt.net_coarse.initialize(gt.deformer.bbox)
+    bbox = gt.deformer.bbox.cpu().numpy().astype(np.float64)
+    enc, col = synthetic.analytic_avatar_params(gt.deformer.joints_cano[0].cpu().numpy(), (bbox[0] + bbox[1]) / 2, bbox[1] - bbox[0])
+    gt.net_coarse.load_flat_params(torch.from_numpy(enc).cuda(), torch.from_numpy(col).cuda())
+    rgb_gt, _, alpha_gt, _ = gt.render_image_fast(dict(batch), (H, W))
+    rgb_gt, alpha_gt = rgb_gt.reshape(-1, 3), alpha_gt.reshape(-1)
+    # rays in a box around the body (the reference's samplers concentrate on the mask)
+    ys, xs = np.arange(36, 96), np.arange(44, 86)
+    sel = torch.from_numpy((ys[:, None] * W + xs[None]).ravel()).cuda()
+
+    model, _, _ = make_model(0)
+    losses = []
+    for step in range(60):
+        pick = sel[torch.randint(0, len(sel), (1024,), device="cuda")]
+        b = dict(batch)
+        b["rays_o"], b["rays_d"] = batch["rays_o"][:, pick], batch["rays_d"][:, pick]
+        b["near"], b["far"] = batch["near"][:, pick], batch["far"][:, pick]
+        bg = torch.rand((1, 1024, 3), device="cuda")
+        a = alpha_gt[pick][None]
+        premult = rgb_gt[pick][None] - (1 - a[..., None])  # the GT render is composited over white
+        b["rgb"] = premult + (1 - a[..., None]) * bg  # random background per pixel, peoplesnapshot.py:109-114
+        b["alpha"], b["bg_color"] = a, bg
+        out = model.training_step(b)
+        losses.append(out["loss"].item())
+    assert all(np.isfinite(losses))
+    assert np.mean(losses[-10:]) < 0.6 * np.mean(losses[:5]), (losses[:5], losses[-10:])
+    assert model.scaler.scale_t.item() >= 1.0
