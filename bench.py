@@ -162,6 +162,59 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25):
+    """second half of BASELINE.json's metric: ms per training step (DNeRF.py:112-161) at 4096 rays per step
+    (4 patches of 32x32, confs/sampler/patch.yaml), rays sharded over the ranks, one gradient all-reduce per step;
+    includes the every-20-steps occupancy-grid refresh amortised over the timed steps."""
+    import torch
+    import torch.distributed as dist
+    from instantavatar_b200 import parallel
+    model.eval()
+    rgb_gt, _, alpha_gt, _ = model.render_image_fast(dict(batch), (H, W))
+    rgb_gt, alpha_gt = rgb_gt.reshape(-1, 3), alpha_gt.reshape(-1)
+    torch.manual_seed(1234)  # identical on every rank: replicated grid refresh needs identical jitter
+    idx = []
+    for (y0, x0) in ((150, 240), (200, 232), (250, 236), (300, 240)):
+        ys, xs = torch.arange(y0, y0 + 32), torch.arange(x0, x0 + 32)
+        idx.append((ys[:, None] * W + xs[None]).reshape(-1))
+    idx = torch.cat(idx)
+    sl = parallel.shard_train_rays(len(idx), rank, world)
+    pick = idx[sl].to(device)
+    n = len(pick)
+    b = dict(batch)
+    for k in ("rays_o", "rays_d", "near", "far"):
+        b[k] = batch[k][:, pick].contiguous()
+    a = alpha_gt[pick][None]
+    model.world_size = world
+    model.global_step = 2000  # steady state: no density noise, grid refresh uses the previous field as `valid`
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def one():
+        bg = torch.rand((1, n, 3), device=device)
+        b["bg_color"], b["alpha"] = bg, a
+        b["rgb"] = rgb_gt[pick][None] - (1 - a[..., None]) + (1 - a[..., None]) * bg
+        return model.training_step(b)
+
+    for _ in range(warmup):
+        one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        out = one()
+    ev1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1) / steps], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return {"ms_per_step": float(ms.item()), "rays_per_step": int(len(idx)), "rays_per_rank": int(n), "steps": steps,
+            "grid_refresh_every": 20, "allreduce_elems": 13036208 if world > 1 else 0, "final_loss": float(out["loss"].item()),
+            "scaling": "strong"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -191,8 +244,7 @@ def run_ours(args):
     def step_e2e():
         b = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
         rgb, depth, alpha, counter = model.render_image_fast(b, (H, W))
-        out_host[:, :3].copy_(rgb.reshape(-1, 3), non_blocking=True)
-        out_host[:, 3].copy_(alpha.reshape(-1), non_blocking=True)
+        out_host.copy_(torch.cat([rgb.reshape(-1, 3), alpha.reshape(-1, 1)], dim=1), non_blocking=True)
         return rgb
 
     def barrier():
@@ -251,6 +303,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     occ_ms = float(np.median([a.elapsed_time(b) for a, b in qev]))
 
+    train = bench_train(model, batch, device, rank, world, flush)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -287,6 +341,7 @@ def run_ours(args):
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
+        "train": train,
         "roofline": {"kernel": "render_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": algo_bytes,

@@ -61,7 +61,7 @@ const char* ia_last_error(void);
 /* number of SMs of the current device (grid sizing is a multiple of this) [host result] */
 int ia_sm_count(void);
 
-/* tuning knobs (do not change results): "render_rays_per_warp" in {32,16,8,4} */
+/* tuning knobs (do not change results): "render_rays_per_warp" in {32,16,8,4}, "train_rays_per_warp" in {4,2,1} */
 int ia_set_option(const char* name, int value);
 
 /* tiny-cuda-nn HashGrid level table (models/networks/ngp.py:27-37 config). [host] outputs. */
@@ -71,8 +71,7 @@ int ia_hashgrid_layout(uint32_t res[IA_NUM_LEVELS], float scale[IA_NUM_LEVELS], 
 /* Replaces precompute_cuda.precompute (deformers/fast_snarf/cuda/precompute/precompute.cpp:7-13,
  * precompute.cu:24-103).  voxel_w [24][D][H][W] skinning weights, tfs [24][4][4].
  * field_out [D][H][W][12]; voxel_d_out [3][D][H][W] (nullable; reference layout, deformer.voxel_d);
- * aabb_out [6] = min/max of voxel_d (nullable; SNARFDeformer.get_bbox_deformed, snarf_deformer.py:105-107).
- * aabb_out must be pre-initialised by the caller to (+inf x3, -inf x3). */
+ * aabb_out [6] = min/max of voxel_d (nullable; SNARFDeformer.get_bbox_deformed, snarf_deformer.py:105-107). */
 int ia_precompute(const float* voxel_w, const float* tfs, const float* offset_k, const float* scale_k, int D, int H,
                   int W, float* field_out, float* voxel_d_out, float* aabb_out, ia_stream_t stream);
 
@@ -113,6 +112,12 @@ int ia_render_fwd(const IaScene* scene /*[host]*/, const float* rays_o, const fl
  * best_init [n] int8 (nullable; index 0..12 of the winning initialisation, -1 if none valid). */
 int ia_deform_query(const IaScene* scene /*[host]*/, const float* pts, int n, int eval_mode, float* rgb, float* sigma,
                     float* xc_best, int8_t* best_init, IaStats* stats, ia_stream_t stream);
+
+/* DensityGrid.initialize's density pass (models/structures/density_grid.py:94-103) in one launch: for each of
+ * `passes` jitter tensors [G][G][G][3] the G^3 cell points (idx/G + jitter/G) * (max - min) + min are queried in eval
+ * mode and max(sigma, 0) is reduced into density_max [G][G][G] (zeroed by the library).  aabb [6] device. */
+int ia_occupancy_query(const IaScene* scene /*[host]*/, const float* jitter, const float* aabb, int G, int passes,
+                       float* density_max, IaStats* stats, ia_stream_t stream);
 
 /* Fine-grained entry points (serve the legacy `model(pts)` callback path and the tinycudann-named shim):
  * ia_broyden replaces fuse_kernel.fuse_broyden + filter_cuda.filter
@@ -164,6 +169,17 @@ int ia_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
                  float beta2, float eps, int step, float inv_grad_scale, const float* grad_scale_dev /*nullable: divides*/,
                  const float* found_inf, ia_stream_t stream);
 int ia_grad_check_finite(const float* grads, long n, float* found_inf, ia_stream_t stream);
+
+/* CUDA-graph friendly variant: every per-step scalar lives in device memory.  state [8] floats =
+ * {lr, beta1, beta2, eps, step, bc1, bc2_sqrt, inv_scale}.  ia_adam_prepare (one thread) increments state[4] unless
+ * *found_inf, recomputes the bias corrections and inv_scale = inv_world / *grad_scale_dev (1 if NULL).
+ * ia_adam_step_dev applies the update (skipped when *found_inf), ALWAYS zeroes the gradient it consumed, and, when
+ * half_out is non-NULL, refreshes the fp16 working copy half_out[i - half_skip] = half(params[i]) for i >= half_skip. */
+int ia_adam_prepare(float* state, float inv_world, const float* grad_scale_dev, const float* found_inf, ia_stream_t stream);
+int ia_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long n, const float* state,
+                     const float* found_inf, void* half_out, long half_skip, ia_stream_t stream);
+/* fp16 refresh of the padded MLP weight block only (the hash table is refreshed by ia_adam_step_dev) */
+int ia_mlp_to_half(const float* enc_params, const float* col_params, void* mlp_h, ia_stream_t stream);
 
 #ifdef __cplusplus
 }

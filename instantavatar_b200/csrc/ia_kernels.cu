@@ -9,6 +9,8 @@
 using namespace ia;
 
 static int g_render_rays = 8;  // rays per warp (32 / 16 / 8 / 4), tunable through ia_set_option
+static int g_train_rays = 2;   // rays per warp of the training forward (4 / 2 / 1)
+int ia_train_rays_per_warp() { return g_train_rays; }
 
 #include "ia_host.h"
 #include "ia_scene.cuh"
@@ -253,6 +255,9 @@ struct QueryArgs {
     const float* pts; int n; int eval_mode;
     float* rgb; float* sigma; float* xc_best; int8_t* best_init;
     IaStats* stats;
+    // grid mode (DensityGrid.initialize, density_grid.py:94-103): points are generated from the cell index and the
+    // per-pass jitter, and max(sigma, 0) is reduced over the passes into density_max[G^3]
+    const float* grid_jitter; const float* grid_aabb; int G; float* density_max;
 };
 
 template <int kWarps>
@@ -287,11 +292,28 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
         const int p = bidx * 32 + lane;
         const bool act = p < a.n;
         float x = 0, y = 0, z = 0;
-        if (act) { x = a.pts[p * 3]; y = a.pts[p * 3 + 1]; z = a.pts[p * 3 + 2]; }
+        int cell = 0;
+        if (act) {
+            if (a.grid_aabb) {
+                // coords = (idx / G + jitter / G) * (max - min) + min   (density_grid.py:20-23,100)
+                const int G = a.G, n3 = G * G * G;
+                cell = p % n3;
+                const int ci = cell / (G * G), cj = (cell / G) % G, ck = cell % G;
+                const float* jit = a.grid_jitter + (long)p * 3;
+                const float fG = (float)G;
+                x = ((float)ci / fG + jit[0] / fG) * (a.grid_aabb[3] - a.grid_aabb[0]) + a.grid_aabb[0];
+                y = ((float)cj / fG + jit[1] / fG) * (a.grid_aabb[4] - a.grid_aabb[1]) + a.grid_aabb[1];
+                z = ((float)ck / fG + jit[2] / fG) * (a.grid_aabb[5] - a.grid_aabb[2]) + a.grid_aabb[2];
+            } else {
+                x = a.pts[p * 3]; y = a.pts[p * 3 + 1]; z = a.pts[p * 3 + 2];
+            }
+        }
         SampleOut so;
         warp_eval_samples<true>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots);
         st_samples += act ? 1u : 0u;
-        if (act) {
+        if (act && a.grid_aabb) {
+            if (so.sigma > 0.f) atomicMax(reinterpret_cast<int*>(a.density_max) + cell, __float_as_int(so.sigma));
+        } else if (act) {
             a.sigma[p] = so.sigma;
             a.rgb[p * 3] = so.r; a.rgb[p * 3 + 1] = so.g; a.rgb[p * 3 + 2] = so.b;
             if (a.xc_best) { a.xc_best[p * 3] = so.xc[0]; a.xc_best[p * 3 + 1] = so.xc[1]; a.xc_best[p * 3 + 2] = so.xc[2]; }
@@ -465,10 +487,14 @@ __global__ void __launch_bounds__(256) precompute_kernel(const float* __restrict
     }
 }
 
+__global__ void aabb_init_kernel(float* aabb) {
+    if (threadIdx.x < 6) aabb[threadIdx.x] = threadIdx.x < 3 ? INFINITY : -INFINITY;
+}
+
 __global__ void params_to_half_kernel(const float* __restrict__ enc, const float* __restrict__ col,
                                       __half2* __restrict__ table, __half* __restrict__ mlp, uint32_t total_entries) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total_entries) {
+    if (table && i < total_entries) {
         const float2 v = *reinterpret_cast<const float2*>(enc + IA_ENC_MLP_PARAMS + 2 * i);
         table[i] = __floats2half2_rn(v.x, v.y);
     }
@@ -535,6 +561,11 @@ int ia_set_option(const char* name, int value) {
         g_render_rays = value;
         return IA_OK;
     }
+    if (!strcmp(name, "train_rays_per_warp")) {
+        IA_REQUIRE(value == 4 || value == 2 || value == 1);
+        g_train_rays = value;
+        return IA_OK;
+    }
     return set_err(IA_EINVAL, "unknown option: %s", name);
 }
 
@@ -558,6 +589,7 @@ int ia_precompute(const float* voxel_w, const float* tfs, const float* offset_k,
     IA_REQUIRE(voxel_w && tfs && offset_k && scale_k && field_out);
     IA_REQUIRE(D > 1 && H > 1 && W > 1);
     const long V = (long)D * H * W;
+    if (aabb_out) aabb_init_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(aabb_out);
     precompute_kernel<<<(unsigned)((V + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         voxel_w, tfs, offset_k, scale_k, D, H, W, reinterpret_cast<float4*>(field_out), voxel_d_out, aabb_out);
     IA_CHECK_CUDA(cudaPeekAtLastError());
@@ -575,6 +607,14 @@ int ia_params_to_half(const float* enc_params, const float* col_params, void* ta
     return IA_OK;
 }
 
+int ia_mlp_to_half(const float* enc_params, const float* col_params, void* mlp_h, ia_stream_t stream) {
+    IA_REQUIRE(enc_params && col_params && mlp_h);
+    params_to_half_kernel<<<(kMlpAllHalfs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(enc_params, col_params, nullptr,
+                                                                                      reinterpret_cast<__half*>(mlp_h), 0);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
 int ia_pack_occupancy(const uint8_t* field_bool, uint32_t* bits, int G, ia_stream_t stream) {
     IA_REQUIRE(field_bool && bits && G >= 32 && G % 32 == 0);
     const int n_words = G * G * G / 32;
@@ -585,7 +625,7 @@ int ia_pack_occupancy(const uint8_t* field_bool, uint32_t* bits, int G, ia_strea
 }
 
 constexpr int kRenderWarps = 12;
-constexpr int kQueryWarps = 8;
+constexpr int kQueryWarps = 12;
 
 int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d, const float* near, const float* far,
                   int n_rays, const float* bg, int image_width, float* rgb, float* depth, float* alpha, float* counter,
@@ -627,6 +667,8 @@ int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d
     return IA_OK;
 }
 
+static int launch_query(QueryArgs& a, cudaStream_t stream);
+
 int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode, float* rgb, float* sigma,
                     float* xc_best, int8_t* best_init, IaStats* stats, ia_stream_t stream) {
     IA_REQUIRE(n >= 0);
@@ -637,6 +679,12 @@ int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode
     if (rc) return rc;
     a.pts = pts; a.n = n; a.eval_mode = eval_mode; a.rgb = rgb; a.sigma = sigma; a.xc_best = xc_best;
     a.best_init = best_init; a.stats = stats;
+    a.grid_jitter = nullptr; a.grid_aabb = nullptr; a.G = 0; a.density_max = nullptr;
+    return launch_query(a, (cudaStream_t)stream);
+}
+
+static int launch_query(QueryArgs& a, cudaStream_t stream) {
+    const int n = a.n;
     const size_t smem = sizeof(QuerySmem<kQueryWarps>);
     static bool attr_set = false;
     if (!attr_set) {
@@ -644,12 +692,25 @@ int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode
         attr_set = true;
     }
     const int n_batches = (n + 31) / 32;
-    int grid = sm_count() * 2;
+    int grid = sm_count();
     if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
     grid = min(grid, (n_batches + kQueryWarps - 1) / kQueryWarps);
-    deform_query_kernel<kQueryWarps><<<grid, kQueryWarps * 32, smem, (cudaStream_t)stream>>>(a);
+    deform_query_kernel<kQueryWarps><<<grid, kQueryWarps * 32, smem, stream>>>(a);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
+}
+
+extern "C" int ia_occupancy_query(const IaScene* scene, const float* jitter, const float* aabb, int G, int passes,
+                                  float* density_max, IaStats* stats, ia_stream_t stream) {
+    IA_REQUIRE(jitter && aabb && density_max && G > 0 && passes > 0);
+    QueryArgs a;
+    int rc = make_scene_dev(scene, a.sd, false);
+    if (rc) return rc;
+    a.pts = nullptr; a.n = passes * G * G * G; a.eval_mode = 1; a.rgb = nullptr; a.sigma = nullptr; a.xc_best = nullptr;
+    a.best_init = nullptr; a.stats = stats;
+    a.grid_jitter = jitter; a.grid_aabb = aabb; a.G = G; a.density_max = density_max;
+    IA_CHECK_CUDA(cudaMemsetAsync(density_max, 0, sizeof(float) * G * G * G, (cudaStream_t)stream));
+    return launch_query(a, (cudaStream_t)stream);
 }
 
 int ia_broyden(const IaScene* scene, const float* xd, int n, float* xc, uint8_t* valid, float* j_inv, ia_stream_t stream) {

@@ -55,20 +55,29 @@ __global__ void pool_kernel(const float* __restrict__ density, int G, float* __r
     }
 }
 
-__global__ void threshold_kernel(const float* __restrict__ pooled, int N, const double* __restrict__ sum,
+__global__ void threshold_kernel(const float* __restrict__ pooled, int N, int G, const double* __restrict__ sum,
                                  int* __restrict__ parent, int* __restrict__ count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const float mean = (float)(*sum / (double)N);
     const float thr = fminf(mean, 0.01f);  // torch.clamp(mean, max=0.01)
-    parent[i] = pooled[i] > thr ? i : -1;
+    // runs along z (the contiguous axis) are pre-linked: parent = next cell of the run, so only the 12 other forward
+    // neighbours need atomic unions
+    const bool on = pooled[i] > thr;
+    const bool next_on = on && ((i % G) < G - 1) && pooled[i + 1] > thr;
+    parent[i] = on ? (next_on ? i + 1 : i) : -1;
     count[i] = 0;
 }
 
+// find with path halving; parent[x] >= x always holds (roots are the largest index), so the racy shortcut writes are safe
 __device__ __forceinline__ int uf_find(int* parent, int i) {
-    int p = parent[i];
-    while (p != i) { i = p; p = parent[i]; }
-    return i;
+    for (;;) {
+        const int p = parent[i];
+        if (p == i) return i;
+        const int gp = parent[p];
+        if (gp != p) parent[i] = gp;
+        i = p;
+    }
 }
 
 // roots are the largest linear index of the component (the label the reference's max-flood converges to)
@@ -93,7 +102,7 @@ __global__ void union_kernel(int* __restrict__ parent, int G) {
     for (int dx = 0; dx <= 1; dx++)
         for (int dy = -1; dy <= 1; dy++)
             for (int dz = -1; dz <= 1; dz++) {
-                if (dx == 0 && (dy < 0 || (dy == 0 && dz <= 0))) continue;
+                if (dx == 0 && (dy < 0 || (dy == 0 && dz <= 1))) continue;  // (0,0,+1) is pre-linked
                 const int xx = x + dx, yy = y + dy, zz = z + dz;
                 if (xx >= G || yy < 0 || yy >= G || zz < 0 || zz >= G) continue;
                 const int j = (xx * G + yy) * G + zz;
@@ -171,7 +180,7 @@ extern "C" int ia_occupancy_build(const float* density, int G, uint8_t* field_ou
     init_box_kernel<<<1, 32, 0, st>>>(bits_out, N / 32, G);
     const int blocks = (N + kThreads - 1) / kThreads;
     pool_kernel<<<blocks, kThreads, 0, st>>>(density, G, pooled, sum);
-    threshold_kernel<<<blocks, kThreads, 0, st>>>(pooled, N, sum, parent, count);
+    threshold_kernel<<<blocks, kThreads, 0, st>>>(pooled, N, G, sum, parent, count);
     union_kernel<<<blocks, kThreads, 0, st>>>(parent, G);
     flatten_count_kernel<<<blocks, kThreads, 0, st>>>(parent, count, N);
     argmax_kernel<<<blocks, kThreads, 0, st>>>(count, N, best);

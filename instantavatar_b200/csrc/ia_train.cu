@@ -555,21 +555,42 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const __half* __restrict__ s
         __syncthreads();
         for (int r = 0; r < n; r++) {
             const __half* row = rows[r];
+            auto ld8 = [&](int off, float* o) {  // 8 consecutive halfs -> floats (16-byte aligned offsets)
+                const uint4 u = *reinterpret_cast<const uint4*>(row + off);
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int q = 0; q < 4; q++) { const float2 f = __half22float2(h[q]); o[2 * q] = f.x; o[2 * q + 1] = f.y; }
+            };
+            float in[16];
             const float d4 = __half2float(row[kOffD4 + o4]);
+            ld8(kOffH2 + i4, in); ld8(kOffH2 + i4 + 8, in + 8);
 #pragma unroll
-            for (int i = 0; i < 16; i++) a4[i] = __fmaf_rn(d4, __half2float(row[kOffH2 + i4 + i]), a4[i]);
+            for (int i = 0; i < 16; i++) a4[i] = __fmaf_rn(d4, in[i], a4[i]);
             const float d1 = __half2float(row[kOffD1 + o1]);
+            ld8(kOffEnc + i1, in);
 #pragma unroll
-            for (int i = 0; i < 8; i++) a1[i] = __fmaf_rn(d1, __half2float(row[kOffEnc + i1 + i]), a1[i]);
+            for (int i = 0; i < 8; i++) a1[i] = __fmaf_rn(d1, in[i], a1[i]);
             const float d2 = __half2float(row[kOffD2 + o2]);
-#pragma unroll
-            for (int i = 0; i < 4; i++) a2[i] = __fmaf_rn(d2, __half2float(row[kOffH1 + i2 + i]), a2[i]);
+            {
+                const uint2 u = *reinterpret_cast<const uint2*>(row + kOffH1 + i2);
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+                a2[0] = __fmaf_rn(d2, f0.x, a2[0]); a2[1] = __fmaf_rn(d2, f0.y, a2[1]);
+                a2[2] = __fmaf_rn(d2, f1.x, a2[2]); a2[3] = __fmaf_rn(d2, f1.y, a2[3]);
+            }
             const float d3 = __half2float(row[kOffD3 + o3]);
-#pragma unroll
-            for (int i = 0; i < 4; i++) a3[i] = __fmaf_rn(d3, __half2float(row[kOffC3 + i3 + i]), a3[i]);
+            {
+                const uint2 u = *reinterpret_cast<const uint2*>(row + kOffC3 + i3);
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+                a3[0] = __fmaf_rn(d3, f0.x, a3[0]); a3[1] = __fmaf_rn(d3, f0.y, a3[1]);
+                a3[2] = __fmaf_rn(d3, f1.x, a3[2]); a3[3] = __fmaf_rn(d3, f1.y, a3[3]);
+            }
             const float d5 = __half2float(row[kOffD5 + o5]);
-#pragma unroll
-            for (int i = 0; i < 2; i++) a5[i] = __fmaf_rn(d5, __half2float(row[kOffH3 + i5 + i]), a5[i]);
+            {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(row + kOffH3 + i5));
+                a5[0] = __fmaf_rn(d5, f.x, a5[0]); a5[1] = __fmaf_rn(d5, f.y, a5[1]);
+            }
         }
     }
     // flush (tcnn parameter order; W3 column un-rotation: column 0 of W3' is the pad column 15 of W3)
@@ -606,6 +627,37 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     p[i] = p[i] - (lr / bc1) * (mi / denom);
 }
 
+__global__ void adam_prepare_kernel(float* state, float inv_world, const float* grad_scale_dev, const float* found_inf) {
+    if (threadIdx.x != 0) return;
+    if (!(found_inf && *found_inf != 0.f)) state[4] += 1.f;
+    const double t = fmax((double)state[4], 1.0);
+    state[5] = (float)(1.0 - pow((double)state[1], t));
+    state[6] = (float)sqrt(1.0 - pow((double)state[2], t));
+    state[7] = grad_scale_dev ? inv_world / *grad_scale_dev : inv_world;
+}
+
+__global__ void adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
+                                const float* __restrict__ state, const float* __restrict__ found_inf, __half* __restrict__ half_out,
+                                long half_skip) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi_raw = g[i];
+    g[i] = 0.f;  // zero_grad fused into the step
+    const bool skip = found_inf && *found_inf != 0.f;
+    float pi = p[i];
+    if (!skip) {
+        const float lr = state[0], beta1 = state[1], beta2 = state[2], eps = state[3], bc1 = state[5], bc2_sqrt = state[6];
+        const float gi = gi_raw * state[7];
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi = pi - (lr / bc1) * (mi / denom);
+        p[i] = pi;
+    }
+    if (half_out && i >= half_skip) half_out[i - half_skip] = __float2half_rn(pi);
+}
+
 __global__ void grad_finite_kernel(const float* __restrict__ g, long n, float* __restrict__ found_inf) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     bool bad = false;
@@ -616,6 +668,8 @@ __global__ void grad_finite_kernel(const float* __restrict__ g, long n, float* _
 }  // namespace
 
 // ================================================================================================
+int ia_train_rays_per_warp();  // ia_kernels.cu (ia_set_option)
+
 extern "C" {
 
 int ia_train_fwd(const IaScene* scene, const float* rays_o, const float* rays_d, const float* near, const float* far,
@@ -636,18 +690,23 @@ int ia_train_fwd(const IaScene* scene, const float* rays_o, const float* rays_d,
     a.stats = stats;
     cudaStream_t st = (cudaStream_t)stream;
     IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
-    constexpr int kW = 8, kR = 4;
+    constexpr int kW = 10;
     const size_t smem = sizeof(TrainSmem<kW>);
     static bool attr_set = false;
     if (!attr_set) {
-        IA_CHECK_CUDA(cudaFuncSetAttribute(train_fwd_kernel<kW, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(train_fwd_kernel<kW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(train_fwd_kernel<kW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(train_fwd_kernel<kW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    const int kR = ia_train_rays_per_warp();
     const int n_tiles = (n_rays + kR - 1) / kR;
     int grid = sm_count();
     if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
     grid = min(grid, (n_tiles + kW - 1) / kW);
-    train_fwd_kernel<kW, kR><<<grid, kW * 32, smem, st>>>(a);
+    if (kR == 4) train_fwd_kernel<kW, 4><<<grid, kW * 32, smem, st>>>(a);
+    else if (kR == 1) train_fwd_kernel<kW, 1><<<grid, kW * 32, smem, st>>>(a);
+    else train_fwd_kernel<kW, 2><<<grid, kW * 32, smem, st>>>(a);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }
@@ -719,6 +778,24 @@ int ia_grad_check_finite(const float* grads, long n, float* found_inf, ia_stream
     if (n == 0) return IA_OK;
     IA_REQUIRE(grads != nullptr);
     grad_finite_kernel<<<sm_count() > 0 ? sm_count() * 8 : 1024, 256, 0, (cudaStream_t)stream>>>(grads, n, found_inf);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_adam_prepare(float* state, float inv_world, const float* grad_scale_dev, const float* found_inf, ia_stream_t stream) {
+    IA_REQUIRE(state != nullptr);
+    adam_prepare_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, inv_world, grad_scale_dev, found_inf);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long n, const float* state,
+                     const float* found_inf, void* half_out, long half_skip, ia_stream_t stream) {
+    IA_REQUIRE(n >= 0);
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(params && grads && exp_avg && exp_avg_sq && state);
+    adam_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, state, found_inf,
+                                                                                  reinterpret_cast<__half*>(half_out), half_skip);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

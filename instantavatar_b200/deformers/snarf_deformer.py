@@ -173,7 +173,13 @@ class SNARFDeformer:
         out = self.body_model(betas=smpl_params["betas"], body_pose=smpl_params["body_pose"],
                               global_orient=smpl_params["global_orient"], transl=smpl_params["transl"])
         s2w = out.A[:, 0].float()
-        w2s = torch.linalg.inv_ex(s2w).inverse  # torch.inverse without the host-synchronising error check
+        # inverse of the rigid root transform in closed form ([R | t]^-1 = [R^T | -R^T t]); the reference calls
+        # torch.inverse (snarf_deformer.py:84), which synchronises the host and cannot be captured in a CUDA graph
+        Rt = s2w[:, :3, :3].transpose(1, 2)
+        w2s = torch.zeros_like(s2w)
+        w2s[:, :3, :3] = Rt
+        w2s[:, :3, 3] = -(Rt @ s2w[:, :3, 3:4])[..., 0]
+        w2s[:, 3, 3] = 1.0
         tfs = (w2s[:, None] @ out.A.float() @ self.tfs_inv_t).type(self.dtype)
         self.deformer.precompute(tfs)
         self.w2s = w2s

@@ -86,7 +86,7 @@ class DNeRFModel(torch.nn.Module):
         self.renderer.idx = int(batch.get("idx", 0)) if not torch.is_tensor(batch.get("idx", 0)) else 0
         self.deformer.prepare_deformer(batch)
         self.net_coarse.initialize(self.deformer.bbox)
-        self.optimizer.zero_grad()
+        self.net_coarse.grad_buffers()  # zeroed at creation and by every fused optimiser step (no separate zero_grad pass)
         reg = self.update_density_grid(grid_jitter)
         predicts = self.forward(batch, eval_mode=False, jitter=jitter, noise_tensor=noise_tensor)
         losses = self.loss_fn(predicts, batch)

@@ -72,6 +72,16 @@ class NeRFNGPNet(nn.Module):
     def mark_dirty(self):
         self._dirty = True
 
+    def mark_clean(self):
+        """the optimiser refreshed the fp16 copies itself"""
+        self._dirty = False
+
+    def half_buffers(self):
+        """persistent fp16 working copies (allocated on first use), without refreshing them"""
+        if self._table_h is None or self._table_h.device != self.encoder.params.device:
+            self.half_params()
+        return self._table_h, self._mlp_h
+
     def grad_buffers(self):
         """persistent flat fp32 gradient buffers the fused backward accumulates into (aliased as `.grad`)"""
         p, c = self.encoder.params, self.color_net.params

@@ -79,9 +79,12 @@ class DensityGrid(torch.nn.Module):
         self._version += 1
 
     def build_from_density(self, density):
-        """density -> density_field + bit field in one pass of the occupancy kernels"""
-        field, self._bits = ops.occupancy_build(density, self._bits)
-        self.density_field = field
+        """density -> density_field + bit field in one pass of the occupancy kernels (in place: the buffers keep their
+        addresses, which CUDA-graph replays rely on)"""
+        self._ws = getattr(self, "_ws", None)
+        if self._ws is None:
+            self._ws = torch.empty(12 * self.grid_size ** 3 + 64, device=density.device, dtype=torch.uint8)
+        _, self._bits = ops.occupancy_build(density, self._bits, field=self.density_field, workspace=self._ws)
         self._version += 1
         self._bits_version = self._version
 
@@ -93,8 +96,8 @@ class DensityGrid(torch.nn.Module):
         with torch.enable_grad():
             _, density = deformer(coords.reshape(-1, 3), net, eval_mode=False)
         density = density.clip(min=0).reshape(coords.shape[:-1])
-        old = self.density_field
-        self.density_cached = torch.maximum(self.density_cached * 0.8, density.detach())
+        old = self.density_field.clone()
+        self.density_cached.copy_(torch.maximum(self.density_cached * 0.8, density.detach()))
         self.build_from_density(self.density_cached)
         density = 1 - torch.exp(0.01 * -F.relu(density))
         valid = self.density_field if step < 500 else old
@@ -104,6 +107,15 @@ class DensityGrid(torch.nn.Module):
     def initialize(self, deformer, net, iters=5, jitters=None):
         """density_grid.py:94-110 (test-time, per frame)."""
         self.aabb = deformer.get_bbox_deformed()
+        from ..networks.ngp import NeRFNGPNet
+        if isinstance(net, NeRFNGPNet) and hasattr(deformer, "scene"):
+            # all passes in one launch of the fused point-query kernel (points generated from the cell index)
+            if jitters is None:
+                jitters = torch.rand((iters, *self.coords.shape), device=self.coords.device)
+            net.initialize(deformer.bbox)
+            self._density = ops.occupancy_query(deformer.scene(net), jitters[:iters], self.aabb6(), getattr(self, "_density", None))
+            self.build_from_density(self._density)
+            return
         density = torch.zeros_like(self.coords[..., 0])
         for i in range(iters):
             j = torch.rand_like(self.coords) if jitters is None else jitters[i]

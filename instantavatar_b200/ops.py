@@ -22,7 +22,7 @@ def precompute(voxel_w: torch.Tensor, tfs: torch.Tensor, offset_k: torch.Tensor,
     dev = voxel_w.device
     fld = torch.empty((D, H, W, 12), device=dev, dtype=f32)
     vd = torch.empty((3, D, H, W), device=dev, dtype=f32) if want_voxel_d else None
-    aabb = torch.tensor([float("inf")] * 3 + [float("-inf")] * 3, device=dev, dtype=f32)
+    aabb = torch.empty(6, device=dev, dtype=f32)  # initialised by the library
     _lib.count(1); check(lib().ia_precompute(ptr(voxel_w, f32), ptr(tfs.reshape(24, 4, 4).contiguous(), f32),
                               ptr(offset_k.reshape(3).contiguous(), f32), ptr(scale_k.reshape(3).contiguous(), f32),
                               C.c_int(D), C.c_int(H), C.c_int(W), ptr(fld), ptr(vd), ptr(aabb), stream()))
@@ -50,12 +50,13 @@ def pack_occupancy(field_bool: torch.Tensor, bits=None):
     return bits
 
 
-def occupancy_build(density: torch.Tensor, bits=None, want_field=True, workspace=None):
+def occupancy_build(density: torch.Tensor, bits=None, want_field=True, workspace=None, field=None):
     """density [G,G,G] -> (density_field bool [G,G,G] | None, occupancy bit field) -- density_grid.py:78-85,118-125"""
     G = density.shape[0]
     dev = density.device
     density = density.contiguous().float()
-    field = torch.empty((G, G, G), device=dev, dtype=torch.bool) if want_field else None
+    if field is None:
+        field = torch.empty((G, G, G), device=dev, dtype=torch.bool) if want_field else None
     if bits is None:
         bits = torch.empty(G * G * G // 32 + 8, device=dev, dtype=torch.int32)
     nbytes = 12 * G * G * G + 64
@@ -63,6 +64,17 @@ def occupancy_build(density: torch.Tensor, bits=None, want_field=True, workspace
         workspace = torch.empty(nbytes, device=dev, dtype=torch.uint8)
     _lib.count(7); check(lib().ia_occupancy_build(ptr(density, f32), C.c_int(G), ptr(field), ptr(bits), ptr(workspace), C.c_size_t(nbytes), stream()))
     return field, bits
+
+
+def occupancy_query(scene, jitters: torch.Tensor, aabb6: torch.Tensor, density=None, stats=None):
+    """5-pass density query of DensityGrid.initialize in one launch -> density [G,G,G] (max over passes, >= 0)"""
+    P, G = jitters.shape[0], jitters.shape[1]
+    if density is None:
+        density = torch.empty((G, G, G), device=jitters.device, dtype=f32)
+    s = scene.c_struct()
+    _lib.count(1); check(lib().ia_occupancy_query(C.byref(s), ptr(jitters.contiguous(), f32), ptr(aabb6, f32), C.c_int(G), C.c_int(P),
+                                                  ptr(density), ptr(stats), stream()))
+    return density
 
 
 @dataclass
@@ -226,3 +238,17 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, betas, eps, step, inv_grad
 
 def grad_check_finite(grads, found_inf):
     _lib.count(1); check(lib().ia_grad_check_finite(ptr(grads, f32), C.c_long(grads.numel()), ptr(found_inf, f32), stream()))
+
+
+def adam_prepare(state, inv_world=1.0, grad_scale_dev=None, found_inf=None):
+    _lib.count(1); check(lib().ia_adam_prepare(ptr(state, f32), C.c_float(inv_world), ptr(grad_scale_dev), ptr(found_inf), stream()))
+
+
+def adam_step_dev(params, grads, exp_avg, exp_avg_sq, state, found_inf=None, half_out=None, half_skip=0):
+    _lib.count(1); check(lib().ia_adam_step_dev(ptr(params, f32), ptr(grads, f32), ptr(exp_avg, f32), ptr(exp_avg_sq, f32),
+                                                C.c_long(params.numel()), ptr(state, f32), ptr(found_inf), ptr(half_out),
+                                                C.c_long(half_skip), stream()))
+
+
+def mlp_to_half(enc_params, col_params, mlp_h):
+    _lib.count(1); check(lib().ia_mlp_to_half(ptr(enc_params, f32), ptr(col_params, f32), ptr(mlp_h), stream()))

@@ -30,32 +30,46 @@ class GradScaler:
 
 
 class FusedAdam:
+    """All per-step scalars (step count, bias corrections, lr, 1/scale) live in a device tensor, so a training step is
+    a fixed launch sequence that can be captured in a CUDA graph and replayed."""
+
     def __init__(self, net, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, max_epochs=30):
         self.net = net
         self.base_lr, self.betas, self.eps = lr, betas, eps
         self.max_epochs, self.epoch = max_epochs, 0
         self.params = [net.encoder.params, net.color_net.params]
         self.state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in self.params]
-        self.step_count = 0
+        dev = net.encoder.params.device
+        # {lr, beta1, beta2, eps, step, bc1, bc2_sqrt, inv_scale}
+        self.state_t = torch.tensor([lr, betas[0], betas[1], eps, 0.0, 1.0, 1.0, 1.0], dtype=torch.float32).to(dev)
 
     @property
     def lr(self):  # LambdaLR of DNeRF.py:52-55, stepped in on_validation_epoch_end only
         return self.base_lr * (1 - self.epoch / self.max_epochs) ** 1.5
 
+    @property
+    def step_count(self):
+        return int(self.state_t[4].item())
+
     def scheduler_step(self):
         self.epoch += 1
+        self.state_t[0:1].fill_(self.lr)
 
     def zero_grad(self):
+        """explicit zeroing (the fused step already leaves the gradient buffers zeroed)"""
         for g in self.net.grad_buffers():
             g.zero_()
 
     def step(self, scaler: GradScaler | None = None, world_size: int = 1):
-        self.step_count += 1
-        grads = self.net.grad_buffers()
+        g_enc, g_col = self.net.grad_buffers()
+        found = scaler.found_inf if scaler is not None else None
         if scaler is not None:
-            for g in grads:
-                ops.grad_check_finite(g, scaler.found_inf)
-        for p, g, (m, v) in zip(self.params, grads, self.state):
-            ops.adam_step(p.data, g, m, v, self.lr, self.betas, self.eps, self.step_count, 1.0 / world_size,
-                          scaler.found_inf if scaler is not None else None, scaler.scale_t if scaler is not None else None)
-        self.net.mark_dirty()
+            ops.grad_check_finite(g_enc, found)
+            ops.grad_check_finite(g_col, found)
+        ops.adam_prepare(self.state_t, 1.0 / world_size, scaler.scale_t if scaler is not None else None, found)
+        table_h, mlp_h = self.net.half_buffers()
+        (m0, v0), (m1, v1) = self.state
+        ops.adam_step_dev(self.params[0].data, g_enc, m0, v0, self.state_t, found, table_h, 3072)
+        ops.adam_step_dev(self.params[1].data, g_col, m1, v1, self.state_t, found, None, 0)
+        ops.mlp_to_half(self.params[0].data, self.params[1].data, mlp_h)
+        self.net.mark_clean()

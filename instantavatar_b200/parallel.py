@@ -1,0 +1,68 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink on the box, gloo in the CPU tests).
+
+The reference has no distributed code.  The path shards by rays:
+  * render: whole frames (or 8192-ray tiles dealt round-robin) per rank, no data-path collective;
+  * training: each rank marches its shard of the step's rays, then ONE all-reduce (sum) of the flat fp32 gradient
+    [encoder.params | color_net.params] (13 036 208 elements, 52.1 MB) precedes the (replicated) Adam step, which
+    divides by the world size.  The density-grid refresh is replicated bit-identically (same jitter on every rank).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+TILE = 8192  # BASELINE.json config 3: 8192 rays per batch
+
+
+def init_from_env(backend: str | None = None, device: torch.device | None = None):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+        dist.init_process_group(backend, **kw)
+    return rank, world
+
+
+def shard_tiles(n_rays: int, rank: int, world: int, tile: int = TILE) -> torch.Tensor:
+    """indices of the rays this rank renders: tiles of `tile` consecutive rays dealt round-robin (the body sits in
+    the image centre, so contiguous blocks would be badly imbalanced)"""
+    n_tiles = (n_rays + tile - 1) // tile
+    mine = torch.arange(rank, n_tiles, world)
+    idx = (mine[:, None] * tile + torch.arange(tile)[None]).reshape(-1)
+    return idx[idx < n_rays]
+
+
+def shard_train_rays(n_rays: int, rank: int, world: int) -> slice:
+    """contiguous equal shards of the step's rays (whole 32x32 patches while world <= 4)"""
+    per = n_rays // world
+    return slice(rank * per, (rank + 1) * per if rank < world - 1 else n_rays)
+
+
+def allreduce_sum_(buffers, group=None):
+    """the single collective of a training step: in-place sum of the flat gradient buffers"""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        for b in buffers:
+            dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
+    return buffers
+
+
+def gather_image(local: torch.Tensor, idx: torch.Tensor, n_rays: int, group=None) -> torch.Tensor | None:
+    """assemble a ray-sharded render on rank 0: local [n_local, C] rows at global positions idx"""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        out = local.new_zeros((n_rays, local.shape[1]))
+        out[idx.to(local.device)] = local
+        return out
+    rank = dist.get_rank(group)
+    sizes = [len(shard_tiles(n_rays, r, world)) for r in range(world)]
+    bufs = [local.new_empty((s, local.shape[1])) for s in sizes] if rank == 0 else None
+    dist.gather(local.contiguous(), bufs, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = local.new_zeros((n_rays, local.shape[1]))
+    for r, b in enumerate(bufs):
+        out[shard_tiles(n_rays, r, world).to(local.device)] = b
+    return out
