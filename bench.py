@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays-per-warp", type=int, default=0)
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -162,7 +163,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25):
+def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, use_graph=True):
     """second half of BASELINE.json's metric: ms per training step (DNeRF.py:112-161) at 4096 rays per step
     (4 patches of 32x32, confs/sampler/patch.yaml), rays sharded over the ranks, one gradient all-reduce per step;
     includes the every-20-steps occupancy-grid refresh amortised over the timed steps."""
@@ -189,11 +190,17 @@ def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25):
     model.global_step = 2000  # steady state: no density noise, grid refresh uses the previous field as `valid`
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
+    graphed = None
+    if use_graph:
+        from instantavatar_b200.graphs import GraphedTrainStep
+        b["bg_color"], b["alpha"], b["rgb"] = torch.rand((1, n, 3), device=device), a, rgb_gt[pick][None].clone()
+        graphed = GraphedTrainStep(model, b)
+
     def one():
         bg = torch.rand((1, n, 3), device=device)
         b["bg_color"], b["alpha"] = bg, a
         b["rgb"] = rgb_gt[pick][None] - (1 - a[..., None]) + (1 - a[..., None]) * bg
-        return model.training_step(b)
+        return graphed(b) if graphed is not None else model.training_step(b)
 
     for _ in range(warmup):
         one()
@@ -211,7 +218,7 @@ def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return {"ms_per_step": float(ms.item()), "rays_per_step": int(len(idx)), "rays_per_rank": int(n), "steps": steps,
-            "grid_refresh_every": 20, "allreduce_elems": 13036208 if world > 1 else 0, "final_loss": float(out["loss"].item()),
+            "cuda_graph": bool(use_graph), "grid_refresh_every": 20, "allreduce_elems": 13036208 if world > 1 else 0, "final_loss": float(out["loss"].item()),
             "scaling": "strong"}
 
 
@@ -238,12 +245,21 @@ def run_ours(args):
     d2h_bytes = out_host.numel() * 4
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
 
+    from instantavatar_b200.graphs import GraphedFrame
+    use_graph = not args.no_graph
+    frame_graph = GraphedFrame(model, batch, (H, W)) if use_graph else None
+
     def step_resident():
+        if use_graph:
+            return frame_graph()  # inputs already resident in the graph's static buffers
         return model.render_image_fast(dict(batch), (H, W))
 
     def step_e2e():
-        b = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
-        rgb, depth, alpha, counter = model.render_image_fast(b, (H, W))
+        if use_graph:
+            rgb, depth, alpha, counter = frame_graph(pinned)  # pinned host -> static device buffers, replay
+        else:
+            b = {k: v.to(device, non_blocking=True) for k, v in pinned.items()}
+            rgb, depth, alpha, counter = model.render_image_fast(b, (H, W))
         out_host.copy_(torch.cat([rgb.reshape(-1, 3), alpha.reshape(-1, 1)], dim=1), non_blocking=True)
         return rgb
 
@@ -303,7 +319,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     occ_ms = float(np.median([a.elapsed_time(b) for a, b in qev]))
 
-    train = bench_train(model, batch, device, rank, world, flush)
+    train = bench_train(model, batch, device, rank, world, flush, use_graph=use_graph)
 
     if rank != 0:
         if world > 1:
@@ -333,7 +349,7 @@ def run_ours(args):
         "dtype": "f32 geometry + f16 hash-grid/MLP (fp32 accumulate)", "data": "synthetic",
         "config": {"workload": "male-3-casual-shaped synthetic avatar, one 512x512 frame per step per GPU "
                                "(SMPL prep + 5-pass occupancy init + fused render), frames of different poses per rank",
-                   "rays_per_step_per_gpu": N_RAYS, "l2_flush_between_steps": True,
+                   "rays_per_step_per_gpu": N_RAYS, "l2_flush_between_steps": True, "cuda_graph": bool(use_graph),
                    "breakdown_ms": {"fused_render_kernel": k_ms, "occupancy_init": occ_ms,
                                     "frame_total": total_ms / args.steps},
                    "work_per_frame": st},

@@ -8,7 +8,7 @@
 
 using namespace ia;
 
-static int g_render_rays = 8;  // rays per warp (32 / 16 / 8 / 4), tunable through ia_set_option
+static int g_render_rays = 4;  // rays per warp (32 / 16 / 8 / 4), tunable through ia_set_option
 static int g_train_rays = 2;   // rays per warp of the training forward (4 / 2 / 1)
 int ia_train_rays_per_warp() { return g_train_rays; }
 
@@ -257,7 +257,7 @@ struct QueryArgs {
     IaStats* stats;
     // grid mode (DensityGrid.initialize, density_grid.py:94-103): points are generated from the cell index and the
     // per-pass jitter, and max(sigma, 0) is reduced over the passes into density_max[G^3]
-    const float* grid_jitter; const float* grid_aabb; int G; float* density_max;
+    const float* grid_jitter; const float* grid_aabb; int G; float* density_max; int passes;
 };
 
 template <int kWarps>
@@ -287,17 +287,26 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
     ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
     ctx.Wsm = sm.W; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
     unsigned st_gather = 0, st_roots = 0, st_samples = 0;
-    const int n_batches = (a.n + 31) / 32;
+    // grid mode: a batch holds all jitter passes of 32/passes neighbouring cells, so that the 32 lanes stay within a
+    // few voxels of the skinning field (L1 wavefronts, not DRAM, bound this kernel)
+    const int cells_per_batch = a.grid_aabb ? 32 / a.passes : 32;
+    const int n3g = a.G * a.G * a.G;
+    const int n_batches = a.grid_aabb ? (n3g + cells_per_batch - 1) / cells_per_batch : (a.n + 31) / 32;
     for (int bidx = blockIdx.x * kWarps + warp; bidx < n_batches; bidx += gridDim.x * kWarps) {
-        const int p = bidx * 32 + lane;
-        const bool act = p < a.n;
+        int p = bidx * 32 + lane;
+        bool act = p < a.n;
         float x = 0, y = 0, z = 0;
         int cell = 0;
+        if (a.grid_aabb) {
+            cell = bidx * cells_per_batch + lane / a.passes;
+            const int pass = lane % a.passes;
+            act = lane < cells_per_batch * a.passes && cell < n3g;
+            p = pass * n3g + cell;
+        }
         if (act) {
             if (a.grid_aabb) {
                 // coords = (idx / G + jitter / G) * (max - min) + min   (density_grid.py:20-23,100)
-                const int G = a.G, n3 = G * G * G;
-                cell = p % n3;
+                const int G = a.G;
                 const int ci = cell / (G * G), cj = (cell / G) % G, ck = cell % G;
                 const float* jit = a.grid_jitter + (long)p * 3;
                 const float fG = (float)G;
@@ -679,7 +688,7 @@ int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode
     if (rc) return rc;
     a.pts = pts; a.n = n; a.eval_mode = eval_mode; a.rgb = rgb; a.sigma = sigma; a.xc_best = xc_best;
     a.best_init = best_init; a.stats = stats;
-    a.grid_jitter = nullptr; a.grid_aabb = nullptr; a.G = 0; a.density_max = nullptr;
+    a.grid_jitter = nullptr; a.grid_aabb = nullptr; a.G = 0; a.density_max = nullptr; a.passes = 1;
     return launch_query(a, (cudaStream_t)stream);
 }
 
@@ -691,7 +700,7 @@ static int launch_query(QueryArgs& a, cudaStream_t stream) {
         IA_CHECK_CUDA(cudaFuncSetAttribute(deform_query_kernel<kQueryWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const int n_batches = (n + 31) / 32;
+    const int n_batches = a.grid_aabb ? (a.G * a.G * a.G + (32 / a.passes) - 1) / (32 / a.passes) : (n + 31) / 32;
     int grid = sm_count();
     if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
     grid = min(grid, (n_batches + kQueryWarps - 1) / kQueryWarps);
@@ -702,13 +711,13 @@ static int launch_query(QueryArgs& a, cudaStream_t stream) {
 
 extern "C" int ia_occupancy_query(const IaScene* scene, const float* jitter, const float* aabb, int G, int passes,
                                   float* density_max, IaStats* stats, ia_stream_t stream) {
-    IA_REQUIRE(jitter && aabb && density_max && G > 0 && passes > 0);
+    IA_REQUIRE(jitter && aabb && density_max && G > 0 && passes > 0 && passes <= 32);
     QueryArgs a;
     int rc = make_scene_dev(scene, a.sd, false);
     if (rc) return rc;
     a.pts = nullptr; a.n = passes * G * G * G; a.eval_mode = 1; a.rgb = nullptr; a.sigma = nullptr; a.xc_best = nullptr;
     a.best_init = nullptr; a.stats = stats;
-    a.grid_jitter = jitter; a.grid_aabb = aabb; a.G = G; a.density_max = density_max;
+    a.grid_jitter = jitter; a.grid_aabb = aabb; a.G = G; a.density_max = density_max; a.passes = passes;
     IA_CHECK_CUDA(cudaMemsetAsync(density_max, 0, sizeof(float) * G * G * G, (cudaStream_t)stream));
     return launch_query(a, (cudaStream_t)stream);
 }

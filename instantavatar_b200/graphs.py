@@ -25,9 +25,12 @@ class GraphedFrame:
                 model.render_image_fast(dict(self.static_in), img_size, self.jitters)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        from . import _lib
         self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.LAUNCHES
         with torch.cuda.graph(self.graph):
             self.out = model.render_image_fast(dict(self.static_in), img_size, self.jitters)
+        self.launches_per_replay = _lib.LAUNCHES - n0  # libia_b200 kernels inside one replay
 
     def __call__(self, batch: dict | None = None):
         if batch is not None:
@@ -35,6 +38,8 @@ class GraphedFrame:
                 if k in self.static_in:
                     self.static_in[k].copy_(v, non_blocking=True)
         self.graph.replay()
+        from . import _lib
+        _lib.count(self.launches_per_replay)
         return self.out
 
 
@@ -65,11 +70,15 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         model.global_step = step0
+        from . import _lib
         g = torch.cuda.CUDAGraph()
+        n0 = _lib.LAUNCHES
         with torch.cuda.graph(g):
             out = model.training_step(dict(self.static_in))
         model.global_step = step0
         self.graphs[key], self.outs[key] = g, out
+        self.launches = getattr(self, "launches", {})
+        self.launches[key] = _lib.LAUNCHES - n0
 
     def __call__(self, batch: dict | None = None):
         if batch is not None:
@@ -80,5 +89,7 @@ class GraphedTrainStep:
         if key not in self.graphs:
             self._capture(key)
         self.graphs[key].replay()
+        from . import _lib
+        _lib.count(self.launches[key])
         self.model.global_step += 1
         return self.outs[key]
