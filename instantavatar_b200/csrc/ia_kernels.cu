@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
     mbar_wait(&sm.mbar, 0);
 
     EvalCtx ctx;
-    ctx.field.data = reinterpret_cast<const float4*>(a.sd.s.field);
+    ctx.field.data = a.sd.s.field;
     ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
     ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
     ctx.Wsm = sm.W;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
     __syncthreads();
     mbar_wait(&sm.mbar, 0);
     EvalCtx ctx;
-    ctx.field.data = reinterpret_cast<const float4*>(a.sd.s.field);
+    ctx.field.data = a.sd.s.field;
     ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
     ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
     ctx.Wsm = sm.W; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) broyden_kernel(SceneDev sd, const float* 
     load_frame_const(fc, sd);
     __syncthreads();
     FieldDesc f;
-    f.data = reinterpret_cast<const float4*>(sd.s.field); f.D = sd.s.D; f.H = sd.s.H; f.W = sd.s.W;
+    f.data = sd.s.field; f.D = sd.s.D; f.H = sd.s.H; f.W = sd.s.W;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const float t0 = xd[p * 3], t1 = xd[p * 3 + 1], t2 = xd[p * 3 + 2];
@@ -471,9 +471,10 @@ __global__ void __launch_bounds__(256) precompute_kernel(const float* __restrict
 #pragma unroll
             for (int c = 0; c < 12; c++) J[c] = __fmaf_rn(w, T[j][c], J[c]);
         }
-        field[index * 3 + 0] = make_float4(J[0], J[1], J[2], J[3]);
-        field[index * 3 + 1] = make_float4(J[4], J[5], J[6], J[7]);
-        field[index * 3 + 2] = make_float4(J[8], J[9], J[10], J[11]);
+        field[index * 4 + 0] = make_float4(J[0], J[1], J[2], J[3]);
+        field[index * 4 + 1] = make_float4(J[4], J[5], J[6], J[7]);
+        field[index * 4 + 2] = make_float4(J[8], J[9], J[10], J[11]);
+        field[index * 4 + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i0 = 0; i0 < 3; i0++) {
             vd[i0] = aff3f(J[i0 * 4 + 0], cx, J[i0 * 4 + 1], cy, J[i0 * 4 + 2], cz, J[i0 * 4 + 3]);

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) train_fwd_kernel(const __grid_
     mbar_wait(&sm.mbar, 0);
 
     EvalCtx ctx;
-    ctx.field.data = reinterpret_cast<const float4*>(a.sd.s.field);
+    ctx.field.data = a.sd.s.field;
     ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
     ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
     ctx.Wsm = sm.W; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
