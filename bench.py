@@ -312,6 +312,11 @@ def run_ours(args):
     k_ms = float(np.median([a.elapsed_time(b) for a, b in kev]))
     # occupancy-init point queries (5 x 64^3 points)
     grid = rays.density_grid_test
+    qstats = ops.new_stats(device)
+    from instantavatar_b200.models.structures import density_grid as _dg
+    _q = ops.occupancy_query(model.deformer.scene(model.net_coarse), torch.rand((5, 64, 64, 64, 3), device=device), grid.aabb6(), None, qstats)
+    torch.cuda.synchronize()
+    qst = ops.stats_dict(qstats)
     qev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
     for a, b in qev:
         flush.zero_()
@@ -352,7 +357,7 @@ def run_ours(args):
                    "rays_per_step_per_gpu": N_RAYS, "l2_flush_between_steps": True, "cuda_graph": bool(use_graph),
                    "breakdown_ms": {"fused_render_kernel": k_ms, "occupancy_init": occ_ms,
                                     "frame_total": total_ms / args.steps},
-                   "work_per_frame": st},
+                   "work_per_frame": st, "work_per_occupancy_init": qst},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / args.steps},

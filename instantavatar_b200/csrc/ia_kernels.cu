@@ -78,7 +78,7 @@ __device__ __forceinline__ void occupied_interval(const FrameConst& fc, const in
 template <int kWarps, int kRays>
 __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid_constant__ RenderArgs a) {
     constexpr int kDepth = 32 / kRays;
-    constexpr int kTileW = kRays == 32 ? 8 : (kRays >= 8 ? 4 : 2);
+    constexpr int kTileW = kRays == 32 ? 8 : (kRays >= 8 ? 4 : (kRays >= 2 ? 2 : 1));
     constexpr int kTileH = kRays / kTileW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RenderSmem<kWarps>& sm = *reinterpret_cast<RenderSmem<kWarps>*>(smem_raw);
@@ -567,7 +567,7 @@ int ia_sm_count(void) { return sm_count(); }
 int ia_set_option(const char* name, int value) {
     IA_REQUIRE(name != nullptr);
     if (!strcmp(name, "render_rays_per_warp")) {
-        IA_REQUIRE(value == 32 || value == 16 || value == 8 || value == 4);
+        IA_REQUIRE(value == 32 || value == 16 || value == 8 || value == 4 || value == 2 || value == 1);
         g_render_rays = value;
         return IA_OK;
     }
@@ -660,6 +660,8 @@ int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d
         IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int rpw = g_render_rays;
@@ -671,6 +673,8 @@ int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d
         case 32: render_fwd_kernel<kRenderWarps, 32><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
         case 16: render_fwd_kernel<kRenderWarps, 16><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
         case 4: render_fwd_kernel<kRenderWarps, 4><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
+        case 2: render_fwd_kernel<kRenderWarps, 2><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
+        case 1: render_fwd_kernel<kRenderWarps, 1><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
         default: render_fwd_kernel<kRenderWarps, 8><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
     }
     IA_CHECK_CUDA(cudaPeekAtLastError());

@@ -636,26 +636,35 @@ __global__ void adam_prepare_kernel(float* state, float inv_world, const float* 
     state[7] = grad_scale_dev ? inv_world / *grad_scale_dev : inv_world;
 }
 
-__global__ void adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
-                                const float* __restrict__ state, const float* __restrict__ found_inf, __half* __restrict__ half_out,
-                                long half_skip) {
+// 4 elements per thread (128-bit loads/stores; the flat tensors are multiples of 4 long and 16-byte aligned)
+__global__ void __launch_bounds__(256) adam_dev_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                                                        float4* __restrict__ v, long n4, const float* __restrict__ state,
+                                                        const float* __restrict__ found_inf, __half2* __restrict__ half_out,
+                                                        long half_skip4) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float gi_raw = g[i];
-    g[i] = 0.f;  // zero_grad fused into the step
+    if (i >= n4) return;
+    const float4 gr = g[i];
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // zero_grad fused into the step
     const bool skip = found_inf && *found_inf != 0.f;
-    float pi = p[i];
+    float4 pi = p[i];
     if (!skip) {
-        const float lr = state[0], beta1 = state[1], beta2 = state[2], eps = state[3], bc1 = state[5], bc2_sqrt = state[6];
-        const float gi = gi_raw * state[7];
-        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        pi = pi - (lr / bc1) * (mi / denom);
-        p[i] = pi;
+        const float lr = state[0], beta1 = state[1], beta2 = state[2], eps = state[3], bc1 = state[5], bc2_sqrt = state[6],
+                    inv = state[7];
+        float4 mi = m[i], vi = v[i];
+        const float step_size = lr / bc1;
+        auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+            const float gi = gg * inv;
+            mm = beta1 * mm + (1.f - beta1) * gi;
+            vv = beta2 * vv + (1.f - beta2) * gi * gi;
+            pp = pp - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+        };
+        upd(pi.x, gr.x, mi.x, vi.x); upd(pi.y, gr.y, mi.y, vi.y); upd(pi.z, gr.z, mi.z, vi.z); upd(pi.w, gr.w, mi.w, vi.w);
+        m[i] = mi; v[i] = vi; p[i] = pi;
     }
-    if (half_out && i >= half_skip) half_out[i - half_skip] = __float2half_rn(pi);
+    if (half_out && i >= half_skip4) {
+        half_out[2 * (i - half_skip4)] = __floats2half2_rn(pi.x, pi.y);
+        half_out[2 * (i - half_skip4) + 1] = __floats2half2_rn(pi.z, pi.w);
+    }
 }
 
 __global__ void grad_finite_kernel(const float* __restrict__ g, long n, float* __restrict__ found_inf) {
@@ -794,8 +803,11 @@ int ia_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg
     IA_REQUIRE(n >= 0);
     if (n == 0) return IA_OK;
     IA_REQUIRE(params && grads && exp_avg && exp_avg_sq && state);
-    adam_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, state, found_inf,
-                                                                                  reinterpret_cast<__half*>(half_out), half_skip);
+    IA_REQUIRE(n % 4 == 0 && half_skip % 4 == 0);
+    const long n4 = n / 4;
+    adam_dev_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(params), reinterpret_cast<float4*>(grads), reinterpret_cast<float4*>(exp_avg),
+        reinterpret_cast<float4*>(exp_avg_sq), n4, state, found_inf, reinterpret_cast<__half2*>(half_out), half_skip / 4);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

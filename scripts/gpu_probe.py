@@ -13,7 +13,7 @@ o, d, near, far = oscene.camera_rays(fr, 512, 512)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 o, d, near, far = t(o), t(d), t(near), t(far)
 res = {}
-for rpw in (32, 16, 8, 4):
+for rpw in (8, 4, 2, 1):
   ops.set_option("render_rays_per_warp", rpw)
   for width in (512, 0):
     stats = ops.new_stats("cuda")

@@ -168,3 +168,34 @@ def test_adam_matches_torch(dev):
     ops.adam_step(p, g, m, v, 1e-2, (0.9, 0.99), 1e-15, 6, 1.0, found)
     torch.cuda.synchronize()
     assert found.item() == 1.0 and torch.equal(p, before)
+
+
+def test_adam_device_state_matches_torch(dev):
+    """graph-friendly variant: step count / bias corrections / 1/scale on the device, fused zero-grad + fp16 refresh"""
+    import torch
+    from instantavatar_b200 import ops
+    torch.manual_seed(1)
+    n = 40000
+    p0 = torch.randn(n, device="cuda"); p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    p = p0.clone(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    state = torch.tensor([1e-2, 0.9, 0.99, 1e-15, 0, 1, 1, 1], dtype=torch.float32).cuda()
+    found = torch.zeros(1, device="cuda"); scale = torch.full((1,), 1024.0, device="cuda")
+    half = torch.zeros(n - 8, device="cuda", dtype=torch.float16)
+    for step in range(1, 5):
+        g = torch.randn(n, device="cuda") * 0.1
+        p_ref.grad = g.clone(); opt.step()
+        gs = g * 1024.0 * 2  # scaled loss, summed over 2 ranks
+        ops.adam_prepare(state, 0.5, scale, found)
+        ops.adam_step_dev(p, gs, m, v, state, found, half, 8)
+        assert not gs.any()  # gradient consumed and zeroed
+    torch.cuda.synchronize()
+    assert state[4].item() == 4.0
+    assert torch.allclose(p, p_ref.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.equal(half, p[8:].half())
+    found.fill_(1.0)
+    before = p.clone()
+    ops.adam_prepare(state, 0.5, scale, found)
+    ops.adam_step_dev(p, torch.ones(n, device="cuda"), m, v, state, found, half, 8)
+    torch.cuda.synchronize()
+    assert torch.equal(p, before) and state[4].item() == 4.0
