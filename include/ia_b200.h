@@ -61,7 +61,7 @@ const char* ia_last_error(void);
 /* number of SMs of the current device (grid sizing is a multiple of this) [host result] */
 int ia_sm_count(void);
 
-/* tuning knobs (do not change results): "render_rays_per_warp" in {32,16,8,4}, "train_rays_per_warp" in {4,2,1} */
+/* tuning knobs (do not change results): "render_rays_per_warp" in {32,16,8,4,2,1}, "render_plan" in {0,1}, "train_rays_per_warp" in {4,2,1} */
 int ia_set_option(const char* name, int value);
 
 /* tiny-cuda-nn HashGrid level table (models/networks/ngp.py:27-37 config). [host] outputs. */
@@ -98,11 +98,14 @@ int ia_occupancy_build(const float* density, int G, uint8_t* field_out, uint32_t
  * NeRFNGPNet.forward (models/networks/ngp.py:73-83).
  * rays_o/rays_d [n][3], near/far [n] in the SMPL-root frame (after transform_rays_w2s); bg [n][3] or NULL (white).
  * Outputs rgb [n][3], depth [n], alpha [n], counter [n] (occupied samples evaluated per ray).
- * image_width: optional hint (>0: rays are a row-major image of that width -> 8x4 pixel warp tiles).
- * workspace: >= 256 bytes, zeroed by the library on the stream.  stats: nullable. */
+ * image_width: optional hint (>0: rays are a row-major image of that width -> small pixel tiles per warp).
+ * workspace: >= 256 bytes; with >= ia_render_workspace_bytes(n_rays) the tiles are scheduled longest-first from a
+ * cheap planning pass (same results).  stats: nullable. */
+size_t ia_render_workspace_bytes(int n_rays);
 int ia_render_fwd(const IaScene* scene /*[host]*/, const float* rays_o, const float* rays_d, const float* near,
                   const float* far, int n_rays, const float* bg, int image_width, float* rgb, float* depth,
-                  float* alpha, float* counter, void* workspace, IaStats* stats, ia_stream_t stream);
+                  float* alpha, float* counter, void* workspace, size_t workspace_bytes, IaStats* stats,
+                  ia_stream_t stream);
 
 /* Point query: per point, max density over the valid canonical correspondences.  Replaces
  * SNARFDeformer.__call__(pts, model, eval_mode) (deformers/snarf_deformer.py:126-165), used by

@@ -9,6 +9,7 @@
 using namespace ia;
 
 static int g_render_rays = 4;  // rays per warp (32 / 16 / 8 / 4), tunable through ia_set_option
+static int g_render_plan = 1;  // longest-first tile scheduling (needs the large workspace)
 static int g_train_rays = 2;   // rays per warp of the training forward (4 / 2 / 1)
 int ia_train_rays_per_warp() { return g_train_rays; }
 
@@ -28,6 +29,8 @@ struct RenderArgs {
     float* rgb; float* depth; float* alpha; float* counter;
     int* tile_counter;
     IaStats* stats;
+    const int* tile_order;   // optional: tiles sorted by decreasing estimated cost (render_plan kernels)
+    const int* n_active;     // number of entries of tile_order
 };
 
 struct RenderWarpExtra {
@@ -72,6 +75,98 @@ __device__ __forceinline__ void occupied_interval(const FrameConst& fc, const in
     }
 }
 
+template <int kRays>
+__device__ __forceinline__ int tile_ray(int tile, int rl, bool tiled, int image_width) {
+    constexpr int kTileW = kRays == 32 ? 8 : (kRays >= 8 ? 4 : (kRays >= 2 ? 2 : 1));
+    if (tiled) {
+        const int tiles_x = image_width / kTileW;
+        const int ty = tile / tiles_x, tx = tile % tiles_x;
+        return (ty * (kRays / kTileW) + rl / kTileW) * image_width + tx * kTileW + (rl % kTileW);
+    }
+    return tile * kRays + rl;
+}
+
+// Planning pass (longest-processing-time-first scheduling of the fused kernel): counts the occupied steps of every
+// ray (the scan of raymarcher.cu:13-73 without evaluating anything), reduces them per tile, and writes the
+// background result of tiles that cannot produce a sample.  The per-tile cost feeds order_tiles_kernel.
+template <int kRays>
+__global__ void __launch_bounds__(256) render_plan_kernel(const __grid_constant__ RenderArgs a, int* __restrict__ cost) {
+    __shared__ FrameConst fc;
+    load_frame_const(fc, a.sd);
+    __syncthreads();
+    constexpr int kTileW = kRays == 32 ? 8 : (kRays >= 8 ? 4 : (kRays >= 2 ? 2 : 1));
+    constexpr int kTileH = kRays / kTileW;
+    const int G = a.sd.s.G;
+    const uint32_t* occ = a.sd.s.occ_bits;
+    const int* cbox = reinterpret_cast<const int*>(occ + G * G * G / 32);
+    const bool tiled = a.image_width > 0 && (a.image_width % kTileW) == 0 && (a.n_rays % (a.image_width * kTileH)) == 0;
+    const int n_tiles = (a.n_rays + kRays - 1) / kRays;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tile = gid / kRays, rl = gid % kRays;
+    int cnt = 0, ray = -1;
+    if (tile < n_tiles) {
+        ray = tile_ray<kRays>(tile, rl, tiled, a.image_width);
+        if (ray < a.n_rays) {
+            const float ox = a.rays_o[ray * 3], oy = a.rays_o[ray * 3 + 1], oz = a.rays_o[ray * 3 + 2];
+            const float dx = a.rays_d[ray * 3], dy = a.rays_d[ray * 3 + 1], dz = a.rays_d[ray * 3 + 2];
+            float t = a.near[ray];
+            const float far = a.far[ray];
+            const float dt = (far - t) / (float)IA_MAX_SAMPLES;
+            float t0, t1;
+            occupied_interval(fc, cbox, G, ox, oy, oz, dx, dy, dz, t0, t1);
+            if (cbox[6] != 0 && t0 <= t1 && dt > 0.f) {
+                const float k0f = floorf((fmaxf(t0, t) - t) / dt) - 2.f, k1f = ceilf((fminf(t1, far) - t) / dt) + 2.f;
+                const int kbeg = (int)fminf(fmaxf(k0f, 0.f), 1024.f), kend = (int)fminf(fmaxf(k1f, -1.f), 1024.f);
+                for (int i = 0; i < kbeg; i++) t += dt;
+                for (int k = kbeg; k <= kend && t < far; k++) {
+                    const float x = __fmaf_rn(t, dx, ox), y = __fmaf_rn(t, dy, oy), z = __fmaf_rn(t, dz, oz);
+                    const int nx = (int)clampf((x - fc.occ_min[0]) * fc.occ_s[0], 0.0f, (float)G - 1.0f);
+                    const int ny = (int)clampf((y - fc.occ_min[1]) * fc.occ_s[1], 0.0f, (float)G - 1.0f);
+                    const int nz = (int)clampf((z - fc.occ_min[2]) * fc.occ_s[2], 0.0f, (float)G - 1.0f);
+                    const int bit = (nx * G + ny) * G + nz;
+                    cnt += (__ldg(occ + (bit >> 5)) >> (bit & 31)) & 1u;
+                    t += dt;
+                }
+            }
+        } else {
+            ray = -1;
+        }
+    }
+    int tot = cnt;
+#pragma unroll
+    for (int o = 1; o < kRays; o <<= 1) tot += __shfl_xor_sync(kFull, tot, o);
+    if (tile < n_tiles) {
+        if (rl == 0) cost[tile] = tot;
+        if (tot == 0 && ray >= 0) {  // no sample anywhere in the tile: the fused kernel would leave T = 1, C = 0
+            float b0 = 1.f, b1 = 1.f, b2 = 1.f;
+            if (a.bg) { b0 = a.bg[ray * 3]; b1 = a.bg[ray * 3 + 1]; b2 = a.bg[ray * 3 + 2]; }
+            a.rgb[ray * 3 + 0] = 0.f + 1.f * b0; a.rgb[ray * 3 + 1] = 0.f + 1.f * b1; a.rgb[ray * 3 + 2] = 0.f + 1.f * b2;
+            a.depth[ray] = 0.f; a.alpha[ray] = 0.f; a.counter[ray] = 0.f;
+        }
+    }
+}
+
+// one CTA: counting sort of the non-empty tiles by decreasing cost (256 buckets)
+__global__ void __launch_bounds__(1024) order_tiles_kernel(const int* __restrict__ cost, int n_tiles, int* __restrict__ order,
+                                                           int* __restrict__ n_active) {
+    __shared__ int hist[256];
+    __shared__ int offs[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    auto bucket = [](int c) { return 255 - min(255, c >> 2); };  // bucket 0 = most expensive
+    for (int i = threadIdx.x; i < n_tiles; i += blockDim.x)
+        if (cost[i] > 0) atomicAdd(&hist[bucket(cost[i])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < 256; b++) { offs[b] = acc; acc += hist[b]; }
+        *n_active = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_tiles; i += blockDim.x)
+        if (cost[i] > 0) order[atomicAdd(&offs[bucket(cost[i])], 1)] = i;
+}
+
 // kRays rays per warp, each marched kDepth = 32/kRays steps ahead (lane = depth * kRays + ray): the batch of 32
 // samples a warp evaluates stays spatially coherent (neighbouring pixels x consecutive steps) while the number of
 // independent work units grows by kDepth -- there are fewer hit rays in a 512^2 frame than resident lanes.
@@ -110,22 +205,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
 
     const bool tiled = a.image_width > 0 && (a.image_width % kTileW) == 0 && (a.n_rays % (a.image_width * kTileH)) == 0;
     const int n_tiles = (a.n_rays + kRays - 1) / kRays;
-    const int tiles_x = tiled ? a.image_width / kTileW : 1;
     const int rl = lane % kRays, jl = lane / kRays;
     unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_hit = 0;
 
     for (;;) {
         int tile = 0;
-        if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
+        if (lane == 0) {
+            tile = atomicAdd(a.tile_counter, 1);
+            if (a.tile_order) tile = tile < *a.n_active ? a.tile_order[tile] : n_tiles;
+        }
         tile = __shfl_sync(kFull, tile, 0);
         if (tile >= n_tiles) break;
-        int ray;
-        if (tiled) {
-            const int ty = tile / tiles_x, tx = tile % tiles_x;
-            ray = (ty * kTileH + rl / kTileW) * a.image_width + tx * kTileW + (rl % kTileW);
-        } else {
-            ray = tile * kRays + rl;
-        }
+        const int ray = tile_ray<kRays>(tile, rl, tiled, a.image_width);
         const bool has = ray < a.n_rays;
         float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, t = 0, far = 0, dt = 0;
         int k = jl, kend = -1;
@@ -571,6 +662,10 @@ int ia_set_option(const char* name, int value) {
         g_render_rays = value;
         return IA_OK;
     }
+    if (!strcmp(name, "render_plan")) {
+        g_render_plan = value != 0;
+        return IA_OK;
+    }
     if (!strcmp(name, "train_rays_per_warp")) {
         IA_REQUIRE(value == 4 || value == 2 || value == 1);
         g_train_rays = value;
@@ -637,9 +732,29 @@ int ia_pack_occupancy(const uint8_t* field_bool, uint32_t* bits, int G, ia_strea
 constexpr int kRenderWarps = 12;
 constexpr int kQueryWarps = 12;
 
+size_t ia_render_workspace_bytes(int n_rays) { return 256 + 2 * sizeof(int) * (size_t)(n_rays + 1); }
+
+}  // extern "C"
+
+template <int kRays>
+static int launch_render(RenderArgs& a, bool plan, int* ws_cost, int* ws_order, int grid, size_t smem, cudaStream_t st) {
+    if (plan) {
+        const int n_tiles = (a.n_rays + kRays - 1) / kRays;
+        const long threads = (long)n_tiles * kRays;
+        render_plan_kernel<kRays><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a, ws_cost);
+        order_tiles_kernel<<<1, 1024, 0, st>>>(ws_cost, n_tiles, ws_order, a.tile_counter + 1);
+        a.tile_order = ws_order;
+        a.n_active = a.tile_counter + 1;
+    }
+    render_fwd_kernel<kRenderWarps, kRays><<<grid, kRenderWarps * 32, smem, st>>>(a);
+    return 0;
+}
+
+extern "C" {
+
 int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d, const float* near, const float* far,
                   int n_rays, const float* bg, int image_width, float* rgb, float* depth, float* alpha, float* counter,
-                  void* workspace, IaStats* stats, ia_stream_t stream) {
+                  void* workspace, size_t workspace_bytes, IaStats* stats, ia_stream_t stream) {
     IA_REQUIRE(n_rays >= 0);
     if (n_rays == 0) return IA_OK;
     IA_REQUIRE(rays_o && rays_d && near && far && rgb && depth && alpha && counter && workspace);
@@ -649,10 +764,16 @@ int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d
     a.rays_o = rays_o; a.rays_d = rays_d; a.near = near; a.far = far; a.bg = bg;
     a.n_rays = n_rays; a.image_width = image_width;
     a.rgb = rgb; a.depth = depth; a.alpha = alpha; a.counter = counter;
+    IA_REQUIRE(workspace_bytes >= 256);
     a.tile_counter = reinterpret_cast<int*>(workspace);
     a.stats = stats;
+    a.tile_order = nullptr; a.n_active = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+    // with a large enough workspace the tiles are scheduled longest-first (removes the load-balance tail)
+    const bool plan = g_render_plan && workspace_bytes >= ia_render_workspace_bytes(n_rays);
+    int* ws_cost = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + 256);
+    int* ws_order = ws_cost + (n_rays + 1);
     const size_t smem = sizeof(RenderSmem<kRenderWarps>);
     static bool attr_set = false;
     if (!attr_set) {
@@ -670,12 +791,12 @@ int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d
     if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
     grid = min(grid, (n_tiles + kRenderWarps - 1) / kRenderWarps);
     switch (rpw) {
-        case 32: render_fwd_kernel<kRenderWarps, 32><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
-        case 16: render_fwd_kernel<kRenderWarps, 16><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
-        case 4: render_fwd_kernel<kRenderWarps, 4><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
-        case 2: render_fwd_kernel<kRenderWarps, 2><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
-        case 1: render_fwd_kernel<kRenderWarps, 1><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
-        default: render_fwd_kernel<kRenderWarps, 8><<<grid, kRenderWarps * 32, smem, st>>>(a); break;
+        case 32: launch_render<32>(a, plan, ws_cost, ws_order, grid, smem, st); break;
+        case 16: launch_render<16>(a, plan, ws_cost, ws_order, grid, smem, st); break;
+        case 4: launch_render<4>(a, plan, ws_cost, ws_order, grid, smem, st); break;
+        case 2: launch_render<2>(a, plan, ws_cost, ws_order, grid, smem, st); break;
+        case 1: launch_render<1>(a, plan, ws_cost, ws_order, grid, smem, st); break;
+        default: launch_render<8>(a, plan, ws_cost, ws_order, grid, smem, st); break;
     }
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;

@@ -131,11 +131,12 @@ def render_fwd(scene: Scene, rays_o, rays_d, near, far, bg=None, image_width: in
         out = {"rgb": torch.empty((n, 3), device=dev, dtype=f32), "depth": torch.empty(n, device=dev, dtype=f32),
                "alpha": torch.empty(n, device=dev, dtype=f32), "counter": torch.empty(n, device=dev, dtype=f32)}
     if workspace is None:
-        workspace = torch.empty(64, device=dev, dtype=torch.int32)
+        workspace = torch.empty(int(lib().ia_render_workspace_bytes(C.c_int(n))), device=dev, dtype=torch.uint8)
     s = scene.c_struct()
-    _lib.count(1); check(lib().ia_render_fwd(C.byref(s), ptr(rays_o, f32), ptr(rays_d, f32), ptr(near, f32), ptr(far, f32), C.c_int(n),
+    _lib.count(3); check(lib().ia_render_fwd(C.byref(s), ptr(rays_o, f32), ptr(rays_d, f32), ptr(near, f32), ptr(far, f32), C.c_int(n),
                               ptr(bg), C.c_int(image_width), ptr(out["rgb"]), ptr(out["depth"]), ptr(out["alpha"]),
-                              ptr(out["counter"]), ptr(workspace), ptr(stats), stream()))
+                              ptr(out["counter"]), ptr(workspace), C.c_size_t(workspace.numel() * workspace.element_size()),
+                              ptr(stats), stream()))
     return out
 
 

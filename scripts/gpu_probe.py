@@ -13,8 +13,8 @@ o, d, near, far = oscene.camera_rays(fr, 512, 512)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 o, d, near, far = t(o), t(d), t(near), t(far)
 res = {}
-for rpw in (8, 4, 2, 1):
-  ops.set_option("render_rays_per_warp", rpw)
+for rpw, plan in ((8, 0), (8, 1), (4, 0), (4, 1), (2, 1)):
+  ops.set_option("render_rays_per_warp", rpw); ops.set_option("render_plan", plan)
   for width in (512, 0):
     stats = ops.new_stats("cuda")
     out = ops.render_fwd(scene, o, d, near, far, None, width, stats)
@@ -25,7 +25,7 @@ for rpw in (8, 4, 2, 1):
     for i in range(20):
         ev0.record(); ops.render_fwd(scene, o, d, near, far, None, width, None, out); ev1.record(); torch.cuda.synchronize()
         ts.append(ev0.elapsed_time(ev1))
-    key = f"rpw{rpw}_width{width}"
+    key = f"rpw{rpw}_plan{plan}_width{width}"
     res[key] = {"ms_median": float(np.median(ts)), "ms_min": float(min(ts)), "stats": st,
                 "rays_per_s": 262144 / (np.median(ts) * 1e-3), "alpha_sum": float(out["alpha"].sum())}
     print(key, res[key])
