@@ -163,6 +163,47 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def bench_ref_structure(model, batch, device, iters=5):
+    """The reference's own CUDA kernels (oracle/_ref, built from /root/reference) + the reference's host loop, with this
+    repo's hash-grid/MLP standing in for tiny-cuda-nn, on the same frame: per-frame time of precompute +
+    DensityGrid.initialize + render_test (bench infrastructure; see oracle/ref_structure.py)."""
+    import torch
+    try:
+        from oracle import ref_structure
+        if not ref_structure.available():
+            return {"unavailable": "oracle/_ref not built"}
+        from instantavatar_b200.models.dnerf import Rays
+        dfm = model.deformer
+        rs = ref_structure.RefStructure(dfm.deformer.lbs_voxel_final, dfm.deformer.offset_kernel, dfm.deformer.scale_kernel,
+                                        lambda x: model.net_coarse(x))
+        model.eval()
+        dfm.prepare_deformer(batch)
+        r = Rays(o=batch["rays_o"].clone(), d=batch["rays_d"].clone(), near=batch["near"].clone(), far=batch["far"].clone())
+        dfm.transform_rays_w2s(r)
+        o, d = r.o.reshape(-1, 3).contiguous(), r.d.reshape(-1, 3).contiguous()
+        near, far = r.near.reshape(-1).contiguous(), r.far.reshape(-1).contiguous()
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        t_all, t_march = [], []
+        for i in range(iters + 2):
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record()
+            rs.precompute(dfm.tfs)
+            rs.density_grid_initialize()
+            e1.record()
+            out = rs.render_test(o, d, near, far)
+            e2.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                t_all.append(e0.elapsed_time(e2)); t_march.append(e1.elapsed_time(e2))
+        ms = float(np.median(t_all))
+        return {"ms_per_frame": ms, "rays_per_s": N_RAYS / (ms * 1e-3), "ms_render_test_only": float(np.median(t_march)),
+                "alpha_sum": float(out["alpha"].sum().item()),
+                "what": "reference kernels (raymarcher.cu, fuse_cuda_kernel_fast.cu, filter.cu, precompute.cu built for sm_100) + "
+                        "reference host loop; tiny-cuda-nn replaced by ia_ngp_forward; SMPL forward excluded"}
+    except Exception as e:  # the checker must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, use_graph=True):
     """second half of BASELINE.json's metric: ms per training step (DNeRF.py:112-161) at 4096 rays per step
     (4 patches of 32x32, confs/sampler/patch.yaml), rays sharded over the ranks, one gradient all-reduce per step;
@@ -324,6 +365,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     occ_ms = float(np.median([a.elapsed_time(b) for a, b in qev]))
 
+    ref_struct = bench_ref_structure(model, batch, device) if rank == 0 else None
     train = bench_train(model, batch, device, rank, world, flush, use_graph=use_graph)
 
     if rank != 0:
@@ -363,6 +405,7 @@ def run_ours(args):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
         "train": train,
+        "ref_structure": ref_struct,
         "roofline": {"kernel": "render_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": algo_bytes,
