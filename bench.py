@@ -125,6 +125,7 @@ class CpuFrame:
         from oracle import capi, scene as oscene
         from instantavatar_b200 import synthetic
         self.capi = capi
+        capi.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
         self.subj = oscene.build_subject()
         self.net = oscene.build_net(self.subj)
         self.pose = synthetic.load_pose(frame)
