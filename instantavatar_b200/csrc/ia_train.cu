@@ -526,87 +526,110 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) ngp_backward_kernel(const _
     }
 }
 
-// weight gradients: dW_l[o][i] += sum_rows dZ_l[row][o] * In_l[row][i] from the scratch rows
+// weight gradients on tensor cores: dW_l[o][i] += sum_rows dZ_l[row][o] * In_l[row][i] from the scratch rows.
+// Per 32-row chunk (K = 32) both operands are read transposed out of the row-major shared-memory tile with
+// ldmatrix.trans (row stride 912 B = 228 words: the 8 row addresses of a matrix fall in disjoint bank groups).
+// The 8 warps own disjoint slices of the five gradient matrices in registers (36 fp32 per lane) for the whole kernel
+// and flush once with fp32 atomics.
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+// A fragment of dZ^T: m-tile rows o0..o0+15 (full = false: only o0..o0+7 exist), k-tile rows r0..r0+15 of the chunk
+__device__ __forceinline__ void load_a_t(const __half* rows, int off, int o0, int r0, int lane, bool full, uint32_t a[4]) {
+    const int j = lane >> 3, i = lane & 7;  // matrix j, row i
+    if (full) {
+        const __half* p = rows + (r0 + (j >> 1) * 8 + i) * kRowHalfs + off + o0 + (j & 1) * 8;
+        ldsm_x4_t(smem_u32(p), a[0], a[1], a[2], a[3]);
+    } else {
+        const __half* p = rows + (r0 + (j & 1) * 8 + i) * kRowHalfs + off + o0;
+        ldsm_x2_t(smem_u32(p), a[0], a[2]);
+        a[1] = 0u; a[3] = 0u;
+    }
+}
+// B fragments of the input for two adjacent n-tiles (i0..i0+7, i0+8..i0+15), k-tile rows r0..r0+15
+__device__ __forceinline__ void load_b_t2(const __half* rows, int off, int i0, int r0, int lane, uint32_t b[4]) {
+    const int j = lane >> 3, i = lane & 7;
+    const __half* p = rows + (r0 + (j & 1) * 8 + i) * kRowHalfs + off + i0 + (j >> 1) * 8;
+    ldsm_x4_t(smem_u32(p), b[0], b[1], b[2], b[3]);  // {b0,b1} of n-tile 0, {b0,b1} of n-tile 1
+}
+
 __global__ void __launch_bounds__(256) wgrad_kernel(const __half* __restrict__ scratch, const int* __restrict__ count_p, int capacity,
                                                     float inv_scale, float* __restrict__ grad_enc, float* __restrict__ grad_col) {
     constexpr int kChunk = 32;
-    __shared__ __align__(16) __half rows[kChunk][kRowHalfs];
-    const int t = threadIdx.x;
+    __shared__ __align__(16) __half rows[kChunk * kRowHalfs];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int count = min(*count_p, capacity);
-    float a4[16], a1[8], a2[4], a3[4], a5[2];
+    float c4[4][4], c1[2][4], c2[4], c3[4], c5[4];
 #pragma unroll
-    for (int i = 0; i < 16; i++) a4[i] = 0.f;
+    for (int i = 0; i < 4; i++) {
+        c2[i] = c3[i] = c5[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; i++) a1[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; i++) { a2[i] = 0.f; a3[i] = 0.f; }
-    a5[0] = a5[1] = 0.f;
-    const int o4 = t / 4, i4 = (t % 4) * 16;   // W4 [64][64]
-    const int o1 = t / 4, i1 = (t % 4) * 8;    // W1 [64][32]
-    const int o2 = t / 16, i2 = (t % 16) * 4;  // W2 [16][64]
-    const int o3 = t / 4, i3 = (t % 4) * 4;    // W3' [64][16]
-    const int o5 = t / 32, i5 = (t % 32) * 2;  // W5 [8][64]
+        for (int j = 0; j < 4; j++) c4[j][i] = 0.f;
+        c1[0][i] = c1[1][i] = 0.f;
+    }
+    const int mt = w >> 1, half = w & 1;
     for (int base = blockIdx.x * kChunk; base < count; base += gridDim.x * kChunk) {
         const int n = min(kChunk, count - base);
         __syncthreads();
         const uint4* src = reinterpret_cast<const uint4*>(scratch + (long)base * kRowHalfs);
-        uint4* dst = reinterpret_cast<uint4*>(&rows[0][0]);
-        for (int i = t; i < n * (kRowHalfs / 8); i += 256) dst[i] = src[i];
+        uint4* dst = reinterpret_cast<uint4*>(rows);
+        constexpr int kVecPerRow = kRowHalfs / 8;
+        for (int i = t; i < kChunk * kVecPerRow; i += 256) dst[i] = i < n * kVecPerRow ? src[i] : make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
-        for (int r = 0; r < n; r++) {
-            const __half* row = rows[r];
-            auto ld8 = [&](int off, float* o) {  // 8 consecutive halfs -> floats (16-byte aligned offsets)
-                const uint4 u = *reinterpret_cast<const uint4*>(row + off);
-                const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-                for (int q = 0; q < 4; q++) { const float2 f = __half22float2(h[q]); o[2 * q] = f.x; o[2 * q + 1] = f.y; }
-            };
-            float in[16];
-            const float d4 = __half2float(row[kOffD4 + o4]);
-            ld8(kOffH2 + i4, in); ld8(kOffH2 + i4 + 8, in + 8);
+        for (int kt = 0; kt < 2; kt++) {
+            const int r0 = kt * 16;
+            uint32_t a[4], b[4];
+            // W4: dZ3^T (64 x rows) . h2 (rows x 64): this warp's m-tile `mt`, n-tiles half*4 .. half*4+3
+            load_a_t(rows, kOffD4, mt * 16, r0, lane, true, a);
 #pragma unroll
-            for (int i = 0; i < 16; i++) a4[i] = __fmaf_rn(d4, in[i], a4[i]);
-            const float d1 = __half2float(row[kOffD1 + o1]);
-            ld8(kOffEnc + i1, in);
-#pragma unroll
-            for (int i = 0; i < 8; i++) a1[i] = __fmaf_rn(d1, in[i], a1[i]);
-            const float d2 = __half2float(row[kOffD2 + o2]);
-            {
-                const uint2 u = *reinterpret_cast<const uint2*>(row + kOffH1 + i2);
-                const __half2* h = reinterpret_cast<const __half2*>(&u);
-                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-                a2[0] = __fmaf_rn(d2, f0.x, a2[0]); a2[1] = __fmaf_rn(d2, f0.y, a2[1]);
-                a2[2] = __fmaf_rn(d2, f1.x, a2[2]); a2[3] = __fmaf_rn(d2, f1.y, a2[3]);
+            for (int np = 0; np < 2; np++) {
+                load_b_t2(rows, kOffH2, (half * 4 + np * 2) * 8, r0, lane, b);
+                mma16816(c4[np * 2], a, b[0], b[1]);
+                mma16816(c4[np * 2 + 1], a, b[2], b[3]);
             }
-            const float d3 = __half2float(row[kOffD3 + o3]);
-            {
-                const uint2 u = *reinterpret_cast<const uint2*>(row + kOffC3 + i3);
-                const __half2* h = reinterpret_cast<const __half2*>(&u);
-                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-                a3[0] = __fmaf_rn(d3, f0.x, a3[0]); a3[1] = __fmaf_rn(d3, f0.y, a3[1]);
-                a3[2] = __fmaf_rn(d3, f1.x, a3[2]); a3[3] = __fmaf_rn(d3, f1.y, a3[3]);
-            }
-            const float d5 = __half2float(row[kOffD5 + o5]);
-            {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(row + kOffH3 + i5));
-                a5[0] = __fmaf_rn(d5, f.x, a5[0]); a5[1] = __fmaf_rn(d5, f.y, a5[1]);
-            }
+            // W1: dZ1^T (64 x rows) . enc (rows x 32): m-tile mt, n-tiles half*2, half*2+1
+            load_a_t(rows, kOffD1, mt * 16, r0, lane, true, a);
+            load_b_t2(rows, kOffEnc, half * 16, r0, lane, b);
+            mma16816(c1[0], a, b[0], b[1]);
+            mma16816(c1[1], a, b[2], b[3]);
+            // W3': dZ2'^T (64 x rows) . c3 (rows x 16): m-tile mt, n-tile half
+            load_a_t(rows, kOffD3, mt * 16, r0, lane, true, a);
+            load_b_t2(rows, kOffC3, 0, r0, lane, b);
+            if (half == 0) mma16816(c3, a, b[0], b[1]); else mma16816(c3, a, b[2], b[3]);
+            // W2: dOut16^T (16 x rows) . h1 (rows x 64): n-tile w ;  W5: dO5^T (8 x rows) . h3: n-tile w
+            load_b_t2(rows, kOffH1, (w >> 1) * 16, r0, lane, b);
+            load_a_t(rows, kOffD2, 0, r0, lane, true, a);
+            if ((w & 1) == 0) mma16816(c2, a, b[0], b[1]); else mma16816(c2, a, b[2], b[3]);
+            load_b_t2(rows, kOffH3, (w >> 1) * 16, r0, lane, b);
+            load_a_t(rows, kOffD5, 0, r0, lane, false, a);
+            if ((w & 1) == 0) mma16816(c5, a, b[0], b[1]); else mma16816(c5, a, b[2], b[3]);
         }
     }
-    // flush (tcnn parameter order; W3 column un-rotation: column 0 of W3' is the pad column 15 of W3)
+    // flush: accumulator (g, t) holds D[m = g (+8)][n = 2t (+1)] ; tcnn parameter order, W3 column un-rotation
+    const int g = lane >> 2, tt = lane & 3;
+    auto flush = [&](float* dst, int stride, int o0, int i0, const float c[4], int omax) {
+        if (o0 + g < omax) { atomicAdd(dst + (o0 + g) * stride + i0 + 2 * tt, c[0] * inv_scale); atomicAdd(dst + (o0 + g) * stride + i0 + 2 * tt + 1, c[1] * inv_scale); }
+        if (o0 + g + 8 < omax) { atomicAdd(dst + (o0 + g + 8) * stride + i0 + 2 * tt, c[2] * inv_scale); atomicAdd(dst + (o0 + g + 8) * stride + i0 + 2 * tt + 1, c[3] * inv_scale); }
+    };
 #pragma unroll
-    for (int i = 0; i < 16; i++) atomicAdd(&grad_col[1024 + o4 * 64 + i4 + i], a4[i] * inv_scale);
-#pragma unroll
-    for (int i = 0; i < 8; i++) atomicAdd(&grad_enc[o1 * 32 + i1 + i], a1[i] * inv_scale);
-#pragma unroll
-    for (int i = 0; i < 4; i++) atomicAdd(&grad_enc[2048 + o2 * 64 + i2 + i], a2[i] * inv_scale);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int c = i3 + i;
-        atomicAdd(&grad_col[o3 * 16 + (c == 0 ? 15 : c - 1)], a3[i] * inv_scale);
+    for (int q = 0; q < 4; q++) flush(grad_col + 1024, 64, mt * 16, (half * 4 + q) * 8, c4[q], 64);
+    flush(grad_enc, 32, mt * 16, half * 16, c1[0], 64);
+    flush(grad_enc, 32, mt * 16, half * 16 + 8, c1[1], 64);
+    flush(grad_enc + 2048, 64, 0, w * 8, c2, 16);
+    flush(grad_col + 1024 + 4096, 64, 0, w * 8, c5, 8);
+    {   // W3' (column c of W3' = column c-1 of W3, column 0 = the pad column 15)
+        const int i0 = half * 8 + 2 * tt;
+        auto col3 = [](int c) { return c == 0 ? 15 : c - 1; };
+        atomicAdd(grad_col + (mt * 16 + g) * 16 + col3(i0), c3[0] * inv_scale);
+        atomicAdd(grad_col + (mt * 16 + g) * 16 + col3(i0 + 1), c3[1] * inv_scale);
+        atomicAdd(grad_col + (mt * 16 + g + 8) * 16 + col3(i0), c3[2] * inv_scale);
+        atomicAdd(grad_col + (mt * 16 + g + 8) * 16 + col3(i0 + 1), c3[3] * inv_scale);
     }
-#pragma unroll
-    for (int i = 0; i < 2; i++) atomicAdd(&grad_col[1024 + 4096 + o5 * 64 + i5 + i], a5[i] * inv_scale);
 }
 
 // ================================================================================================
