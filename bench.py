@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays-per-warp", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--train-rays-per-warp", type=int, default=0)
     return ap.parse_args()
 
 
@@ -278,6 +279,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     if args.rays_per_warp:
         ops.set_option("render_rays_per_warp", args.rays_per_warp)
+    if args.train_rays_per_warp:
+        ops.set_option("train_rays_per_warp", args.train_rays_per_warp)
 
     frame = FRAMES[rank % len(FRAMES)]
     model, hb, batch = build_model(device, frame)

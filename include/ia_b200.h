@@ -118,9 +118,10 @@ int ia_deform_query(const IaScene* scene /*[host]*/, const float* pts, int n, in
 
 /* DensityGrid.initialize's density pass (models/structures/density_grid.py:94-103) in one launch: for each of
  * `passes` jitter tensors [G][G][G][3] the G^3 cell points (idx/G + jitter/G) * (max - min) + min are queried in eval
- * mode and max(sigma, 0) is reduced into density_max [G][G][G] (zeroed by the library).  aabb [6] device. */
+ * mode and max(sigma, 0) is reduced into density_max [G][G][G] (zeroed by the library).  aabb [6] device.
+ * workspace: nullable; >= 256 bytes enables dynamic batch scheduling. */
 int ia_occupancy_query(const IaScene* scene /*[host]*/, const float* jitter, const float* aabb, int G, int passes,
-                       float* density_max, IaStats* stats, ia_stream_t stream);
+                       float* density_max, void* workspace, IaStats* stats, ia_stream_t stream);
 
 /* Fine-grained entry points (serve the legacy `model(pts)` callback path and the tinycudann-named shim):
  * ia_broyden replaces fuse_kernel.fuse_broyden + filter_cuda.filter
