@@ -133,6 +133,20 @@ int ia_broyden(const IaScene* scene /*[host]*/, const float* xd, int n, float* x
 int ia_ngp_forward(const IaScene* scene /*[host]*/, const float* x, int n, float* sigma, float* rgb,
                    ia_stream_t stream);
 
+/* Kernel-for-kernel replacements of the reference's raymarcher extension (renderers/cuda/raymarcher.cpp:16-81), for
+ * the legacy `model(pts)` callback path.  Layouts are the reference's: density_grid bool [G][G][G], alive int64,
+ * outputs zero-initialised by the caller (the reference allocates them with at::zeros), `nears` / `color` / `depth` /
+ * `no_hit` updated in place. */
+int ia_raymarch_train(const float* rays_o, const float* rays_d, const float* nears, const float* fars, int n_rays,
+                      const uint8_t* density_grid, int grid_size, const float* scale, const float* offset,
+                      const float* step_size, int N_steps, float* depths, ia_stream_t stream);
+int ia_raymarch_test(const float* rays_o, const float* rays_d, float* nears, const float* fars, const int64_t* alive,
+                     int n_alive, const uint8_t* density_grid, int grid_size, const float* scale, const float* offset,
+                     const float* step_size, int N_steps, float* pts, float* deltas, float* depths, ia_stream_t stream);
+int ia_composite_test(const float* rgb_vals, const float* sigma_vals, const float* delta_vals, const float* depth_vals,
+                      const int64_t* alive, int n_alive, int N_steps, float* color, float* depth, float* no_hit,
+                      float thresh, ia_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Training path
  * --------------------------------------------------------------------------------------------------------- */

@@ -255,3 +255,40 @@ def adam_step_dev(params, grads, exp_avg, exp_avg_sq, state, found_inf=None, hal
 
 def mlp_to_half(enc_params, col_params, mlp_h):
     _lib.count(1); check(lib().ia_mlp_to_half(ptr(enc_params, f32), ptr(col_params, f32), ptr(mlp_h), stream()))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# legacy kernel-for-kernel operators (raymarch_kernel.* of the reference, renderers/cuda/raymarcher.cpp:77-81)
+# ------------------------------------------------------------------------------------------------------------------
+def _grid_u8(density_grid):
+    g = density_grid.contiguous()
+    return g.view(torch.uint8) if g.dtype == torch.bool else g
+
+
+def raymarch_train(rays_o, rays_d, nears, fars, density_grid, scale, offset, step_size, N_steps):
+    n = rays_o.shape[0]
+    depths = torch.zeros((n, N_steps), device=rays_o.device, dtype=f32)
+    _lib.count(1); check(lib().ia_raymarch_train(ptr(rays_o, f32), ptr(rays_d, f32), ptr(nears, f32), ptr(fars, f32), C.c_int(n),
+                                                 ptr(_grid_u8(density_grid)), C.c_int(density_grid.shape[0]), ptr(scale, f32), ptr(offset, f32),
+                                                 ptr(step_size, f32), C.c_int(N_steps), ptr(depths), stream()))
+    return depths
+
+
+def raymarch_test(rays_o, rays_d, nears, fars, alives, density_grid, scale, offset, step_size, N_steps):
+    """returns [pts, deltas, depths]; `nears` is advanced in place (raymarcher.cu:72)"""
+    a = alives.shape[0]
+    dev = rays_o.device
+    pts = torch.zeros((a, N_steps, 3), device=dev, dtype=f32); deltas = torch.zeros((a, N_steps), device=dev, dtype=f32)
+    depths = torch.zeros((a, N_steps), device=dev, dtype=f32)
+    _lib.count(1); check(lib().ia_raymarch_test(ptr(rays_o, f32), ptr(rays_d, f32), ptr(nears, f32), ptr(fars, f32), ptr(alives, torch.int64),
+                                                C.c_int(a), ptr(_grid_u8(density_grid)), C.c_int(density_grid.shape[0]), ptr(scale, f32),
+                                                ptr(offset, f32), ptr(step_size, f32), C.c_int(N_steps), ptr(pts), ptr(deltas), ptr(depths), stream()))
+    return [pts, deltas, depths]
+
+
+def composite_test(rgb_vals, sigma_vals, delta_vals, depth_vals, alive_indices, color, depth, no_hit, thresh):
+    a = alive_indices.shape[0]
+    n_steps = sigma_vals.shape[1] if a else 0
+    _lib.count(1); check(lib().ia_composite_test(ptr(rgb_vals.contiguous(), f32), ptr(sigma_vals.contiguous(), f32), ptr(delta_vals, f32),
+                                                 ptr(depth_vals, f32), ptr(alive_indices, torch.int64), C.c_int(a), C.c_int(n_steps),
+                                                 ptr(color, f32), ptr(depth, f32), ptr(no_hit, f32), C.c_float(thresh), stream()))

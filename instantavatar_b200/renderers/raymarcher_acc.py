@@ -62,10 +62,47 @@ class Raymarcher(torch.nn.Module):
         return self.render_train(rays, model, noise, bg_color)
 
     @torch.no_grad()
+    def render_test_legacy(self, rays, model, bg_color):
+        """raymarcher_acc.py:82-138 verbatim control flow on the kernel-for-kernel operators, for any `model(pts, None)`
+        callable (host-synchronous window loop, as in the reference)."""
+        device = rays.o.device
+        rays_o = rays.o.reshape(-1, 3).float().contiguous()
+        rays_d = rays.d.reshape(-1, 3).float().contiguous()
+        near = rays.near.reshape(-1).float().clone()
+        far = rays.far.reshape(-1).float().contiguous()
+        N = rays_o.shape[0]
+        color = torch.zeros(N, 3, device=device); depth = torch.zeros(N, device=device)
+        no_hit = torch.ones(N, device=device); counter = torch.zeros_like(depth)
+        alive = torch.arange(N, device=device)
+        step_size = ((far - near) / self.MAX_SAMPLES).contiguous()
+        grid = self.density_grid_test
+        offset = grid.min_corner.float().contiguous(); scale = (grid.max_corner - grid.min_corner).float().contiguous()
+        k = 0
+        while k < self.MAX_SAMPLES:
+            N_alive = len(alive)
+            if N_alive == 0:
+                break
+            N_step = max(min(self.MAX_BATCH_SIZE // N_alive, self.MAX_SAMPLES), 1)
+            pts, d_new, z_new = ops.raymarch_test(rays_o, rays_d, near, far, alive, grid.density_field, scale, offset, step_size, N_step)
+            counter[alive] += (d_new > 0).sum(dim=-1)
+            mask = d_new > 0
+            rgb_vals = torch.zeros_like(pts); sigma_vals = torch.zeros_like(rgb_vals[..., 0])
+            if mask.any():
+                r, s = model(pts[mask], None)
+                rgb_vals[mask], sigma_vals[mask] = r.float(), s.float()
+            ops.composite_test(rgb_vals, sigma_vals, d_new, z_new, alive, color, depth, no_hit, 0.01)
+            alive = alive[(no_hit[alive] > 1e-4) & (z_new[:, -1] > 0)]
+            k += N_step
+        bg = bg_color.reshape(-1, 3) if bg_color is not None else 1.0
+        color = color + no_hit[..., None] * bg
+        return {"rgb_coarse": color.reshape(rays.o.shape), "depth_coarse": depth.reshape(rays.near.shape),
+                "alpha_coarse": (1 - no_hit).reshape(rays.near.shape), "counter_coarse": counter.reshape(rays.near.shape)}
+
+    @torch.no_grad()
     def render_test(self, rays, model, bg_color, stats=None):
         bound = _unwrap(model)
         if bound is None:
-            raise NotImplementedError("Raymarcher.render_test: only SNARFDeformer + NeRFNGPNet models are fused")
+            return self.render_test_legacy(rays, model, bg_color)
         deformer, net = bound
         net.initialize(deformer.bbox)
         grid = self.density_grid_test
