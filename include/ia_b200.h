@@ -75,6 +75,15 @@ int ia_hashgrid_layout(uint32_t res[IA_NUM_LEVELS], float scale[IA_NUM_LEVELS], 
 int ia_precompute(const float* voxel_w, const float* tfs, const float* offset_k, const float* scale_k, int D, int H,
                   int W, float* field_out, float* voxel_d_out, float* aabb_out, ia_stream_t stream);
 
+/* Per-frame bone transforms in one launch.  Replaces, for everything the renderer consumes, the SMPL forward + tfs
+ * algebra of SNARFDeformer.prepare_deformer (deformers/snarf_deformer.py:79-86; smplx/lbs.py:295-329 Rodrigues,
+ * :345-401 kinematic chain; body_models.py:353-360 transl): global_orient [3], body_pose [69], transl [3] (nullable),
+ * joints [24][3] rest-pose joint locations of the subject (function of betas only; cached by the caller), parents [24]
+ * (int32, -1 for the root), tfs_inv_t [24][4][4] inverse canonical-pose transforms (snarf_deformer.py:52).
+ * Outputs tfs [24][4][4], w2s [4][4], A_out [24][4][4] (nullable). */
+int ia_smpl_tfs(const float* global_orient, const float* body_pose, const float* transl, const float* joints,
+                const int* parents, const float* tfs_inv_t, float* tfs, float* w2s, float* A_out, ia_stream_t stream);
+
 /* fp32 master parameters -> fp16 working copies (tiny-cuda-nn casts params to fp16 every forward).
  * enc_params [3072 + 2*total] = [W1 64x32 | W2 16x64 | grid]; col_params [6144] = [W3 64x16 | W4 64x64 | W5 16x64]
  * (models/networks/ngp.py:27-57 `encoder.params`, `color_net.params`). */
@@ -179,6 +188,14 @@ size_t ia_ngp_backward_scratch_bytes(int capacity);
 int ia_ngp_backward(const IaScene* scene /*[host]*/, const float* xc, const float* dsigma, const float* drgb,
                     const int* count, int capacity, float grad_scale, float* grad_enc, float* grad_col, void* scratch,
                     ia_stream_t stream);
+
+/* NeRFLoss forward + analytic backward in one pass (instant_avatar/utils/loss.py:53-79):
+ * loss = w_rgb mse(rgb) + w_alpha mse(alpha) + w_reg (mean reg(alpha) + mean reg(weights) + 2*0.313262),
+ * reg(x) = -log(exp(-x) + exp(x-1)).  sums [4] receives {sum (rgb-t)^2, sum (alpha-a)^2, sum reg(alpha), sum reg(w)};
+ * g_* receive d loss / d output times *scale_dev (GradScaler scale; NULL = 1). */
+int ia_nerf_loss(int n_rays, int n_samples, const float* rgb, const float* alpha, const float* weights,
+                 const float* target_rgb, const float* target_alpha, float w_rgb, float w_alpha, float w_reg,
+                 const float* scale_dev, float* g_rgb, float* g_alpha, float* g_weights, float* sums, ia_stream_t stream);
 
 /* Fused dense Adam (torch.optim.Adam semantics, models/DNeRF.py:46-50) on a flat fp32 tensor; gradients are
  * multiplied by inv_grad_scale (GradScaler unscale, DNeRF.py:157-158); if found_inf (device, nullable) is non-zero

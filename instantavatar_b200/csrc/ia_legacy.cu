@@ -137,3 +137,91 @@ int ia_composite_test(const float* rgb_vals, const float* sigma_vals, const floa
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// per-frame bone transforms in one launch
+// ================================================================================================
+// Replaces the SMPL forward + tfs algebra of SNARFDeformer.prepare_deformer (snarf_deformer.py:79-86) for everything the
+// renderer needs: the 24 bone transforms depend on the pose only through Rodrigues + the kinematic chain
+// (smplx/lbs.py:295-329,345-401); joint locations J depend on betas alone and are cached by the caller; the pose blend
+// shapes only move vertices, which the hot path never reads.
+//   A_j   = chain_j [R | rel] ... minus the rest-pose joint (lbs.py:396-399), + transl (body_models.py:353-360)
+//   w2s   = A_0^-1 (rigid, closed form) ;  tfs_j = w2s . A_j . tfs_inv_t_j
+namespace {
+
+__device__ __forceinline__ void mat4_mul(const float* a, const float* b, float* c) {
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            float s = 0.f;
+            for (int k = 0; k < 4; k++) s = __fmaf_rn(a[i * 4 + k], b[k * 4 + j], s);
+            c[i * 4 + j] = s;
+        }
+}
+
+__global__ void __launch_bounds__(32) smpl_tfs_kernel(const float* __restrict__ global_orient, const float* __restrict__ body_pose,
+                                                      const float* __restrict__ transl, const float* __restrict__ J,
+                                                      const int* __restrict__ parents, const float* __restrict__ tfs_inv_t,
+                                                      float* __restrict__ tfs, float* __restrict__ w2s_out, float* __restrict__ A_out) {
+    __shared__ float tm[24][16], chain[24][16], A[24][16], w2s[16];
+    const int j = threadIdx.x;
+    if (j < 24) {
+        // Rodrigues (lbs.py:295-329): angle = ||r + 1e-8||, K from r/angle, R = I + sin K + (1-cos) K^2
+        const float* r = j == 0 ? global_orient : body_pose + (j - 1) * 3;
+        const float ax = r[0] + 1e-8f, ay = r[1] + 1e-8f, az = r[2] + 1e-8f;
+        const float angle = sqrtf(ax * ax + ay * ay + az * az);
+        const float rx = r[0] / angle, ry = r[1] / angle, rz = r[2] / angle;
+        const float s = sinf(angle), c = 1.f - cosf(angle);
+        const float K[9] = {0.f, -rz, ry, rz, 0.f, -rx, -ry, rx, 0.f};
+        float K2[9];
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) K2[a * 3 + b] = K[a * 3] * K[b] + K[a * 3 + 1] * K[3 + b] + K[a * 3 + 2] * K[6 + b];
+        const int p = parents[j];
+        for (int a = 0; a < 3; a++) {
+            for (int b = 0; b < 3; b++) tm[j][a * 4 + b] = (a == b ? 1.f : 0.f) + s * K[a * 3 + b] + c * K2[a * 3 + b];
+            tm[j][a * 4 + 3] = J[j * 3 + a] - (j > 0 ? J[p * 3 + a] : 0.f);
+        }
+        tm[j][12] = tm[j][13] = tm[j][14] = 0.f; tm[j][15] = 1.f;
+    }
+    __syncwarp();
+    if (j == 0) {  // kinematic chain (24 tiny products; sequential dependency along the tree)
+        for (int e = 0; e < 16; e++) chain[0][e] = tm[0][e];
+        for (int i = 1; i < 24; i++) mat4_mul(chain[parents[i]], tm[i], chain[i]);
+    }
+    __syncwarp();
+    if (j < 24) {
+        // A = chain - pad(chain . [J;0])  (lbs.py:396-399), then + transl
+        for (int e = 0; e < 16; e++) A[j][e] = chain[j][e];
+        for (int a = 0; a < 3; a++) {
+            const float tj = chain[j][a * 4] * J[j * 3] + chain[j][a * 4 + 1] * J[j * 3 + 1] + chain[j][a * 4 + 2] * J[j * 3 + 2];
+            A[j][a * 4 + 3] = chain[j][a * 4 + 3] - tj + (transl ? transl[a] : 0.f);
+        }
+        if (A_out) for (int e = 0; e < 16; e++) A_out[j * 16 + e] = A[j][e];
+    }
+    __syncwarp();
+    if (j == 0) {  // w2s = A_0^-1 = [R^T | -R^T t]
+        for (int a = 0; a < 3; a++) {
+            for (int b = 0; b < 3; b++) w2s[a * 4 + b] = A[0][b * 4 + a];
+            w2s[a * 4 + 3] = -(A[0][a] * A[0][3] + A[0][4 + a] * A[0][7] + A[0][8 + a] * A[0][11]);
+        }
+        w2s[12] = w2s[13] = w2s[14] = 0.f; w2s[15] = 1.f;
+        for (int e = 0; e < 16; e++) w2s_out[e] = w2s[e];
+    }
+    __syncwarp();
+    if (j < 24) {
+        float t1[16], t2[16];
+        mat4_mul(w2s, A[j], t1);
+        mat4_mul(t1, tfs_inv_t + j * 16, t2);
+        for (int e = 0; e < 16; e++) tfs[j * 16 + e] = t2[e];
+    }
+}
+
+}  // namespace
+
+extern "C" int ia_smpl_tfs(const float* global_orient, const float* body_pose, const float* transl, const float* joints,
+                           const int* parents, const float* tfs_inv_t, float* tfs, float* w2s, float* A_out,
+                           ia_stream_t stream) {
+    IA_REQUIRE(global_orient && body_pose && joints && parents && tfs_inv_t && tfs && w2s);
+    smpl_tfs_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(global_orient, body_pose, transl, joints, parents, tfs_inv_t, tfs, w2s, A_out);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}

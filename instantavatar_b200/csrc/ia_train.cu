@@ -836,3 +836,71 @@ int ia_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// NeRFLoss forward + analytic backward in one pass (instant_avatar/utils/loss.py:53-79)
+// ================================================================================================
+namespace {
+
+__device__ __forceinline__ void reg_term(float x, float& val, float& dval) {
+    // reg(x) = -log(exp(-x) + exp(x - 1));  d/dx = (exp(-x) - exp(x - 1)) / (exp(-x) + exp(x - 1))
+    const float a = expf(-x), b = expf(x - 1.f);
+    val = -logf(a + b);
+    dval = (a - b) / (a + b);
+}
+
+// out[0..4] += {sum (rgb-t)^2, sum (alpha-a)^2, sum reg(alpha), sum reg(w)} ; gradients of
+// loss = w_rgb mse_rgb + w_alpha mse_alpha + w_reg (mean reg(alpha) + mean reg(w)) (+ constants), times *scale
+__global__ void __launch_bounds__(256) nerf_loss_kernel(int n_rays, int S, const float* __restrict__ rgb, const float* __restrict__ alpha,
+                                                        const float* __restrict__ weights, const float* __restrict__ t_rgb,
+                                                        const float* __restrict__ t_alpha, float w_rgb, float w_alpha, float w_reg,
+                                                        const float* __restrict__ scale_dev, float* __restrict__ g_rgb,
+                                                        float* __restrict__ g_alpha, float* __restrict__ g_weights, float* __restrict__ sums) {
+    const float scale = scale_dev ? *scale_dev : 1.f;
+    const long total = (long)n_rays * S;
+    float s_rgb = 0.f, s_a = 0.f, s_ra = 0.f, s_rw = 0.f;
+    const float gw = scale * w_reg / (float)total;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        float v, dv;
+        reg_term(weights[i], v, dv);
+        s_rw += v;
+        g_weights[i] = dv * gw;
+    }
+    for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += (long)gridDim.x * blockDim.x) {
+        for (int c = 0; c < 3; c++) {
+            const float d = rgb[r * 3 + c] - t_rgb[r * 3 + c];
+            s_rgb += d * d;
+            g_rgb[r * 3 + c] = scale * w_rgb * 2.f * d / (float)(n_rays * 3);
+        }
+        const float da = alpha[r] - t_alpha[r];
+        s_a += da * da;
+        float v, dv;
+        reg_term(alpha[r], v, dv);
+        s_ra += v;
+        g_alpha[r] = scale * (w_alpha * 2.f * da / (float)n_rays + w_reg * dv / (float)n_rays);
+    }
+    float vals[4] = {s_rgb, s_a, s_ra, s_rw};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float v = vals[k];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sums[k], v);
+    }
+}
+
+}  // namespace
+
+extern "C" int ia_nerf_loss(int n_rays, int n_samples, const float* rgb, const float* alpha, const float* weights,
+                            const float* target_rgb, const float* target_alpha, float w_rgb, float w_alpha, float w_reg,
+                            const float* scale_dev, float* g_rgb, float* g_alpha, float* g_weights, float* sums,
+                            ia_stream_t stream) {
+    IA_REQUIRE(n_rays > 0 && n_samples > 0);
+    IA_REQUIRE(rgb && alpha && weights && target_rgb && target_alpha && g_rgb && g_alpha && g_weights && sums);
+    cudaStream_t st = (cudaStream_t)stream;
+    IA_CHECK_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(float), st));
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    nerf_loss_kernel<<<sms * 4, 256, 0, st>>>(n_rays, n_samples, rgb, alpha, weights, target_rgb, target_alpha, w_rgb, w_alpha, w_reg,
+                                              scale_dev, g_rgb, g_alpha, g_weights, sums);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}

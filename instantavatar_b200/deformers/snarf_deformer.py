@@ -142,6 +142,8 @@ class SNARFDeformer:
         self.initialized = False
         self.opt = opt
         self.dtype = torch.float32
+        self.fast_prepare = True  # per-frame bone transforms through ia_smpl_tfs (False: full SMPL forward in torch)
+        self._vertices = None
 
     def initialize(self, betas, device, lbs_voxel=None):
         """snarf_deformer.py:41-69"""
@@ -155,6 +157,12 @@ class SNARFDeformer:
         self.tfs_inv_t = torch.inverse(out.A.float().detach())
         self.vs_template = out.vertices
         self.joints_cano = out.joints
+        # rest-pose joint locations (function of betas only) for the one-launch per-frame transform kernel
+        bm = self.body_model
+        v_shaped = bm.v_template + torch.einsum("bl,mkl->bmk", betas[:1], bm.shapedirs)
+        self.joints_rest = torch.einsum("jv,bvk->bjk", bm.J_regressor, v_shaped)[0].contiguous()
+        self.parents_i32 = bm.parents.to(torch.int32).contiguous()
+        self._betas_init = betas[:1].detach().clone()
         self.deformer.device = device
         self.deformer.switch_to_explicit(resolution=_opt_get(self.opt, "resolution", 128),
                                          smpl_verts=out.vertices.float().detach(),
@@ -170,6 +178,15 @@ class SNARFDeformer:
         if not self.initialized:
             self.initialize(smpl_params["betas"], device)
             self.initialized = True
+        if self.fast_prepare and smpl_params["body_pose"].shape[0] == 1 and not smpl_params["body_pose"].requires_grad:
+            # one launch: Rodrigues + kinematic chain + w2s + tfs (vertices are not needed by the renderer)
+            self.tfs, self.w2s, _ = ops.smpl_tfs(smpl_params["global_orient"], smpl_params["body_pose"], smpl_params["transl"],
+                                                 self.joints_rest, self.parents_i32, self.tfs_inv_t)
+            self.deformer.precompute(self.tfs)
+            self.smpl_params = smpl_params
+            self.smpl_outputs = None
+            self._vertices = None
+            return
         out = self.body_model(betas=smpl_params["betas"], body_pose=smpl_params["body_pose"],
                               global_orient=smpl_params["global_orient"], transl=smpl_params["transl"])
         s2w = out.A[:, 0].float()
@@ -183,10 +200,19 @@ class SNARFDeformer:
         tfs = (w2s[:, None] @ out.A.float() @ self.tfs_inv_t).type(self.dtype)
         self.deformer.precompute(tfs)
         self.w2s = w2s
-        self.vertices = (out.vertices @ w2s[:, :3, :3].permute(0, 2, 1)) + w2s[:, None, :3, 3]
+        self._vertices = (out.vertices @ w2s[:, :3, :3].permute(0, 2, 1)) + w2s[:, None, :3, 3]
         self.tfs = tfs
         self.smpl_outputs = out
         self.smpl_params = smpl_params
+
+    @property
+    def vertices(self):
+        """posed vertices in the root frame (snarf_deformer.py:90); computed on demand on the fast path"""
+        if self._vertices is None:
+            p = self.smpl_params
+            out = self.body_model(betas=p["betas"], body_pose=p["body_pose"], global_orient=p["global_orient"], transl=p["transl"])
+            self._vertices = (out.vertices @ self.w2s[:, :3, :3].permute(0, 2, 1)) + self.w2s[:, None, :3, 3]
+        return self._vertices
 
     def transform_rays_w2s(self, rays):
         """snarf_deformer.py:95-103"""

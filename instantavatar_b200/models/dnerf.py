@@ -8,6 +8,7 @@ from dataclasses import dataclass
 
 import torch
 
+from .. import ops
 from ..deformers.snarf_deformer import SNARFDeformer
 from ..renderers.raymarcher_acc import BoundModel, Raymarcher
 from .networks.ngp import NeRFNGPNet
@@ -39,6 +40,7 @@ class DNeRFModel(torch.nn.Module):
         self.optimizer = FusedAdam(self.net_coarse, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, max_epochs=30)
         self.scaler = GradScaler(device)
         self.world_size = 1
+        self.fused_loss = True  # NeRFLoss forward/backward in one kernel (False: torch autograd through utils_loss.NeRFLoss)
 
     def forward(self, batch, eval_mode=None, jitter=None, noise_tensor=None):
         """DNeRF.py:61-70"""
@@ -86,15 +88,41 @@ class DNeRFModel(torch.nn.Module):
         self.renderer.idx = int(batch.get("idx", 0)) if not torch.is_tensor(batch.get("idx", 0)) else 0
         self.deformer.prepare_deformer(batch)
         self.net_coarse.initialize(self.deformer.bbox)
-        self.net_coarse.grad_buffers()  # zeroed at creation and by every fused optimiser step (no separate zero_grad pass)
+        g_enc, g_col = self.net_coarse.grad_buffers()  # zeroed at creation and by every fused optimiser step
         reg = self.update_density_grid(grid_jitter)
-        predicts = self.forward(batch, eval_mode=False, jitter=jitter, noise_tensor=noise_tensor)
-        losses = self.loss_fn(predicts, batch)
-        loss = losses["loss"]
-        if reg is not None:
-            losses["reg"] = reg
-            loss = loss + reg
-        self.scaler.scale(loss).backward()
+        if self.fused_loss:
+            # forward kernel -> NeRFLoss forward+backward kernel -> compositing backward -> network backward: no autograd
+            # graph for the per-ray path (the grid regulariser below still goes through autograd, every 20 steps)
+            rays = Rays(o=batch["rays_o"], d=batch["rays_d"], near=batch["near"], far=batch["far"])
+            self.deformer.transform_rays_w2s(rays)
+            grid = self.renderer.density_grid_train
+            scene = self.deformer.scene(self.net_coarse, grid.occupancy_bits(), grid.aabb6())
+            o, d = rays.o.reshape(-1, 3).float().contiguous(), rays.d.reshape(-1, 3).float().contiguous()
+            near, far = rays.near.reshape(-1).float().contiguous(), rays.far.reshape(-1).float().contiguous()
+            n = near.numel()
+            if jitter is None:
+                jitter = torch.rand((n, 256), device=near.device)
+            if noise_tensor is None and self.global_step < 1000:
+                noise_tensor = torch.randn((n, 256), device=near.device)
+            bg = batch["bg_color"].reshape(-1, 3).float().contiguous() if batch.get("bg_color", None) is not None else None
+            out, saved = ops.train_fwd(scene, o, d, near, far, bg, jitter, noise_tensor)
+            losses, g_rgb, g_alpha, g_w = ops.nerf_loss(out, batch["rgb"], batch["alpha"], self.loss_fn.w_rgb, self.loss_fn.w_alpha,
+                                                        self.loss_fn.w_reg, self.scaler.scale_t)
+            l_xc, l_ds, l_dc, l_count = ops.composite_bwd(near, far, bg, noise_tensor, saved, g_rgb, None, g_alpha, g_w)
+            from ..autograd import GRAD_SCALE
+            ops.ngp_backward(scene, l_xc, l_ds, l_dc, l_count, g_enc, g_col, GRAD_SCALE)
+            if reg is not None:
+                losses["reg"] = reg
+                losses["loss"] = losses["loss"] + reg.detach()
+                self.scaler.scale(reg).backward()
+        else:
+            predicts = self.forward(batch, eval_mode=False, jitter=jitter, noise_tensor=noise_tensor)
+            losses = self.loss_fn(predicts, batch)
+            loss = losses["loss"]
+            if reg is not None:
+                losses["reg"] = reg
+                loss = loss + reg
+            self.scaler.scale(loss).backward()
         if self.world_size > 1:
             import torch.distributed as dist
             for g in self.net_coarse.grad_buffers():

@@ -292,3 +292,33 @@ def composite_test(rgb_vals, sigma_vals, delta_vals, depth_vals, alive_indices, 
     _lib.count(1); check(lib().ia_composite_test(ptr(rgb_vals.contiguous(), f32), ptr(sigma_vals.contiguous(), f32), ptr(delta_vals, f32),
                                                  ptr(depth_vals, f32), ptr(alive_indices, torch.int64), C.c_int(a), C.c_int(n_steps),
                                                  ptr(color, f32), ptr(depth, f32), ptr(no_hit, f32), C.c_float(thresh), stream()))
+
+
+def smpl_tfs(global_orient, body_pose, transl, joints, parents_i32, tfs_inv_t, want_A=False):
+    """bone transforms of one frame in one launch (snarf_deformer.py:79-86) -> (tfs [1,24,4,4], w2s [1,4,4], A | None)"""
+    dev = body_pose.device
+    tfs = torch.empty((1, 24, 4, 4), device=dev, dtype=f32); w2s = torch.empty((1, 4, 4), device=dev, dtype=f32)
+    A = torch.empty((1, 24, 4, 4), device=dev, dtype=f32) if want_A else None
+    _lib.count(1); check(lib().ia_smpl_tfs(ptr(global_orient.reshape(-1).contiguous(), f32), ptr(body_pose.reshape(-1).contiguous(), f32),
+                                           ptr(transl.reshape(-1).contiguous(), f32) if transl is not None else None,
+                                           ptr(joints.reshape(-1).contiguous(), f32), ptr(parents_i32, torch.int32),
+                                           ptr(tfs_inv_t.reshape(-1).contiguous(), f32), ptr(tfs), ptr(w2s), ptr(A), stream()))
+    return tfs, w2s, A
+
+
+def nerf_loss(out: dict, target_rgb, target_alpha, w_rgb=1.0, w_alpha=0.1, w_reg=0.1, scale_dev=None):
+    """NeRFLoss (utils/loss.py:53-79) forward + gradients w.r.t. (rgb, alpha, weights) in one launch.
+    Returns (losses dict of device scalars, g_rgb, g_alpha, g_weights)."""
+    n, S = out["weights"].shape
+    dev = out["rgb"].device
+    g_rgb = torch.empty_like(out["rgb"]); g_alpha = torch.empty_like(out["alpha"]); g_w = torch.empty_like(out["weights"])
+    sums = torch.empty(4, device=dev, dtype=f32)
+    _lib.count(1); check(lib().ia_nerf_loss(C.c_int(n), C.c_int(S), ptr(out["rgb"], f32), ptr(out["alpha"], f32), ptr(out["weights"], f32),
+                                            ptr(target_rgb.reshape(-1, 3).contiguous(), f32), ptr(target_alpha.reshape(-1).contiguous(), f32),
+                                            C.c_float(w_rgb), C.c_float(w_alpha), C.c_float(w_reg), ptr(scale_dev), ptr(g_rgb), ptr(g_alpha),
+                                            ptr(g_w), ptr(sums), stream()))
+    OFFSET = 0.313262
+    mse, msa, ra, rw = sums[0] / (3.0 * n), sums[1] / n, sums[2] / n + OFFSET, sums[3] / (n * S) + OFFSET
+    losses = {"mse_loss": mse, "loss_alpha_coarse": msa, "reg_alpha": ra, "reg_density": rw,
+              "loss": w_rgb * mse + w_alpha * msa + w_reg * ra + w_reg * rw}
+    return losses, g_rgb, g_alpha, g_w
