@@ -165,6 +165,40 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def bench_frame_sharded(model, batch, device, rank, world, flush, steps=20, warmup=5):
+    """BASELINE.json config 3 (one frame, rays sharded over the GPUs): latency of ONE 512x512 frame rendered cooperatively
+    -- occupancy queries sharded + 1 MB max-all-reduce, ray tiles round-robin, RGBA gathered on rank 0 (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    model.eval()
+    torch.manual_seed(99)  # identical jitter on every rank
+    jit = torch.rand((5, 64, 64, 64, 3), device=device)
+    # every rank renders the SAME frame here: broadcast rank 0's pose
+    b = {k: v.clone() for k, v in batch.items()}
+    for k in ("betas", "body_pose", "global_orient", "transl"):
+        dist.broadcast(b[k], 0)
+    graphed = None
+    try:
+        from instantavatar_b200.graphs import GraphedShardedFrame
+        graphed = GraphedShardedFrame(model, b, (H, W), rank, world, jit)
+    except Exception as exc:  # NCCL capture unavailable: fall back to eager launches
+        if rank == 0:
+            print(f"[bench] sharded-frame graph capture failed ({type(exc).__name__}), running eagerly", file=sys.stderr)
+    run = (lambda: graphed()) if graphed is not None else (lambda: model.render_image_sharded(b, (H, W), rank, world, jit))
+    for _ in range(warmup):
+        run()
+    dist.barrier(); torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, e in ev:
+        flush.zero_()
+        a.record(); run(); e.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = torch.tensor([sum(a.elapsed_time(e) for a, e in ev) / steps], device=device, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return {"ms_per_frame": float(ms.item()), "rays_per_s": N_RAYS / (float(ms.item()) * 1e-3), "scaling": "strong",
+            "tile_rays": 2048, "collectives": "all_reduce(max) of the 1 MB density grid + gather of RGBA rows", "cuda_graph": graphed is not None}
+
+
 def bench_ref_structure(model, batch, device, iters=5):
     """The reference's own CUDA kernels (oracle/_ref, built from /root/reference) + the reference's host loop, with this
     repo's hash-grid/MLP standing in for tiny-cuda-nn, on the same frame: per-frame time of precompute +
@@ -369,6 +403,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     occ_ms = float(np.median([a.elapsed_time(b) for a, b in qev]))
 
+    sharded = bench_frame_sharded(model, batch, device, rank, world, flush) if world > 1 else None
     ref_struct = bench_ref_structure(model, batch, device) if rank == 0 else None
     train = bench_train(model, batch, device, rank, world, flush, use_graph=use_graph)
 
@@ -410,6 +445,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "train": train,
         "ref_structure": ref_struct,
+        "frame_sharded": sharded,
         "roofline": {"kernel": "render_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": algo_bytes,

@@ -128,9 +128,10 @@ int ia_deform_query(const IaScene* scene /*[host]*/, const float* pts, int n, in
 /* DensityGrid.initialize's density pass (models/structures/density_grid.py:94-103) in one launch: for each of
  * `passes` jitter tensors [G][G][G][3] the G^3 cell points (idx/G + jitter/G) * (max - min) + min are queried in eval
  * mode and max(sigma, 0) is reduced into density_max [G][G][G] (zeroed by the library).  aabb [6] device.
- * workspace: nullable; >= 256 bytes enables dynamic batch scheduling. */
+ * workspace: nullable; >= 256 bytes enables dynamic batch scheduling.  shard / n_shards: this call evaluates every
+ * n_shards-th batch of cells starting at `shard` (multi-GPU: the caller max-all-reduces density_max; 0 / 1 = all). */
 int ia_occupancy_query(const IaScene* scene /*[host]*/, const float* jitter, const float* aabb, int G, int passes,
-                       float* density_max, void* workspace, IaStats* stats, ia_stream_t stream);
+                       float* density_max, void* workspace, int shard, int n_shards, IaStats* stats, ia_stream_t stream);
 
 /* Fine-grained entry points (serve the legacy `model(pts)` callback path and the tinycudann-named shim):
  * ia_broyden replaces fuse_kernel.fuse_broyden + filter_cuda.filter

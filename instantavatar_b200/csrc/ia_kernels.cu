@@ -350,6 +350,7 @@ struct QueryArgs {
     // per-pass jitter, and max(sigma, 0) is reduced over the passes into density_max[G^3]
     const float* grid_jitter; const float* grid_aabb; int G; float* density_max; int passes;
     int* batch_counter;  // optional: dynamic batch scheduling (zeroed by the launcher)
+    int batch_first, batch_stride;  // grid mode: this launch handles batches first, first+stride, ... (multi-GPU sharding)
 };
 
 template <int kWarps>
@@ -384,12 +385,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
     const int cells_per_batch = a.grid_aabb ? 32 / a.passes : 32;
     const int n3g = a.G * a.G * a.G;
     const int n_batches = a.grid_aabb ? (n3g + cells_per_batch - 1) / cells_per_batch : (a.n + 31) / 32;
-    for (int bidx = blockIdx.x * kWarps + warp;; bidx += gridDim.x * kWarps) {
+    for (int lidx = blockIdx.x * kWarps + warp;; lidx += gridDim.x * kWarps) {
         if (a.batch_counter) {  // dynamic: batches near the body cost several times more than empty space
             int nb = 0;
             if (lane == 0) nb = atomicAdd(a.batch_counter, 1);
-            bidx = __shfl_sync(kFull, nb, 0);
+            lidx = __shfl_sync(kFull, nb, 0);
         }
+        const int bidx = a.batch_first + lidx * a.batch_stride;
         if (bidx >= n_batches) break;
         int p = bidx * 32 + lane;
         bool act = p < a.n;
@@ -822,7 +824,7 @@ int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode
     a.pts = pts; a.n = n; a.eval_mode = eval_mode; a.rgb = rgb; a.sigma = sigma; a.xc_best = xc_best;
     a.best_init = best_init; a.stats = stats;
     a.grid_jitter = nullptr; a.grid_aabb = nullptr; a.G = 0; a.density_max = nullptr; a.passes = 1;
-    a.batch_counter = nullptr;
+    a.batch_counter = nullptr; a.batch_first = 0; a.batch_stride = 1;
     return launch_query(a, (cudaStream_t)stream);
 }
 
@@ -844,8 +846,10 @@ static int launch_query(QueryArgs& a, cudaStream_t stream) {
 }
 
 extern "C" int ia_occupancy_query(const IaScene* scene, const float* jitter, const float* aabb, int G, int passes,
-                                  float* density_max, void* workspace, IaStats* stats, ia_stream_t stream) {
+                                  float* density_max, void* workspace, int shard, int n_shards, IaStats* stats,
+                                  ia_stream_t stream) {
     IA_REQUIRE(jitter && aabb && density_max && G > 0 && passes > 0 && passes <= 32);
+    IA_REQUIRE(n_shards >= 1 && shard >= 0 && shard < n_shards);
     QueryArgs a;
     int rc = make_scene_dev(scene, a.sd, false);
     if (rc) return rc;
@@ -853,6 +857,7 @@ extern "C" int ia_occupancy_query(const IaScene* scene, const float* jitter, con
     a.best_init = nullptr; a.stats = stats;
     a.grid_jitter = jitter; a.grid_aabb = aabb; a.G = G; a.density_max = density_max; a.passes = passes;
     a.batch_counter = reinterpret_cast<int*>(workspace);
+    a.batch_first = shard; a.batch_stride = n_shards;
     if (workspace) IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream));
     IA_CHECK_CUDA(cudaMemsetAsync(density_max, 0, sizeof(float) * G * G * G, (cudaStream_t)stream));
     return launch_query(a, (cudaStream_t)stream);

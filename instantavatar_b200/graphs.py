@@ -93,3 +93,30 @@ class GraphedTrainStep:
         _lib.count(self.launches[key])
         self.model.global_step += 1
         return self.outs[key]
+
+
+class GraphedShardedFrame:
+    """DNeRFModel.render_image_sharded (one frame over several GPUs, two collectives) captured once per rank"""
+
+    def __init__(self, model, batch: dict, img_size, rank, world, jitters, tile=2048, warmup=3):
+        self.static_in = {k: v.clone() for k, v in batch.items() if torch.is_tensor(v)}
+        self.jitters = jitters.clone()
+        model.eval()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                model.render_image_sharded(dict(self.static_in), img_size, rank, world, self.jitters, tile)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = model.render_image_sharded(dict(self.static_in), img_size, rank, world, self.jitters, tile)
+
+    def __call__(self, batch: dict | None = None):
+        if batch is not None:
+            for k, v in batch.items():
+                if k in self.static_in:
+                    self.static_in[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -131,3 +131,23 @@ class DNeRFModel(torch.nn.Module):
         self.scaler.update()
         self.global_step += 1
         return losses
+
+    @torch.no_grad()
+    def render_image_sharded(self, batch, img_size, rank, world, jitters, tile=2048):
+        """One frame rendered cooperatively by `world` GPUs (BASELINE.json config 3): per-frame preparation is replicated
+        (0.1 ms), the occupancy-grid queries are sharded with one 1 MB max-all-reduce, rays are dealt round-robin in tiles
+        of `tile` rays (whole image rows) and the RGBA rows are gathered on rank 0.  `jitters` must be identical on all
+        ranks.  Returns [H*W, 4] on rank 0, None elsewhere."""
+        from .. import parallel
+        H, W = img_size
+        self.deformer.prepare_deformer(batch)
+        self.net_coarse.initialize(self.deformer.bbox)
+        self.renderer.density_grid_test.initialize(self.deformer, self.net_coarse, jitters=jitters, shard=(rank, world))
+        idx = parallel.shard_tiles_cached(H * W, rank, world, tile, batch["rays_o"].device)
+        b = dict(batch)
+        for k in ("rays_o", "rays_d", "near", "far"):
+            b[k] = batch[k][:, idx].contiguous()
+        self.image_width = W if tile % (2 * W) == 0 else 0
+        d = self.forward(b, eval_mode=True)
+        local = torch.cat([d["rgb_coarse"].reshape(-1, 3), d["alpha_coarse"].reshape(-1, 1)], dim=1)
+        return parallel.gather_image(local, idx, H * W, tile=tile)

@@ -104,8 +104,9 @@ class DensityGrid(torch.nn.Module):
         return density, valid
 
     @torch.no_grad()
-    def initialize(self, deformer, net, iters=5, jitters=None):
-        """density_grid.py:94-110 (test-time, per frame)."""
+    def initialize(self, deformer, net, iters=5, jitters=None, shard=(0, 1)):
+        """density_grid.py:94-110 (test-time, per frame).  shard = (rank, world): each rank evaluates every world-th batch
+        of cells and the densities are max-all-reduced (1 MB) -- identical grids on every rank (same jitter required)."""
         self.aabb = deformer.get_bbox_deformed()
         from ..networks.ngp import NeRFNGPNet
         if isinstance(net, NeRFNGPNet) and hasattr(deformer, "scene"):
@@ -113,7 +114,11 @@ class DensityGrid(torch.nn.Module):
             if jitters is None:
                 jitters = torch.rand((iters, *self.coords.shape), device=self.coords.device)
             net.initialize(deformer.bbox)
-            self._density = ops.occupancy_query(deformer.scene(net), jitters[:iters], self.aabb6(), getattr(self, "_density", None))
+            self._density = ops.occupancy_query(deformer.scene(net), jitters[:iters], self.aabb6(), getattr(self, "_density", None),
+                                                shard=shard)
+            if shard[1] > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self._density, op=dist.ReduceOp.MAX)
             self.build_from_density(self._density)
             return
         density = torch.zeros_like(self.coords[..., 0])

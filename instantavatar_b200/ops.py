@@ -66,7 +66,7 @@ def occupancy_build(density: torch.Tensor, bits=None, want_field=True, workspace
     return field, bits
 
 
-def occupancy_query(scene, jitters: torch.Tensor, aabb6: torch.Tensor, density=None, stats=None, workspace=None):
+def occupancy_query(scene, jitters: torch.Tensor, aabb6: torch.Tensor, density=None, stats=None, workspace=None, shard=(0, 1)):
     """5-pass density query of DensityGrid.initialize in one launch -> density [G,G,G] (max over passes, >= 0)"""
     P, G = jitters.shape[0], jitters.shape[1]
     if density is None:
@@ -75,7 +75,7 @@ def occupancy_query(scene, jitters: torch.Tensor, aabb6: torch.Tensor, density=N
         workspace = torch.empty(64, device=jitters.device, dtype=torch.int32)
     s = scene.c_struct()
     _lib.count(1); check(lib().ia_occupancy_query(C.byref(s), ptr(jitters.contiguous(), f32), ptr(aabb6, f32), C.c_int(G), C.c_int(P),
-                                                  ptr(density), ptr(workspace), ptr(stats), stream()))
+                                                  ptr(density), ptr(workspace), C.c_int(shard[0]), C.c_int(shard[1]), ptr(stats), stream()))
     return density
 
 

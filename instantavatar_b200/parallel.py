@@ -26,6 +26,17 @@ def init_from_env(backend: str | None = None, device: torch.device | None = None
     return rank, world
 
 
+_TILE_CACHE = {}
+
+
+def shard_tiles_cached(n_rays: int, rank: int, world: int, tile: int, device) -> torch.Tensor:
+    """device-resident copy of shard_tiles (built once: no per-frame host->device index upload)"""
+    key = (n_rays, rank, world, tile, str(device))
+    if key not in _TILE_CACHE:
+        _TILE_CACHE[key] = shard_tiles(n_rays, rank, world, tile).to(device)
+    return _TILE_CACHE[key]
+
+
 def shard_tiles(n_rays: int, rank: int, world: int, tile: int = TILE) -> torch.Tensor:
     """indices of the rays this rank renders: tiles of `tile` consecutive rays dealt round-robin (the body sits in
     the image centre, so contiguous blocks would be badly imbalanced)"""
@@ -49,7 +60,7 @@ def allreduce_sum_(buffers, group=None):
     return buffers
 
 
-def gather_image(local: torch.Tensor, idx: torch.Tensor, n_rays: int, group=None) -> torch.Tensor | None:
+def gather_image(local: torch.Tensor, idx: torch.Tensor, n_rays: int, group=None, tile: int = TILE) -> torch.Tensor | None:
     """assemble a ray-sharded render on rank 0: local [n_local, C] rows at global positions idx"""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
@@ -57,12 +68,13 @@ def gather_image(local: torch.Tensor, idx: torch.Tensor, n_rays: int, group=None
         out[idx.to(local.device)] = local
         return out
     rank = dist.get_rank(group)
-    sizes = [len(shard_tiles(n_rays, r, world)) for r in range(world)]
-    bufs = [local.new_empty((s, local.shape[1])) for s in sizes] if rank == 0 else None
-    dist.gather(local.contiguous(), bufs, dst=0, group=group)
     if rank != 0:
+        dist.gather(local.contiguous(), None, dst=0, group=group)
         return None
-    out = local.new_zeros((n_rays, local.shape[1]))
-    for r, b in enumerate(bufs):
-        out[shard_tiles(n_rays, r, world).to(local.device)] = b
+    idxs = [shard_tiles_cached(n_rays, r, world, tile, local.device) for r in range(world)]
+    bufs = [local.new_empty((len(i), local.shape[1])) for i in idxs]
+    dist.gather(local.contiguous(), bufs, dst=0, group=group)
+    out = local.new_empty((n_rays, local.shape[1]))
+    for i, b in zip(idxs, bufs):
+        out[i] = b
     return out

@@ -1,0 +1,105 @@
+"""GPU x2 (NCCL): one frame rendered cooperatively by two ranks equals the single-GPU frame bit for bit, and the
+ray-sharded training gradient (one all-reduce) equals the single-GPU gradient.  Skipped on single-GPU boxes."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", device_id=dev)
+    from instantavatar_b200 import parallel, synthetic
+    from instantavatar_b200.models.dnerf import DNeRFModel
+    H = W = 256
+    model = DNeRFModel(smpl_data=synthetic.smpl_dict_cached(0), device=dev).eval()
+    pose = synthetic.load_pose(0)
+    o, d = synthetic.demo_camera_rays(512, 512)
+    idx = (np.arange(0, 512, 2)[:, None] * 512 + np.arange(0, 512, 2)[None]).ravel()
+    batch = {"rays_o": torch.from_numpy(o[idx][None]).to(dev), "rays_d": torch.from_numpy(d[idx][None]).to(dev),
+             "near": torch.zeros((1, len(idx)), device=dev), "far": torch.ones((1, len(idx)), device=dev)}
+    batch.update({k: torch.from_numpy(v).to(dev) for k, v in pose.items()})
+    model.deformer.prepare_deformer(batch)
+    model.net_coarse.initialize(model.deformer.bbox)
+    bbox = model.deformer.bbox.cpu().numpy().astype(np.float64)
+    enc, col = synthetic.analytic_avatar_params(model.deformer.joints_cano[0].cpu().numpy(), (bbox[0] + bbox[1]) / 2, bbox[1] - bbox[0])
+    model.net_coarse.load_flat_params(torch.from_numpy(enc).to(dev), torch.from_numpy(col).to(dev))
+    torch.manual_seed(7)
+    jit = torch.rand((5, 64, 64, 64, 3), device=dev)
+    # ---- cooperative frame vs single-GPU frame ----
+    img = model.render_image_sharded(dict(batch), (H, W), rank, world, jit, tile=1024)
+    rgb, depth, alpha, counter = model.render_image_fast(dict(batch), (H, W), jit)
+    if rank == 0:
+        full = torch.cat([rgb.reshape(-1, 3), alpha.reshape(-1, 1)], dim=1)
+        ret["frame_equal"] = bool(torch.equal(img, full))
+        ret["hit"] = int((alpha > 0.5).sum().item())
+    # ---- sharded training gradient vs single-GPU gradient ----
+    n = 1024
+    pick = torch.arange(100 * W + 96, 100 * W + 96 + n, device=dev)
+    tb = dict(batch)
+    for k in ("rays_o", "rays_d", "near", "far"):
+        tb[k] = batch[k][:, pick].contiguous()
+    torch.manual_seed(11)
+    tb["rgb"] = torch.rand((1, n, 3), device=dev); tb["alpha"] = torch.ones((1, n), device=dev); tb["bg_color"] = torch.rand((1, n, 3), device=dev)
+    jitter = torch.rand((n, 256), device=dev); noise = torch.zeros((n, 256), device=dev)
+    model.train(); model.global_step = 2001   # no grid refresh on this step
+
+    def grads(b, jit_, noi_, world_size):
+        from instantavatar_b200 import ops
+        from instantavatar_b200.autograd import GRAD_SCALE
+        from instantavatar_b200.models.dnerf import Rays
+        g_enc, g_col = model.net_coarse.grad_buffers(); g_enc.zero_(); g_col.zero_()
+        rays = Rays(o=b["rays_o"], d=b["rays_d"], near=b["near"], far=b["far"])
+        model.deformer.transform_rays_w2s(rays)
+        grid = model.renderer.density_grid_train
+        if grid.aabb is None:
+            grid.aabb = model.renderer.aabb
+        grid.set_field(torch.ones((64, 64, 64), dtype=torch.bool, device=dev))
+        scene = model.deformer.scene(model.net_coarse, grid.occupancy_bits(), grid.aabb6())
+        o_, d_ = rays.o.reshape(-1, 3).contiguous(), rays.d.reshape(-1, 3).contiguous()
+        ne, fa = rays.near.reshape(-1).contiguous(), rays.far.reshape(-1).contiguous()
+        bg = b["bg_color"].reshape(-1, 3).contiguous()
+        out, saved = ops.train_fwd(scene, o_, d_, ne, fa, bg, jit_, noi_)
+        losses, g_rgb, g_alpha, g_w = ops.nerf_loss(out, b["rgb"], b["alpha"])
+        l = ops.composite_bwd(ne, fa, bg, noi_, saved, g_rgb, None, g_alpha, g_w)
+        ops.ngp_backward(scene, l[0], l[1], l[2], l[3], g_enc, g_col, GRAD_SCALE)
+        if world_size > 1:
+            parallel.allreduce_sum_([g_enc, g_col])
+        return g_enc.clone() / world_size, g_col.clone() / world_size
+
+    full_enc, full_col = grads(tb, jitter, noise, 1)
+    sl = parallel.shard_train_rays(n, rank, world)
+    sb = dict(tb)
+    for k in ("rays_o", "rays_d", "near", "far", "rgb", "alpha", "bg_color"):
+        sb[k] = tb[k][:, sl].contiguous()
+    sh_enc, sh_col = grads(sb, jitter[sl].contiguous(), noise[sl].contiguous(), world)
+    if rank == 0:
+        rel = lambda a, b: float((a - b).norm() / b.norm())
+        ret["rel_enc"] = rel(sh_enc, full_enc); ret["rel_col"] = rel(sh_col, full_col)
+        ret["gnorm"] = float(full_enc.norm())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_frame_and_gradient():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret["hit"] > 1000
+    assert ret["frame_equal"], "cooperative frame differs from the single-GPU frame"
+    assert ret["gnorm"] > 0 and ret["rel_enc"] < 1e-3 and ret["rel_col"] < 1e-3, dict(ret)
