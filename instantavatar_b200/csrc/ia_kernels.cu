@@ -146,25 +146,44 @@ __global__ void __launch_bounds__(256) render_plan_kernel(const __grid_constant_
     }
 }
 
-// one CTA: counting sort of the non-empty tiles by decreasing cost (256 buckets)
+// one CTA: counting sort of the non-empty tiles by decreasing cost (256 buckets); costs are staged in registers
+// (coalesced, independent loads) so the two passes do not pay a global-load latency per tile
 __global__ void __launch_bounds__(1024) order_tiles_kernel(const int* __restrict__ cost, int n_tiles, int* __restrict__ order,
                                                            int* __restrict__ n_active) {
     __shared__ int hist[256];
     __shared__ int offs[256];
+    constexpr int kPer = 16;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     auto bucket = [](int c) { return 255 - min(255, c >> 2); };  // bucket 0 = most expensive
-    for (int i = threadIdx.x; i < n_tiles; i += blockDim.x)
-        if (cost[i] > 0) atomicAdd(&hist[bucket(cost[i])], 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int b = 0; b < 256; b++) { offs[b] = acc; acc += hist[b]; }
-        *n_active = acc;
+    for (int base = 0; base < n_tiles; base += 1024 * kPer) {
+        int c[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) { const int i = base + j * 1024 + threadIdx.x; c[j] = i < n_tiles ? cost[i] : 0; }
+#pragma unroll
+        for (int j = 0; j < kPer; j++) if (c[j] > 0) atomicAdd(&hist[bucket(c[j])], 1);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_tiles; i += blockDim.x)
-        if (cost[i] > 0) order[atomicAdd(&offs[bucket(cost[i])], 1)] = i;
+    if (threadIdx.x < 32) {  // exclusive scan of the 256 buckets by one warp (8 per lane)
+        int loc[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { loc[j] = hist[threadIdx.x * 8 + j]; sum += loc[j]; }
+        int incl = sum;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += y; }
+        int acc = incl - sum;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { offs[threadIdx.x * 8 + j] = acc; acc += loc[j]; }
+        if (threadIdx.x == 31) *n_active = incl;
+    }
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024 * kPer) {
+        int c[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) { const int i = base + j * 1024 + threadIdx.x; c[j] = i < n_tiles ? cost[i] : 0; }
+#pragma unroll
+        for (int j = 0; j < kPer; j++)
+            if (c[j] > 0) order[atomicAdd(&offs[bucket(c[j])], 1)] = base + j * 1024 + threadIdx.x;
+    }
 }
 
 // kRays rays per warp, each marched kDepth = 32/kRays steps ahead (lane = depth * kRays + ray): the batch of 32

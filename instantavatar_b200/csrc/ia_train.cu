@@ -218,6 +218,8 @@ struct CompBwdArgs {
     float* l_xc; float* l_dsigma; float* l_drgb; int* l_count;  // compact output list
 };
 
+// One ray per thread, but the per-slot loads are staged 8 slots at a time into registers ahead of the serial
+// transmittance recurrence (the first version was bound by one dependent global-load latency per slot).
 __global__ void __launch_bounds__(128) composite_bwd_kernel(CompBwdArgs a) {
     const int ray = blockIdx.x * blockDim.x + threadIdx.x;
     if (ray >= a.n_rays) return;
@@ -225,50 +227,77 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(CompBwdArgs a) {
     if (cnt == 0) return;
     const float dt = (a.far[ray] - a.near[ray]) / (float)IA_MAX_SAMPLES;
     const long base = (long)ray * IA_MAX_SAMPLES;
+    const float* __restrict__ p_sig = a.s_sigma + base;
+    const float* __restrict__ p_noise = a.noise ? a.noise + base : nullptr;
+    const int8_t* __restrict__ p_best = a.s_best + base;
+    const float* __restrict__ p_rgb = a.s_rgb + base * 3;
+    const float* __restrict__ p_xc = a.s_xc + base * 3;
+    const float* __restrict__ p_z = a.s_z + base;
+    const float* __restrict__ p_gw = a.g_weights ? a.g_weights + base : nullptr;
     float gc[3] = {0, 0, 0}, gd = 0, ga = 0;
     if (a.g_rgb) { gc[0] = a.g_rgb[ray * 3]; gc[1] = a.g_rgb[ray * 3 + 1]; gc[2] = a.g_rgb[ray * 3 + 2]; }
     if (a.g_depth) gd = a.g_depth[ray];
     if (a.g_alpha) ga = a.g_alpha[ray];
     float b[3] = {1.f, 1.f, 1.f};
     if (a.bg) { b[0] = a.bg[ray * 3]; b[1] = a.bg[ray * 3 + 1]; b[2] = a.bg[ray * 3 + 2]; }
-    // forward sweep for T_end, then backward sweep; T_s recomputed by division-free re-multiplication:
-    // keep the running products in a small local array (cnt <= 256) -> recompute instead: two passes
+    constexpr int kB = 8;
+    // ---- forward sweep: T after the last sample, number of samples that reached the network ----
     float T = 1.f;
     int nvalid = 0;
-    for (int s = 0; s < cnt; s++) {
-        float sig = a.s_sigma[base + s];
-        if (a.noise) sig = sig + a.noise[base + s];
-        const float al = 1.0f - expf(-fmaxf(sig, 0.f) * dt);
-        T = T * ((1.0f - al) + 1e-10f);
-        nvalid += a.s_best[base + s] >= 0 ? 1 : 0;
+    for (int s0 = 0; s0 < cnt; s0 += kB) {
+        float sg[kB]; int bs[kB];
+#pragma unroll
+        for (int j = 0; j < kB; j++) {
+            const int s = min(s0 + j, cnt - 1);
+            sg[j] = p_sig[s] + (p_noise ? p_noise[s] : 0.f);
+            bs[j] = p_best[s];
+        }
+#pragma unroll
+        for (int j = 0; j < kB; j++) {
+            if (s0 + j < cnt) {
+                const float al = 1.0f - expf(-fmaxf(sg[j], 0.f) * dt);
+                T = T * ((1.0f - al) + 1e-10f);
+                nvalid += bs[j] >= 0 ? 1 : 0;
+            }
+        }
     }
     if (nvalid == 0) return;
     int pos = atomicAdd(a.l_count, nvalid) + nvalid;  // fill this ray's block back to front
-    // S = dL/dT entering the next sample; start with the background term
-    float S = gc[0] * b[0] + gc[1] * b[1] + gc[2] * b[2];
-    float Tn = T;  // T after sample s
-    for (int s = cnt - 1; s >= 0; s--) {
-        float sig = a.s_sigma[base + s];
-        if (a.noise) sig = sig + a.noise[base + s];
-        const float pre = fmaxf(sig, 0.f);
-        const float e = expf(-pre * dt);
-        const float al = 1.0f - e;
-        const float f = (1.0f - al) + 1e-10f;
-        const float Tb = Tn / f;  // T before sample s
-        const float c0 = a.s_rgb[(base + s) * 3], c1 = a.s_rgb[(base + s) * 3 + 1], c2 = a.s_rgb[(base + s) * 3 + 2];
-        float Gs = gc[0] * c0 + gc[1] * c1 + gc[2] * c2 + gd * a.s_z[base + s] + ga;
-        if (a.g_weights) Gs += a.g_weights[base + s];
-        const float dLdf = S * Tb;
-        const float dLdal = Gs * Tb - dLdf;
-        S = S * f + Gs * al;
-        Tn = Tb;
-        if (a.s_best[base + s] >= 0) {
-            const float dsig = sig > 0.f ? dLdal * e * dt : 0.f;  // d alpha / d sigma = exp(-tau) * dt through the relu
-            const float w = al * Tb;
-            pos--;
-            a.l_xc[pos * 3] = a.s_xc[(base + s) * 3]; a.l_xc[pos * 3 + 1] = a.s_xc[(base + s) * 3 + 1]; a.l_xc[pos * 3 + 2] = a.s_xc[(base + s) * 3 + 2];
-            a.l_dsigma[pos] = dsig;
-            a.l_drgb[pos * 3] = w * gc[0]; a.l_drgb[pos * 3 + 1] = w * gc[1]; a.l_drgb[pos * 3 + 2] = w * gc[2];
+    float S = gc[0] * b[0] + gc[1] * b[1] + gc[2] * b[2];  // dL/dT entering the next sample; starts at the background term
+    float Tn = T;                                          // T after sample s
+    for (int s1 = cnt - 1; s1 >= 0; s1 -= kB) {
+        float sg[kB], c0[kB], c1[kB], c2[kB], zz[kB], gw[kB]; int bs[kB];
+#pragma unroll
+        for (int j = 0; j < kB; j++) {
+            const int s = max(s1 - j, 0);
+            sg[j] = p_sig[s] + (p_noise ? p_noise[s] : 0.f);
+            bs[j] = p_best[s];
+            c0[j] = p_rgb[s * 3]; c1[j] = p_rgb[s * 3 + 1]; c2[j] = p_rgb[s * 3 + 2];
+            zz[j] = p_z[s];
+            gw[j] = p_gw ? p_gw[s] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kB; j++) {
+            const int s = s1 - j;
+            if (s < 0) break;
+            const float sig = sg[j];
+            const float e = expf(-fmaxf(sig, 0.f) * dt);
+            const float al = 1.0f - e;
+            const float f = (1.0f - al) + 1e-10f;
+            const float Tb = Tn / f;  // T before sample s
+            const float Gs = gc[0] * c0[j] + gc[1] * c1[j] + gc[2] * c2[j] + gd * zz[j] + ga + gw[j];
+            const float dLdf = S * Tb;
+            const float dLdal = Gs * Tb - dLdf;
+            S = S * f + Gs * al;
+            Tn = Tb;
+            if (bs[j] >= 0) {
+                const float dsig = sig > 0.f ? dLdal * e * dt : 0.f;  // d alpha / d sigma = exp(-tau) * dt through the relu
+                const float w = al * Tb;
+                pos--;
+                a.l_xc[pos * 3] = p_xc[s * 3]; a.l_xc[pos * 3 + 1] = p_xc[s * 3 + 1]; a.l_xc[pos * 3 + 2] = p_xc[s * 3 + 2];
+                a.l_dsigma[pos] = dsig;
+                a.l_drgb[pos * 3] = w * gc[0]; a.l_drgb[pos * 3 + 1] = w * gc[1]; a.l_drgb[pos * 3 + 2] = w * gc[2];
+            }
         }
     }
 }
