@@ -179,7 +179,8 @@ int ia_composite_bwd(int n_rays, const float* near, const float* far, const floa
                      const float* s_sigma, const float* s_rgb, const float* s_xc, const float* s_z, const int* s_count,
                      const int8_t* s_best, const float* g_rgb, const float* g_depth, const float* g_alpha,
                      const float* g_weights, float* l_xc, float* l_dsigma, float* l_drgb, int* l_count,
-                     ia_stream_t stream);
+                     const float* rays_o /*nullable*/, const float* rays_d /*nullable*/, float* l_xd /*nullable [n*256][3]*/,
+                     int8_t* l_best /*nullable [n*256]*/, ia_stream_t stream);
 
 /* Network backward (tiny-cuda-nn's autograd through HashGrid + FullyFusedMLPs, ngp.py:73-83): for the first
  * min(*count, capacity) list entries accumulates (+=) d loss / d encoder.params into grad_enc [3072 + 2*total] and
@@ -188,7 +189,17 @@ int ia_composite_bwd(int n_rays, const float* near, const float* far, const floa
 size_t ia_ngp_backward_scratch_bytes(int capacity);
 int ia_ngp_backward(const IaScene* scene /*[host]*/, const float* xc, const float* dsigma, const float* drgb,
                     const int* count, int capacity, float grad_scale, float* grad_enc, float* grad_col, void* scratch,
+                    float* denc_out /*nullable [capacity][32]: d loss / d hash features, input of ia_pose_grad*/,
                     ia_stream_t stream);
+
+/* Pose gradients (SNARF_NGP_refine / optimize_SMPL): d loss / d tfs [24][4][4] (+=) through Fast-SNARF's implicit
+ * differentiation (deformers/fast_snarf/deformer_torch.py:50-67, version 1): for each list sample the winning
+ * initialisation's Broyden solve is re-run from xd (posed point) to recover x_c and the J_inv the reference stores, the
+ * network's input gradient is formed from denc (ia_ngp_backward) and the hash-grid interpolation weights, and
+ * -J_inv^T g (x) [x_c,1] is accumulated per bone with the border-padded trilinear skinning weights of
+ * lbs_voxel [24][D][H][W] (ForwardDeformer.lbs_voxel_final). */
+int ia_pose_grad(const IaScene* scene /*[host]*/, const float* lbs_voxel, const float* xd, const int8_t* best,
+                 const float* denc, const int* count, int capacity, float* grad_tfs, ia_stream_t stream);
 
 /* NeRFLoss forward + analytic backward in one pass (instant_avatar/utils/loss.py:53-79):
  * loss = w_rgb mse(rgb) + w_alpha mse(alpha) + w_reg (mean reg(alpha) + mean reg(weights) + 2*0.313262),

@@ -3,7 +3,9 @@
 The reference differentiates ~20 ATen ops + two tiny-cuda-nn modules; here one custom Function wraps
 `ia_train_fwd` (forward) and `ia_composite_bwd` + `ia_ngp_backward` (backward): it returns the per-ray outputs the
 loss consumes (rgb, depth, alpha and the dense per-sample weights) and produces gradients for the two flat parameter
-tensors `encoder.params` / `color_net.params`.
+tensors `encoder.params` / `color_net.params`.  When the bone transforms `tfs` carry an autograd history (pose
+optimisation, DNeRF.py:112-127 with `optimize_SMPL.enable`), `ia_pose_grad` additionally returns d loss / d tfs -- the
+implicit-differentiation gradient of deformers/fast_snarf/deformer_torch.py:50-67.
 """
 from __future__ import annotations
 
@@ -16,9 +18,11 @@ GRAD_SCALE = 128.0  # internal loss scale of the fp16 dgrad chain (tiny-cuda-nn 
 
 class _RenderTrain(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, enc_params, col_params, scene, rays_o, rays_d, near, far, bg, jitter, noise, stats, accum=None):
+    def forward(ctx, enc_params, col_params, scene, rays_o, rays_d, near, far, bg, jitter, noise, stats, accum=None,
+                tfs=None, lbs_voxel=None):
         out, saved = ops.train_fwd(scene, rays_o, rays_d, near, far, bg, jitter, noise, stats)
         ctx.scene, ctx.saved, ctx.misc = scene, saved, (near, far, bg, noise)
+        ctx.pose = (rays_o, rays_d, lbs_voxel, tfs.shape) if tfs is not None and tfs.requires_grad else None
         ctx.shapes = (enc_params.shape, col_params.shape)
         ctx.accum = accum  # optional persistent (grad_enc, grad_col) buffers to accumulate into
         return out["rgb"], out["depth"], out["alpha"], out["weights"]
@@ -26,15 +30,26 @@ class _RenderTrain(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_alpha, g_weights):
         near, far, bg, noise = ctx.misc
-        l_xc, l_ds, l_dc, l_count = ops.composite_bwd(near, far, bg, noise, ctx.saved, g_rgb, g_depth, g_alpha, g_weights)
         dev = near.device
+        pose = ctx.pose
+        lists = ops.composite_bwd(near, far, bg, noise, ctx.saved, g_rgb, g_depth, g_alpha, g_weights,
+                                  rays=pose[:2] if pose is not None else None)
+        l_xc, l_ds, l_dc, l_count = lists[:4]
+        denc = torch.empty((l_xc.shape[0], 32), device=dev, dtype=torch.float32) if pose is not None else None
         if ctx.accum is not None:
-            ops.ngp_backward(ctx.scene, l_xc, l_ds, l_dc, l_count, ctx.accum[0], ctx.accum[1], GRAD_SCALE)
-            return (None,) * 12
-        g_enc = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32)
-        g_col = torch.zeros(ctx.shapes[1], device=dev, dtype=torch.float32)
-        ops.ngp_backward(ctx.scene, l_xc, l_ds, l_dc, l_count, g_enc, g_col, GRAD_SCALE)
-        return (g_enc, g_col) + (None,) * 10
+            g_enc, g_col = ctx.accum
+        else:
+            g_enc = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32)
+            g_col = torch.zeros(ctx.shapes[1], device=dev, dtype=torch.float32)
+        ops.ngp_backward(ctx.scene, l_xc, l_ds, l_dc, l_count, g_enc, g_col, GRAD_SCALE, denc)
+        g_tfs = None
+        if pose is not None:
+            g_tfs = torch.zeros((24, 4, 4), device=dev, dtype=torch.float32)
+            ops.pose_grad(ctx.scene, pose[2], lists[4], lists[5], denc, l_count, g_tfs)
+            g_tfs = g_tfs.reshape(pose[3])
+        if ctx.accum is not None:
+            return (None,) * 12 + (g_tfs, None)
+        return (g_enc, g_col) + (None,) * 10 + (g_tfs, None)
 
 
 def render_train_fused(renderer, deformer, net, rays, noise, bg_color, jitter=None, noise_tensor=None, stats=None):
@@ -54,7 +69,7 @@ def render_train_fused(renderer, deformer, net, rays, noise, bg_color, jitter=No
     bg = bg_color.reshape(-1, 3).float().contiguous() if bg_color is not None else None
     rgb, depth, alpha, weights = _RenderTrain.apply(net.encoder.params, net.color_net.params, scene, rays_o, rays_d, near, far, bg,
                                                     jitter.contiguous(), noise_tensor.contiguous() if noise_tensor is not None else None, stats,
-                                                    net.grad_buffers())
+                                                    net.grad_buffers(), deformer.tfs, deformer.deformer.lbs_voxel_final)
     return {
         "rgb_coarse": rgb.reshape(rays.o.shape),
         "depth_coarse": depth.reshape(rays.near.shape),
@@ -67,9 +82,10 @@ class _DeformQueryTrain(torch.autograd.Function):
     """deformer(pts, net, eval_mode=False) with gradients w.r.t. the network parameters (DensityGrid.update regulariser)."""
 
     @staticmethod
-    def forward(ctx, enc_params, col_params, scene, pts, accum=None):
+    def forward(ctx, enc_params, col_params, scene, pts, accum=None, tfs=None, lbs_voxel=None):
         rgb, sigma, xc, best = ops.deform_query(scene, pts, eval_mode=False, want_xc=True)
         ctx.scene, ctx.saved = scene, (xc, best)
+        ctx.pose = (pts.reshape(-1, 3).float().contiguous(), lbs_voxel, tfs.shape) if tfs is not None and tfs.requires_grad else None
         ctx.shapes = (enc_params.shape, col_params.shape)
         ctx.accum = accum
         return rgb, sigma
@@ -82,15 +98,25 @@ class _DeformQueryTrain(torch.autograd.Function):
         g_sigma = torch.where(valid, g_sigma.contiguous().float(), torch.zeros_like(g_sigma)) if g_sigma is not None else torch.zeros(xc.shape[0], device=dev)
         g_rgb = (g_rgb.contiguous().float() * valid[:, None]) if g_rgb is not None else torch.zeros_like(xc)
         count = torch.full((1,), xc.shape[0], device=dev, dtype=torch.int32)
+        pose = ctx.pose
+        denc = torch.empty((xc.shape[0], 32), device=dev, dtype=torch.float32) if pose is not None else None
         if ctx.accum is not None:
-            ops.ngp_backward(ctx.scene, xc, g_sigma.contiguous(), g_rgb.contiguous(), count, ctx.accum[0], ctx.accum[1], GRAD_SCALE)
-            return (None,) * 5
-        g_enc = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32)
-        g_col = torch.zeros(ctx.shapes[1], device=dev, dtype=torch.float32)
-        ops.ngp_backward(ctx.scene, xc, g_sigma.contiguous(), g_rgb.contiguous(), count, g_enc, g_col, GRAD_SCALE)
-        return g_enc, g_col, None, None, None
+            g_enc, g_col = ctx.accum
+        else:
+            g_enc = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32)
+            g_col = torch.zeros(ctx.shapes[1], device=dev, dtype=torch.float32)
+        ops.ngp_backward(ctx.scene, xc, g_sigma.contiguous(), g_rgb.contiguous(), count, g_enc, g_col, GRAD_SCALE, denc)
+        g_tfs = None
+        if pose is not None:
+            g_tfs = torch.zeros((24, 4, 4), device=dev, dtype=torch.float32)
+            ops.pose_grad(ctx.scene, pose[1], pose[0], best.to(torch.int8).contiguous(), denc, count, g_tfs)
+            g_tfs = g_tfs.reshape(pose[2])
+        if ctx.accum is not None:
+            return (None,) * 5 + (g_tfs, None)
+        return g_enc, g_col, None, None, None, g_tfs, None
 
 
 def deform_query_train(deformer, net, pts):
     scene = deformer.scene(net)
-    return _DeformQueryTrain.apply(net.encoder.params, net.color_net.params, scene, pts, net.grad_buffers())
+    return _DeformQueryTrain.apply(net.encoder.params, net.color_net.params, scene, pts, net.grad_buffers(), deformer.tfs,
+                                   deformer.deformer.lbs_voxel_final)

@@ -216,6 +216,7 @@ struct CompBwdArgs {
     const float* s_sigma; const float* s_rgb; const float* s_xc; const float* s_z; const int* s_count; const int8_t* s_best;
     const float* g_rgb; const float* g_depth; const float* g_alpha; const float* g_weights;  // upstream (nullable)
     float* l_xc; float* l_dsigma; float* l_drgb; int* l_count;  // compact output list
+    const float* rays_o; const float* rays_d; float* l_xd; int8_t* l_best;  // optional (pose gradients): posed point + init id
 };
 
 // One ray per thread, but the per-slot loads are staged 8 slots at a time into registers ahead of the serial
@@ -297,6 +298,13 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(CompBwdArgs a) {
                 a.l_xc[pos * 3] = p_xc[s * 3]; a.l_xc[pos * 3 + 1] = p_xc[s * 3 + 1]; a.l_xc[pos * 3 + 2] = p_xc[s * 3 + 2];
                 a.l_dsigma[pos] = dsig;
                 a.l_drgb[pos * 3] = w * gc[0]; a.l_drgb[pos * 3 + 1] = w * gc[1]; a.l_drgb[pos * 3 + 2] = w * gc[2];
+                if (a.l_xd) {  // posed sample position exactly as the forward generated it (z * d + o, separate mul/add)
+                    const float z = zz[j];
+                    a.l_xd[pos * 3] = z * a.rays_d[ray * 3] + a.rays_o[ray * 3];
+                    a.l_xd[pos * 3 + 1] = z * a.rays_d[ray * 3 + 1] + a.rays_o[ray * 3 + 1];
+                    a.l_xd[pos * 3 + 2] = z * a.rays_d[ray * 3 + 2] + a.rays_o[ray * 3 + 2];
+                    a.l_best[pos] = (int8_t)bs[j];
+                }
             }
         }
     }
@@ -311,6 +319,7 @@ struct NgpBwdArgs {
     float grad_scale;       // upstream grads are multiplied by this before the fp16 dgrad chain
     float* grad_enc;        // [3072 + 2*total] fp32, accumulated (+=)
     __half* scratch;        // [capacity][kRowHalfs]
+    float* denc_out;        // optional [capacity][32]: d loss / d (hash-grid features), for the pose-gradient pass
 };
 
 __device__ __forceinline__ float mask_pos(float v, uint32_t packed, bool high) {
@@ -531,6 +540,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) ngp_backward_kernel(const _
         mlp_bwd_tile16(&ws.At[0][0], sm.W, lane, 0, dsig, dr, dg, db, a.grad_scale, a.scratch, (long)tile * 32, nrows, ws.dEnc);
         mlp_bwd_tile16(&ws.At[16][0], sm.W, lane, 1, dsig, dr, dg, db, a.grad_scale, a.scratch, (long)tile * 32, nrows, ws.dEnc);
         __syncwarp();
+        if (has && a.denc_out) {
+#pragma unroll
+            for (int c = 0; c < 32; c++) a.denc_out[(long)p * 32 + c] = ws.dEnc[lane][c] * inv_scale;
+        }
         // ---- hash-grid gradient scatter (lane = sample); samples without upstream gradient contribute nothing ----
         if (has && (dsig != 0.f || dr != 0.f || dg != 0.f || db != 0.f)) {
 #pragma unroll 1
@@ -733,6 +746,148 @@ __global__ void grad_finite_kernel(const float* __restrict__ g, long n, float* _
 }  // namespace
 
 // ================================================================================================
+// pose gradients: d loss / d tfs through the implicit-function trick of Fast-SNARF
+// (deformers/fast_snarf/deformer_torch.py:50-67, version 1): x_c = x_c* - J_inv . (LBS(x_c*; tfs) - stopgrad(...)),
+// hence d loss / d tfs_j[r][c] = sum_samples (-J_inv^T g)_r . w_j(x_c) . [x_c, 1]_c   with g = d loss / d x_c.
+// J_inv is Broyden's inverse-Jacobian estimate before the last update (what fuse_broyden stores, :383-391): it is
+// re-derived here by re-running the winning initialisation's solve (bit-identical trajectory), g comes from the
+// hash-grid interpolation weights' derivative (tiny-cuda-nn's input gradient), and w_j from the 24-channel skinning
+// weight volume sampled with border padding (deformer_torch.py:190-201).
+// ================================================================================================
+namespace {
+
+struct PoseGradArgs {
+    SceneDev sd;
+    const float* lbs_voxel;   // [24][D][H][W] (reference layout)
+    const float* xd; const int8_t* best; const float* denc; const int* count; int capacity;
+    float* grad_tfs;          // [24][4][4], accumulated (+=)
+};
+
+__global__ void __launch_bounds__(256) pose_grad_kernel(const __grid_constant__ PoseGradArgs a) {
+    __shared__ FrameConst fc;
+    __shared__ float acc[24 * 12];
+    load_frame_const(fc, a.sd);
+    for (int i = threadIdx.x; i < 24 * 12; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    FieldDesc f;
+    f.data = a.sd.s.field; f.D = a.sd.s.D; f.H = a.sd.s.H; f.W = a.sd.s.W;
+    const __half2* table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
+    const int count = min(*a.count, a.capacity);
+    const long V = (long)f.D * f.H * f.W;
+    const int n_batches = (count + 31) / 32;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int bidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; bidx < n_batches; bidx += warps) {
+        const int p = bidx * 32 + lane;
+        float v[3] = {0.f, 0.f, 0.f}, xh[4] = {0.f, 0.f, 0.f, 1.f};
+        float wts[24];
+#pragma unroll
+        for (int j = 0; j < 24; j++) wts[j] = 0.f;
+        const int bi = p < count ? (int)a.best[p] : -1;
+        if (bi >= 0) {
+            float x[3], Ji[9];
+            int ng = 0;
+            const bool ok = broyden_solve(f, fc.bp, fc.Tb[bi], a.xd[p * 3], a.xd[p * 3 + 1], a.xd[p * 3 + 2], x, Ji, ng);
+            if (ok) {
+                // ---- g = d loss / d x_c through the hash-grid interpolation weights (ngp.py:75-77 normalisation, clamp) ----
+                float g[3] = {0.f, 0.f, 0.f};
+                float xn[3]; bool inside[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const float u = (x[d] - fc.net_center[d]) / fc.net_scale[d] + 0.5f;
+                    inside[d] = u >= 0.f && u <= 1.f;
+                    xn[d] = fminf(fmaxf(u, 0.f), 1.f);
+                }
+#pragma unroll 1
+                for (int l = 0; l < kLevels; l++) {
+                    const float s = a.sd.hl.scale[l];
+                    const float px = __fmaf_rn(xn[0], s, 0.5f), py = __fmaf_rn(xn[1], s, 0.5f), pz = __fmaf_rn(xn[2], s, 0.5f);
+                    const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
+                    const uint32_t cx = (uint32_t)flx, cy = (uint32_t)fly, cz = (uint32_t)flz;
+                    const float wx = px - flx, wy = py - fly, wz = pz - flz;
+                    const uint32_t res = a.sd.hl.res[l], hs = a.sd.hl.size[l];
+                    const __half2* tb = table + a.sd.hl.offset[l];
+                    const float d0 = a.denc[(long)p * 32 + 2 * l], d1 = a.denc[(long)p * 32 + 2 * l + 1];
+                    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const float2 fv = __half22float2(__ldg(tb + grid_index(cx + (k & 1), cy + ((k >> 1) & 1), cz + (k >> 2), res, hs)));
+                        const float e = fv.x * d0 + fv.y * d1;
+                        const float ax = (k & 1) ? wx : 1.f - wx, ay = (k & 2) ? wy : 1.f - wy, az = (k & 4) ? wz : 1.f - wz;
+                        gx += ((k & 1) ? e : -e) * ay * az;
+                        gy += ((k & 2) ? e : -e) * ax * az;
+                        gz += ((k & 4) ? e : -e) * ax * ay;
+                    }
+                    g[0] += gx * s; g[1] += gy * s; g[2] += gz * s;
+                }
+#pragma unroll
+                for (int d = 0; d < 3; d++) g[d] = inside[d] ? g[d] / fc.net_scale[d] : 0.f;
+                // ---- v = -J_inv^T g ----
+                v[0] = -(Ji[0] * g[0] + Ji[3] * g[1] + Ji[6] * g[2]);
+                v[1] = -(Ji[1] * g[0] + Ji[4] * g[1] + Ji[7] * g[2]);
+                v[2] = -(Ji[2] * g[0] + Ji[5] * g[1] + Ji[8] * g[2]);
+                xh[0] = x[0]; xh[1] = x[1]; xh[2] = x[2];
+                // ---- skinning weights: trilinear, align_corners, BORDER padding (deformer_torch.py:194-198) ----
+                const float q[3] = {fc.bp.scl[0] * (x[0] + fc.bp.off[0]), fc.bp.scl[1] * (x[1] + fc.bp.off[1]), fc.bp.scl[2] * (x[2] + fc.bp.off[2])};
+                const int dims[3] = {f.W, f.H, f.D};
+                int i0[3], i1[3]; float t1[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    float u = ((q[d] + 1.f) / 2.f) * (float)(dims[d] - 1);
+                    u = fminf(fmaxf(u, 0.f), (float)(dims[d] - 1));
+                    const float fl = floorf(u);
+                    i0[d] = (int)fl; i1[d] = min(i0[d] + 1, dims[d] - 1);
+                    t1[d] = u - fl;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int ix = (k & 1) ? i1[0] : i0[0], iy = (k & 2) ? i1[1] : i0[1], iz = (k & 4) ? i1[2] : i0[2];
+                    const float wk = ((k & 1) ? t1[0] : 1.f - t1[0]) * ((k & 2) ? t1[1] : 1.f - t1[1]) * ((k & 4) ? t1[2] : 1.f - t1[2]);
+                    const long off = ((long)iz * f.H + iy) * f.W + ix;
+#pragma unroll
+                    for (int j = 0; j < 24; j++) wts[j] += wk * __ldg(a.lbs_voxel + (long)j * V + off);
+                }
+            }
+        }
+        // ---- warp reduction of w_j * v_r * xh_c into the CTA accumulator ----
+#pragma unroll 1
+        for (int j = 0; j < 24; j++) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    float t = wts[j] * v[r] * xh[c];
+                    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    if (lane == 0 && t != 0.f) atomicAdd(&acc[j * 12 + r * 4 + c], t);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 24 * 12; i += blockDim.x)
+        if (acc[i] != 0.f) atomicAdd(&a.grad_tfs[(i / 12) * 16 + (i % 12)], acc[i]);
+}
+
+}  // namespace
+
+extern "C" int ia_pose_grad(const IaScene* scene, const float* lbs_voxel, const float* xd, const int8_t* best,
+                            const float* denc, const int* count, int capacity, float* grad_tfs, ia_stream_t stream) {
+    IA_REQUIRE(capacity >= 0);
+    if (capacity == 0) return IA_OK;
+    IA_REQUIRE(lbs_voxel && xd && best && denc && count && grad_tfs);
+    PoseGradArgs a;
+    int rc = make_scene_dev(scene, a.sd, false);
+    if (rc) return rc;
+    a.lbs_voxel = lbs_voxel; a.xd = xd; a.best = best; a.denc = denc; a.count = count; a.capacity = capacity; a.grad_tfs = grad_tfs;
+    const int sms = sm_count();
+    if (sms <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    const int n_batches = (capacity + 31) / 32;
+    pose_grad_kernel<<<min(sms * 2, (n_batches + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+// ================================================================================================
 int ia_train_rays_per_warp();  // ia_kernels.cu (ia_set_option)
 
 extern "C" {
@@ -780,8 +935,9 @@ int ia_composite_bwd(int n_rays, const float* near, const float* far, const floa
                      const float* s_sigma, const float* s_rgb, const float* s_xc, const float* s_z, const int* s_count,
                      const int8_t* s_best, const float* g_rgb, const float* g_depth, const float* g_alpha,
                      const float* g_weights, float* l_xc, float* l_dsigma, float* l_drgb, int* l_count,
-                     ia_stream_t stream) {
+                     const float* rays_o, const float* rays_d, float* l_xd, int8_t* l_best, ia_stream_t stream) {
     IA_REQUIRE(n_rays >= 0);
+    IA_REQUIRE(!l_xd || (rays_o && rays_d && l_best));
     if (n_rays == 0) return IA_OK;
     IA_REQUIRE(near && far && s_sigma && s_rgb && s_xc && s_z && s_count && s_best && l_xc && l_dsigma && l_drgb && l_count);
     CompBwdArgs a;
@@ -789,6 +945,7 @@ int ia_composite_bwd(int n_rays, const float* near, const float* far, const floa
     a.s_sigma = s_sigma; a.s_rgb = s_rgb; a.s_xc = s_xc; a.s_z = s_z; a.s_count = s_count; a.s_best = s_best;
     a.g_rgb = g_rgb; a.g_depth = g_depth; a.g_alpha = g_alpha; a.g_weights = g_weights;
     a.l_xc = l_xc; a.l_dsigma = l_dsigma; a.l_drgb = l_drgb; a.l_count = l_count;
+    a.rays_o = rays_o; a.rays_d = rays_d; a.l_xd = l_xd; a.l_best = l_best;
     composite_bwd_kernel<<<(n_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
@@ -797,7 +954,8 @@ int ia_composite_bwd(int n_rays, const float* near, const float* far, const floa
 size_t ia_ngp_backward_scratch_bytes(int capacity) { return (size_t)capacity * kRowHalfs * sizeof(__half); }
 
 int ia_ngp_backward(const IaScene* scene, const float* xc, const float* dsigma, const float* drgb, const int* count,
-                    int capacity, float grad_scale, float* grad_enc, float* grad_col, void* scratch, ia_stream_t stream) {
+                    int capacity, float grad_scale, float* grad_enc, float* grad_col, void* scratch, float* denc_out,
+                    ia_stream_t stream) {
     IA_REQUIRE(capacity >= 0);
     if (capacity == 0) return IA_OK;
     IA_REQUIRE(xc && dsigma && drgb && count && grad_enc && grad_col && scratch && grad_scale > 0.f);
@@ -807,7 +965,7 @@ int ia_ngp_backward(const IaScene* scene, const float* xc, const float* dsigma, 
     host_hash_levels(a.sd.hl, nullptr);
     a.sd.filter_thr = 0.f;
     a.xc = xc; a.dsigma = dsigma; a.drgb = drgb; a.count = count; a.capacity = capacity; a.grad_scale = grad_scale;
-    a.grad_enc = grad_enc; a.scratch = reinterpret_cast<__half*>(scratch);
+    a.grad_enc = grad_enc; a.scratch = reinterpret_cast<__half*>(scratch); a.denc_out = denc_out;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = sizeof(BwdSmem);
     static bool attr_set = false;

@@ -41,6 +41,20 @@ class DNeRFModel(torch.nn.Module):
         self.scaler = GradScaler(device)
         self.world_size = 1
         self.fused_loss = True  # NeRFLoss forward/backward in one kernel (False: torch autograd through utils_loss.NeRFLoss)
+        self.SMPL_param = None
+        self.pose_optimizer = None
+        self.is_refine = False
+
+    def enable_pose_optimisation(self, smpl_params: dict, lr: float = 5e-4, is_refine: bool = False):
+        """DNeRF.py:23-24,40-51 (`opt.optimize_SMPL.enable`): per-frame SMPL parameters become learnable embeddings with
+        their own Adam group (lr 5e-4, betas/eps of confs/SNARF_NGP.yaml).  `smpl_params`: betas [1,10], global_orient
+        [F,3], body_pose [F,69], transl [F,3]."""
+        from .structures.body_model_param import SMPLParamEmbedding
+        dev = self.net_coarse.encoder.params.device
+        self.SMPL_param = SMPLParamEmbedding(**{k: torch.as_tensor(v) for k, v in smpl_params.items()}).to(dev)
+        group = [p for n, p in self.SMPL_param.named_parameters() if not n.startswith("betas")]
+        self.pose_optimizer = torch.optim.Adam(group, lr=lr, betas=(0.9, 0.99), eps=1e-15)
+        self.is_refine = is_refine
 
     def forward(self, batch, eval_mode=None, jitter=None, noise_tensor=None):
         """DNeRF.py:61-70"""
@@ -86,6 +100,16 @@ class DNeRFModel(torch.nn.Module):
         the step, which divides by world_size."""
         self.train()
         self.renderer.idx = int(batch.get("idx", 0)) if not torch.is_tensor(batch.get("idx", 0)) else 0
+        if self.SMPL_param is not None:  # DNeRF.py:113-127
+            batch = dict(batch)
+            idx = torch.as_tensor(batch.get("idx", 0), device=batch["rays_o"].device).reshape(-1)[:1].long()
+            body = self.SMPL_param(idx)
+            for k in ("global_orient", "body_pose", "transl"):
+                batch[k] = body[k]
+            cam_dist = torch.norm(batch["transl"], dim=-1, keepdim=True).detach()
+            batch["near"] = torch.zeros_like(batch["near"]) + cam_dist - 1
+            batch["far"] = torch.zeros_like(batch["far"]) + cam_dist + 1
+            self.pose_optimizer.zero_grad(set_to_none=True)
         self.deformer.prepare_deformer(batch)
         self.net_coarse.initialize(self.deformer.bbox)
         g_enc, g_col = self.net_coarse.grad_buffers()  # zeroed at creation and by every fused optimiser step
@@ -97,8 +121,8 @@ class DNeRFModel(torch.nn.Module):
             self.deformer.transform_rays_w2s(rays)
             grid = self.renderer.density_grid_train
             scene = self.deformer.scene(self.net_coarse, grid.occupancy_bits(), grid.aabb6())
-            o, d = rays.o.reshape(-1, 3).float().contiguous(), rays.d.reshape(-1, 3).float().contiguous()
-            near, far = rays.near.reshape(-1).float().contiguous(), rays.far.reshape(-1).float().contiguous()
+            o, d = rays.o.detach().reshape(-1, 3).float().contiguous(), rays.d.detach().reshape(-1, 3).float().contiguous()
+            near, far = rays.near.detach().reshape(-1).float().contiguous(), rays.far.detach().reshape(-1).float().contiguous()
             n = near.numel()
             if jitter is None:
                 jitter = torch.rand((n, 256), device=near.device)
@@ -108,9 +132,23 @@ class DNeRFModel(torch.nn.Module):
             out, saved = ops.train_fwd(scene, o, d, near, far, bg, jitter, noise_tensor)
             losses, g_rgb, g_alpha, g_w = ops.nerf_loss(out, batch["rgb"], batch["alpha"], self.loss_fn.w_rgb, self.loss_fn.w_alpha,
                                                         self.loss_fn.w_reg, self.scaler.scale_t)
-            l_xc, l_ds, l_dc, l_count = ops.composite_bwd(near, far, bg, noise_tensor, saved, g_rgb, None, g_alpha, g_w)
             from ..autograd import GRAD_SCALE
-            ops.ngp_backward(scene, l_xc, l_ds, l_dc, l_count, g_enc, g_col, GRAD_SCALE)
+            tfs = self.deformer.tfs
+            if tfs.requires_grad:
+                # pose optimisation: d loss / d tfs by implicit differentiation of the roots (deformer_torch.py:50-67),
+                # handed to autograd at `tfs` so that the SMPL forward kinematics are differentiated by torch
+                l_xc, l_ds, l_dc, l_count, l_xd, l_best = ops.composite_bwd(near, far, bg, noise_tensor, saved, g_rgb, None, g_alpha, g_w,
+                                                                            rays=(o, d))
+                denc = torch.empty((l_xc.shape[0], 32), device=o.device, dtype=torch.float32)
+                ops.ngp_backward(scene, l_xc, l_ds, l_dc, l_count, g_enc, g_col, GRAD_SCALE, denc)
+                g_tfs = torch.zeros((24, 4, 4), device=o.device, dtype=torch.float32)
+                ops.pose_grad(scene, self.deformer.deformer.lbs_voxel_final, l_xd, l_best, denc, l_count, g_tfs)
+                tfs.backward(g_tfs.reshape(tfs.shape), retain_graph=reg is not None)
+            else:
+                l_xc, l_ds, l_dc, l_count = ops.composite_bwd(near, far, bg, noise_tensor, saved, g_rgb, None, g_alpha, g_w)
+                ops.ngp_backward(scene, l_xc, l_ds, l_dc, l_count, g_enc, g_col, GRAD_SCALE)
+            if reg is not None and self.is_refine:  # DNeRF.py:139: the regulariser is dropped when refining poses
+                reg = None
             if reg is not None:
                 losses["reg"] = reg
                 losses["loss"] = losses["loss"] + reg.detach()
@@ -119,7 +157,7 @@ class DNeRFModel(torch.nn.Module):
             predicts = self.forward(batch, eval_mode=False, jitter=jitter, noise_tensor=noise_tensor)
             losses = self.loss_fn(predicts, batch)
             loss = losses["loss"]
-            if reg is not None:
+            if reg is not None and not self.is_refine:
                 losses["reg"] = reg
                 loss = loss + reg
             self.scaler.scale(loss).backward()
@@ -127,7 +165,18 @@ class DNeRFModel(torch.nn.Module):
             import torch.distributed as dist
             for g in self.net_coarse.grad_buffers():
                 dist.all_reduce(g)
+        pose_grads = [p.grad for g in self.pose_optimizer.param_groups for p in g["params"] if p.grad is not None] \
+            if self.pose_optimizer is not None else []
+        if pose_grads:
+            if self.world_size > 1:
+                for g in pose_grads:
+                    dist.all_reduce(g)
+            # GradScaler.unscale_ of the pose group; an overflow anywhere skips the whole step as in scaler.step()
+            torch._amp_foreach_non_finite_check_and_unscale_(pose_grads, self.scaler.found_inf,
+                                                             (1.0 / (self.scaler.scale_t * self.world_size)).float())
         self.optimizer.step(self.scaler, self.world_size)
+        if pose_grads and float(self.scaler.found_inf.item()) == 0.0:
+            self.pose_optimizer.step()
         self.scaler.update()
         self.global_step += 1
         return losses

@@ -201,8 +201,9 @@ def train_fwd(scene: Scene, rays_o, rays_d, near, far, bg=None, jitter=None, noi
     return out, saved
 
 
-def composite_bwd(near, far, bg, noise, saved, g_rgb=None, g_depth=None, g_alpha=None, g_weights=None):
-    """autograd of the training compositing -> compact (xc, d sigma, d rgb) list + device count"""
+def composite_bwd(near, far, bg, noise, saved, g_rgb=None, g_depth=None, g_alpha=None, g_weights=None, rays=None):
+    """autograd of the training compositing -> compact (xc, d sigma, d rgb) list + device count.
+    rays = (rays_o, rays_d): additionally return the posed sample points and winning init ids (pose gradients)."""
     n = near.numel()
     dev = near.device
     cap = n * _lib.IA_MAX_SAMPLES
@@ -210,17 +211,22 @@ def composite_bwd(near, far, bg, noise, saved, g_rgb=None, g_depth=None, g_alpha
     l_dc = torch.empty((cap, 3), device=dev, dtype=f32); l_count = torch.zeros(1, device=dev, dtype=torch.int32)
     c = lambda t: t.contiguous().float() if t is not None else None
     g_rgb, g_depth, g_alpha, g_weights = c(g_rgb), c(g_depth), c(g_alpha), c(g_weights)
+    l_xd = torch.empty((cap, 3), device=dev, dtype=f32) if rays is not None else None
+    l_best = torch.empty(cap, device=dev, dtype=torch.int8) if rays is not None else None
     _lib.count(1); check(lib().ia_composite_bwd(C.c_int(n), ptr(near, f32), ptr(far, f32), ptr(bg), ptr(noise), ptr(saved["sigma"]),
                                                 ptr(saved["rgb"]), ptr(saved["xc"]), ptr(saved["z"]), ptr(saved["count"]), ptr(saved["best"]),
                                                 ptr(g_rgb), ptr(g_depth), ptr(g_alpha), ptr(g_weights), ptr(l_xc), ptr(l_ds), ptr(l_dc),
-                                                ptr(l_count), stream()))
+                                                ptr(l_count), ptr(rays[0]) if rays is not None else None,
+                                                ptr(rays[1]) if rays is not None else None, ptr(l_xd), ptr(l_best), stream()))
+    if rays is not None:
+        return l_xc, l_ds, l_dc, l_count, l_xd, l_best
     return l_xc, l_ds, l_dc, l_count
 
 
 _SCRATCH = {}
 
 
-def ngp_backward(scene: Scene, xc, dsigma, drgb, count, grad_enc, grad_col, grad_scale=128.0):
+def ngp_backward(scene: Scene, xc, dsigma, drgb, count, grad_enc, grad_col, grad_scale=128.0, denc_out=None):
     """accumulate d loss / d (encoder.params, color_net.params) for a list of canonical points"""
     cap = xc.shape[0]
     dev = xc.device
@@ -230,7 +236,8 @@ def ngp_backward(scene: Scene, xc, dsigma, drgb, count, grad_enc, grad_col, grad
         _SCRATCH[key] = torch.empty(nbytes, device=dev, dtype=torch.uint8)
     s = scene.c_struct()
     _lib.count(2); check(lib().ia_ngp_backward(C.byref(s), ptr(xc, f32), ptr(dsigma, f32), ptr(drgb, f32), ptr(count), C.c_int(cap),
-                                               C.c_float(grad_scale), ptr(grad_enc, f32), ptr(grad_col, f32), ptr(_SCRATCH[key]), stream()))
+                                               C.c_float(grad_scale), ptr(grad_enc, f32), ptr(grad_col, f32), ptr(_SCRATCH[key]),
+                                               ptr(denc_out), stream()))
 
 
 def adam_step(params, grads, exp_avg, exp_avg_sq, lr, betas, eps, step, inv_grad_scale=1.0, found_inf=None, grad_scale_dev=None):
@@ -322,3 +329,9 @@ def nerf_loss(out: dict, target_rgb, target_alpha, w_rgb=1.0, w_alpha=0.1, w_reg
     losses = {"mse_loss": mse, "loss_alpha_coarse": msa, "reg_alpha": ra, "reg_density": rw,
               "loss": w_rgb * mse + w_alpha * msa + w_reg * ra + w_reg * rw}
     return losses, g_rgb, g_alpha, g_w
+
+
+def pose_grad(scene: Scene, lbs_voxel, xd, best, denc, count, grad_tfs):
+    """d loss / d tfs (+=) by implicit differentiation of the Broyden roots (deformer_torch.py:50-67)"""
+    _lib.count(1); check(lib().ia_pose_grad(C.byref(scene.c_struct()), ptr(lbs_voxel.reshape(24, -1).contiguous(), f32), ptr(xd, f32),
+                                            ptr(best, torch.int8), ptr(denc, f32), ptr(count), C.c_int(xd.shape[0]), ptr(grad_tfs, f32), stream()))

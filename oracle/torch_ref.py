@@ -20,8 +20,9 @@ def ste_half(x: torch.Tensor, emulate=True) -> torch.Tensor:
     return x + (x.half().float() - x).detach()
 
 
-def hash_encode(x01: torch.Tensor, grid: torch.Tensor, emulate=True) -> torch.Tensor:
-    """x01 [P,3] in [0,1]; grid [total,2] fp32 master table -> [P,32]"""
+def hash_encode(x01: torch.Tensor, grid: torch.Tensor, emulate=True, pos_grad=False) -> torch.Tensor:
+    """x01 [P,3] in [0,1]; grid [total,2] fp32 master table -> [P,32].  pos_grad: keep the interpolation weights in the
+    autograd graph (tiny-cuda-nn's input gradient, needed by the pose-gradient test)."""
     lay = capi.hashgrid_layout()
     feats = []
     gtab = ste_half(grid, emulate)
@@ -31,14 +32,14 @@ def hash_encode(x01: torch.Tensor, grid: torch.Tensor, emulate=True) -> torch.Te
         fl = torch.floor(pos)
         w = pos - fl
         c0 = fl.long()
-        acc = torch.zeros((x01.shape[0], 2), dtype=torch.float32)
+        acc = torch.zeros((x01.shape[0], 2), dtype=torch.float32, device=x01.device)
         for k in range(8):
             dx, dy, dz = k & 1, (k >> 1) & 1, (k >> 2) & 1
             cx, cy, cz = c0[:, 0] + dx, c0[:, 1] + dy, c0[:, 2] + dz
             wx = w[:, 0] if dx else 1 - w[:, 0]
             wy = w[:, 1] if dy else 1 - w[:, 1]
             wz = w[:, 2] if dz else 1 - w[:, 2]
-            wt = (wx * wy * wz).detach()
+            wt = (wx * wy * wz) if pos_grad else (wx * wy * wz).detach()
             stride, idx, hashed = 1, torch.zeros_like(cx), False
             for comp in (cx, cy, cz):
                 if stride <= size:
@@ -52,14 +53,14 @@ def hash_encode(x01: torch.Tensor, grid: torch.Tensor, emulate=True) -> torch.Te
     return torch.cat(feats, dim=1)
 
 
-def ngp_forward(x: torch.Tensor, center, scale, enc_params: torch.Tensor, col_params: torch.Tensor, emulate=True):
+def ngp_forward(x: torch.Tensor, center, scale, enc_params: torch.Tensor, col_params: torch.Tensor, emulate=True, pos_grad=False):
     """ngp.py:73-83 -> (sigma [P], rgb [P,3])"""
     W1 = ste_half(enc_params[:2048].view(64, 32), emulate); W2 = ste_half(enc_params[2048:3072].view(16, 64), emulate)
     grid = enc_params[3072:].view(-1, 2)
     W3 = ste_half(col_params[:1024].view(64, 16), emulate); W4 = ste_half(col_params[1024:5120].view(64, 64), emulate)
     W5 = ste_half(col_params[5120:].view(16, 64), emulate)
     xn = ((x - torch.as_tensor(center)) / torch.as_tensor(scale) + 0.5).clamp(0, 1)
-    enc = hash_encode(xn, grid, emulate)
+    enc = hash_encode(xn, grid, emulate, pos_grad)
     h1 = ste_half(torch.relu(enc @ W1.T), emulate)
     o16 = ste_half(h1 @ W2.T, emulate)
     sigma = o16[:, 0]
@@ -115,3 +116,30 @@ def render_train_torch(out_np: dict, net, enc_params: torch.Tensor, col_params: 
     color = (w[..., None] * rgbv).sum(-2) + no_hit[:, None] * torch.as_tensor(bg)
     depth = (w * torch.from_numpy(out_np["z"])).sum(-1)
     return {"rgb": color, "depth": depth, "alpha": w.sum(-1), "weights": w, "n_net": int(valid_any.sum())}
+
+
+def pose_grad_reference(xd, best, xc_opt, j_inv, lbs_voxel, offset_k, scale_k, tfs, center, scale, enc_params, col_params,
+                        g_sigma, g_rgb, emulate=True):
+    """d loss / d tfs of the selected roots, restating deformers/fast_snarf/deformer_torch.py:50-67 (version 1) literally:
+    x_c = x_c*.detach() + bmv(-J_inv, x_d* - x_d*.detach()),  x_d* = forward_skinning(x_c*, tfs) (:171-188) with weights
+    from F.grid_sample(lbs_voxel, scale*(x_c+offset), align_corners=True, padding_mode='border') (:190-201), followed by
+    the network (ngp.py:73-83) whose positional gradient is tiny-cuda-nn's.  All inputs CPU torch tensors; `best` [P]
+    selects the initialisation per point (-1: none).  Returns grad [24,4,4] for loss = sum(g_sigma*sigma + g_rgb*rgb)."""
+    import torch.nn.functional as F
+    sel = best >= 0
+    idx = best.clamp(min=0).long()
+    P = xd.shape[0]
+    xc0 = xc_opt[torch.arange(P), idx][sel].detach()
+    Ji = j_inv[torch.arange(P), idx][sel].detach()
+    tfs = tfs.detach().clone().requires_grad_(True)
+    q = (scale_k.reshape(1, 3) * (xc0 + offset_k.reshape(1, 3))).reshape(1, 1, 1, -1, 3)
+    w = F.grid_sample(lbs_voxel.reshape(1, 24, *lbs_voxel.shape[-3:]), q, align_corners=True, mode="bilinear", padding_mode="border")
+    w = w.reshape(24, -1).T                                           # [Q,24]
+    xh = torch.cat([xc0, torch.ones_like(xc0[:, :1])], dim=1)           # [Q,4]
+    xd_opt = torch.einsum("pn,nij,pj->pi", w, tfs.reshape(24, 4, 4), xh)[:, :3]
+    corr = torch.einsum("pij,pj->pi", -Ji, xd_opt - xd_opt.detach())
+    xc = xc0 + corr
+    sigma, rgb = ngp_forward(xc, center, scale, enc_params, col_params, emulate, pos_grad=True)
+    loss = (sigma * g_sigma[sel]).sum() + (rgb * g_rgb[sel]).sum()
+    loss.backward()
+    return tfs.grad.reshape(24, 4, 4)
