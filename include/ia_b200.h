@@ -75,6 +75,17 @@ int ia_hashgrid_layout(uint32_t res[IA_NUM_LEVELS], float scale[IA_NUM_LEVELS], 
 int ia_precompute(const float* voxel_w, const float* tfs, const float* offset_k, const float* scale_k, int D, int H,
                   int W, float* field_out, float* voxel_d_out, float* aabb_out, ia_stream_t stream);
 
+/* Once-per-subject voxelisation of the SMPL skinning weights (deformers/fast_snarf/deformer_torch.py:225-244
+ * query_weights_smpl, called from switch_to_explicit :150-158): K nearest canonical vertices of every voxel centre
+ * (pytorch3d knn_points contract: squared distances, ascending, ties keep the earlier vertex), weights
+ * 1/clamp(sqrt(d2),1e-4,1) normalised, blended vertex skinning weights, then `smooth_passes` Jacobi passes
+ * ((w-mean6)*0.7+mean6 on interior voxels, renormalise).  verts [n][3], vert_weights [n][24]; xs [W], ys [H], zs [D] =
+ * torch.linspace(-1,1,.) grids; voxel centre = (xs[x], ys[y], zs[z]/ratio) * scale[0] + offset[3] (offset, scale:
+ * device pointers, no host sync).  lbs_voxel [24][D][H][W] out; scratch same size (nullable if smooth_passes == 0). */
+int ia_voxelize_weights(const float* verts, const float* vert_weights, int n_verts, const float* xs, const float* ys,
+                        const float* zs, int D, int H, int W, const float* offset, const float* scale, float ratio,
+                        int knn, int smooth_passes, float* lbs_voxel, float* scratch, ia_stream_t stream);
+
 /* Per-frame bone transforms in one launch.  Replaces, for everything the renderer consumes, the SMPL forward + tfs
  * algebra of SNARFDeformer.prepare_deformer (deformers/snarf_deformer.py:79-86; smplx/lbs.py:295-329 Rodrigues,
  * :345-401 kinematic chain; body_models.py:353-360 transl): global_orient [3], body_pose [69], transl [3] (nullable),

@@ -51,39 +51,6 @@ def get_bbox_from_smpl(vs, factor=1.2):
     return torch.cat([c - s[:, None], c + s[:, None]], dim=0)
 
 
-def knn_points(x: torch.Tensor, verts: torch.Tensor, K: int, chunk: int = 16384):
-    """brute-force K nearest vertices (squared distances), the contract of third_parties/pytorch3d/ops.py:123-206"""
-    d_all, i_all = [], []
-    v2 = (verts * verts).sum(-1)
-    for s in range(0, x.shape[0], chunk):
-        xs = x[s:s + chunk]
-        d2 = (xs * xs).sum(-1, keepdim=True) - 2.0 * xs @ verts.T + v2[None]
-        _, idx = torch.topk(d2, K, dim=1, largest=False)
-        diff = xs[:, None, :] - verts[idx]
-        d_all.append((diff * diff).sum(-1))
-        i_all.append(idx)
-    return torch.cat(d_all), torch.cat(i_all)
-
-
-def query_weights_smpl(x, smpl_verts, smpl_weights, resolution=128):
-    """deformer_torch.py:225-244: inverse-distance blend of the 30 nearest vertices' skinning weights followed by
-    30 Laplacian smoothing passes on the [24, res/4, res, res] grid."""
-    dist, idx = knn_points(x[0], smpl_verts[0], K=30)
-    dist = dist.sqrt().clamp_(0.0001, 1.0)
-    weights = smpl_weights[0, idx]
-    ws = 1.0 / dist
-    ws = ws / ws.sum(-1, keepdim=True)
-    weights = (ws[..., None] * weights).sum(-2)[None]
-    b, c, d, h, w = 1, 24, resolution // 4, resolution, resolution
-    weights = weights.permute(0, 2, 1).reshape(b, c, d, h, w).contiguous()
-    for _ in range(30):
-        mean = (weights[:, :, 2:, 1:-1, 1:-1] + weights[:, :, :-2, 1:-1, 1:-1] + weights[:, :, 1:-1, 2:, 1:-1]
-                + weights[:, :, 1:-1, :-2, 1:-1] + weights[:, :, 1:-1, 1:-1, 2:] + weights[:, :, 1:-1, 1:-1, :-2]) / 6.0
-        weights[:, :, 1:-1, 1:-1, 1:-1] = (weights[:, :, 1:-1, 1:-1, 1:-1] - mean) * 0.7 + mean
-        weights = weights / weights.sum(1, keepdim=True)
-    return weights.detach()
-
-
 class ForwardDeformer(torch.nn.Module):
     """deformers/fast_snarf/deformer_torch.py::ForwardDeformer -- state holder for the voxelised skinning field."""
 
@@ -117,14 +84,10 @@ class ForwardDeformer(torch.nn.Module):
         scale_kernel[:, :, -1] = scale_kernel[:, :, -1] * self.ratio
         self.register_buffer("scale_kernel", scale_kernel)
         if lbs_voxel is None:
-            xr = torch.linspace(-1, 1, steps=w, device=device).view(1, 1, 1, w).expand(1, d, h, w)
-            yr = torch.linspace(-1, 1, steps=h, device=device).view(1, 1, h, 1).expand(1, d, h, w)
-            zr = torch.linspace(-1, 1, steps=d, device=device).view(1, d, 1, 1).expand(1, d, h, w)
-            grid = torch.cat((xr, yr, zr), dim=0).reshape(1, 3, -1).permute(0, 2, 1)
-            g = grid.clone()
-            g[..., -1] /= self.ratio
-            g = g * scale + offset
-            lbs_voxel = query_weights_smpl(g, smpl_verts, smpl_weights, resolution)
+            # deformer_torch.py:150-158 + query_weights_smpl (:225-244): KNN-30 blend + 30 smoothing passes in two kernels
+            lin = lambda n: torch.linspace(-1, 1, steps=n, device=device)
+            lbs_voxel = ops.voxelize_weights(smpl_verts[0].float(), smpl_weights[0].float(), lin(w), lin(h), lin(d),
+                                             offset.reshape(3).float(), scale.reshape(1).float(), float(self.ratio))
         self.register_buffer("lbs_voxel_final", lbs_voxel.reshape(1, 24, d, h, w).contiguous().float())
 
     def precompute(self, tfs):

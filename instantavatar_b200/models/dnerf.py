@@ -69,11 +69,16 @@ class DNeRFModel(torch.nn.Module):
         return self.renderer.render_train(rays, model, 1 if use_noise else 0, batch.get("bg_color", None), jitter, noise_tensor)
 
     @torch.no_grad()
-    def render_image_fast(self, batch, img_size, jitters=None):
-        """DNeRF.py:72-97: per-frame preparation, test occupancy grid, fused render."""
+    def frame_prepare(self, batch, jitters=None):
+        """first half of render_image_fast (DNeRF.py:72-84): everything that depends on the pose only -- bone transforms,
+        skinning field, test occupancy grid.  Does not read the rays."""
         self.deformer.prepare_deformer(batch)
         self.net_coarse.initialize(self.deformer.bbox)
         self.renderer.density_grid_test.initialize(self.deformer, self.net_coarse, jitters=jitters)
+
+    @torch.no_grad()
+    def frame_render(self, batch, img_size):
+        """second half (DNeRF.py:86-97): rays -> root frame -> fused march"""
         self.image_width = img_size[1]
         d = self.forward(batch, eval_mode=True)
         rgb = d["rgb_coarse"].reshape(-1, *img_size, 3)
@@ -81,6 +86,12 @@ class DNeRFModel(torch.nn.Module):
         alpha = d["alpha_coarse"].reshape(-1, *img_size)
         counter = d["counter_coarse"].reshape(-1, *img_size)
         return rgb, depth, alpha, counter
+
+    @torch.no_grad()
+    def render_image_fast(self, batch, img_size, jitters=None):
+        """DNeRF.py:72-97: per-frame preparation, test occupancy grid, fused render."""
+        self.frame_prepare(batch, jitters)
+        return self.frame_render(batch, img_size)
 
     def update_density_grid(self, jitter=None):
         """DNeRF.py:99-110: every 20 steps refresh the train occupancy grid and return the density regulariser."""

@@ -335,3 +335,18 @@ def pose_grad(scene: Scene, lbs_voxel, xd, best, denc, count, grad_tfs):
     """d loss / d tfs (+=) by implicit differentiation of the Broyden roots (deformer_torch.py:50-67)"""
     _lib.count(1); check(lib().ia_pose_grad(C.byref(scene.c_struct()), ptr(lbs_voxel.reshape(24, -1).contiguous(), f32), ptr(xd, f32),
                                             ptr(best, torch.int8), ptr(denc, f32), ptr(count), C.c_int(xd.shape[0]), ptr(grad_tfs, f32), stream()))
+
+
+def voxelize_weights(verts, vert_weights, xs, ys, zs, offset, scale, ratio, knn=30, smooth_passes=30):
+    """query_weights_smpl (deformer_torch.py:225-244) -> lbs_voxel [1,24,D,H,W]"""
+    dev = verts.device
+    D, H, W = zs.numel(), ys.numel(), xs.numel()
+    out = torch.empty((1, 24, D, H, W), device=dev, dtype=f32)
+    scratch = torch.empty_like(out) if smooth_passes > 0 else None
+    _lib.count(1 + smooth_passes)
+    check(lib().ia_voxelize_weights(ptr(verts.reshape(-1, 3).contiguous(), f32), ptr(vert_weights.reshape(-1, 24).contiguous(), f32),
+                                    C.c_int(verts.reshape(-1, 3).shape[0]), ptr(xs.contiguous(), f32), ptr(ys.contiguous(), f32),
+                                    ptr(zs.contiguous(), f32), C.c_int(D), C.c_int(H), C.c_int(W), ptr(offset.reshape(3).contiguous(), f32),
+                                    ptr(scale.reshape(1).contiguous(), f32), C.c_float(ratio), C.c_int(knn), C.c_int(smooth_passes),
+                                    ptr(out), ptr(scratch), stream()))
+    return out
