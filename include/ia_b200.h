@@ -200,8 +200,13 @@ int ia_composite_bwd(int n_rays, const float* near, const float* far, const floa
 size_t ia_ngp_backward_scratch_bytes(int capacity);
 int ia_ngp_backward(const IaScene* scene /*[host]*/, const float* xc, const float* dsigma, const float* drgb,
                     const int* count, int capacity, float grad_scale, float* grad_enc, float* grad_col, void* scratch,
-                    float* denc_out /*nullable [capacity][32]: d loss / d hash features, input of ia_pose_grad*/,
+                    float* denc_out /*nullable [capacity][32]: d loss / d hash features, input of ia_pose_grad;
+                                      grad_enc and grad_col may both be null (frozen network) when denc_out is given*/,
                     ia_stream_t stream);
+
+/* d loss / d x [n][3] of NeRFNGPNet.forward's input (tiny-cuda-nn's input gradient of HashGrid through the bbox
+ * normalisation of ngp.py:75-77) from denc [n][32] = d loss / d (hash features) as written by ia_ngp_backward. */
+int ia_ngp_input_grad(const IaScene* scene /*[host]*/, const float* x, const float* denc, int n, float* dx, ia_stream_t stream);
 
 /* Pose gradients (SNARF_NGP_refine / optimize_SMPL): d loss / d tfs [24][4][4] (+=) through Fast-SNARF's implicit
  * differentiation (deformers/fast_snarf/deformer_torch.py:50-67, version 1): for each list sample the winning

@@ -23,6 +23,7 @@ class _RenderTrain(torch.autograd.Function):
         out, saved = ops.train_fwd(scene, rays_o, rays_d, near, far, bg, jitter, noise, stats)
         ctx.scene, ctx.saved, ctx.misc = scene, saved, (near, far, bg, noise)
         ctx.pose = (rays_o, rays_d, lbs_voxel, tfs.shape) if tfs is not None and tfs.requires_grad else None
+        ctx.frozen = not (enc_params.requires_grad or col_params.requires_grad)  # pose refinement with a fixed network
         ctx.shapes = (enc_params.shape, col_params.shape)
         ctx.accum = accum  # optional persistent (grad_enc, grad_col) buffers to accumulate into
         return out["rgb"], out["depth"], out["alpha"], out["weights"]
@@ -36,7 +37,11 @@ class _RenderTrain(torch.autograd.Function):
                                   rays=pose[:2] if pose is not None else None)
         l_xc, l_ds, l_dc, l_count = lists[:4]
         denc = torch.empty((l_xc.shape[0], 32), device=dev, dtype=torch.float32) if pose is not None else None
-        if ctx.accum is not None:
+        if ctx.frozen:
+            if pose is None:
+                return (None,) * 14
+            g_enc = g_col = None
+        elif ctx.accum is not None:
             g_enc, g_col = ctx.accum
         else:
             g_enc = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32)
@@ -47,7 +52,7 @@ class _RenderTrain(torch.autograd.Function):
             g_tfs = torch.zeros((24, 4, 4), device=dev, dtype=torch.float32)
             ops.pose_grad(ctx.scene, pose[2], lists[4], lists[5], denc, l_count, g_tfs)
             g_tfs = g_tfs.reshape(pose[3])
-        if ctx.accum is not None:
+        if ctx.accum is not None or ctx.frozen:
             return (None,) * 12 + (g_tfs, None)
         return (g_enc, g_col) + (None,) * 10 + (g_tfs, None)
 
@@ -120,3 +125,41 @@ def deform_query_train(deformer, net, pts):
     scene = deformer.scene(net)
     return _DeformQueryTrain.apply(net.encoder.params, net.color_net.params, scene, pts, net.grad_buffers(), deformer.tfs,
                                    deformer.deformer.lbs_voxel_final)
+
+
+class _NGPForward(torch.autograd.Function):
+    """NeRFNGPNet.forward (ngp.py:73-83) as a differentiable op for arbitrary callers (custom deformers, SMPLDeformer's
+    `model(pts_cano)`): gradients w.r.t. the two flat parameter tensors and w.r.t. the input points."""
+
+    @staticmethod
+    def forward(ctx, x, enc_params, col_params, scene, accum=None):
+        x = x.reshape(-1, 3).float().contiguous()
+        rgb, sigma = ops.ngp_forward(scene, x)
+        ctx.scene, ctx.x, ctx.accum = scene, x.detach(), accum
+        ctx.need_x = x.requires_grad
+        ctx.need_p = enc_params.requires_grad or col_params.requires_grad
+        ctx.shapes = (enc_params.shape, col_params.shape)
+        return rgb, sigma
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_sigma):
+        x = ctx.x
+        dev, n = x.device, x.shape[0]
+        if n == 0 or not (ctx.need_x or ctx.need_p):
+            return (torch.zeros_like(x) if ctx.need_x else None), None, None, None, None
+        g_sigma = g_sigma.contiguous().float() if g_sigma is not None else torch.zeros(n, device=dev)
+        g_rgb = g_rgb.contiguous().float() if g_rgb is not None else torch.zeros((n, 3), device=dev)
+        count = torch.full((1,), n, device=dev, dtype=torch.int32)
+        denc = torch.empty((n, 32), device=dev, dtype=torch.float32) if ctx.need_x else None
+        g_enc = g_col = None
+        if ctx.need_p:
+            if ctx.accum is not None:
+                g_enc, g_col = ctx.accum
+            else:
+                g_enc = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32)
+                g_col = torch.zeros(ctx.shapes[1], device=dev, dtype=torch.float32)
+        ops.ngp_backward(ctx.scene, x, g_sigma, g_rgb, count, g_enc, g_col, GRAD_SCALE, denc)
+        dx = ops.ngp_input_grad(ctx.scene, x, denc) if ctx.need_x else None
+        if ctx.accum is not None or not ctx.need_p:
+            return dx, None, None, None, None
+        return dx, g_enc, g_col, None, None

@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) ngp_backward_kernel(const _
             for (int c = 0; c < 32; c++) a.denc_out[(long)p * 32 + c] = ws.dEnc[lane][c] * inv_scale;
         }
         // ---- hash-grid gradient scatter (lane = sample); samples without upstream gradient contribute nothing ----
-        if (has && (dsig != 0.f || dr != 0.f || dg != 0.f || db != 0.f)) {
+        if (a.grad_enc && has && (dsig != 0.f || dr != 0.f || dg != 0.f || db != 0.f)) {
 #pragma unroll 1
             for (int l = 0; l < kLevels; l++) {
                 const float s = a.sd.hl.scale[l];
@@ -756,6 +756,45 @@ __global__ void grad_finite_kernel(const float* __restrict__ g, long n, float* _
 // ================================================================================================
 namespace {
 
+// d loss / d x of the network input from d loss / d (hash features): derivative of the trilinear interpolation weights
+// times the fp16 corner features, per level (tiny-cuda-nn's HashGrid input gradient), through the bbox normalisation
+// of ngp.py:75-77 (zero where the clamp is active).
+__device__ __forceinline__ void hash_input_grad(const HashLevels& hl, const __half2* __restrict__ table, const float* center,
+                                                const float* scale, const float x[3], const float* __restrict__ denc, float g[3]) {
+    float xn[3]; bool inside[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float u = (x[d] - center[d]) / scale[d] + 0.5f;
+        inside[d] = u >= 0.f && u <= 1.f;
+        xn[d] = fminf(fmaxf(u, 0.f), 1.f);
+    }
+    g[0] = g[1] = g[2] = 0.f;
+#pragma unroll 1
+    for (int l = 0; l < kLevels; l++) {
+        const float s = hl.scale[l];
+        const float px = __fmaf_rn(xn[0], s, 0.5f), py = __fmaf_rn(xn[1], s, 0.5f), pz = __fmaf_rn(xn[2], s, 0.5f);
+        const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
+        const uint32_t cx = (uint32_t)flx, cy = (uint32_t)fly, cz = (uint32_t)flz;
+        const float wx = px - flx, wy = py - fly, wz = pz - flz;
+        const uint32_t res = hl.res[l], hs = hl.size[l];
+        const __half2* tb = table + hl.offset[l];
+        const float d0 = denc[2 * l], d1 = denc[2 * l + 1];
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float2 fv = __half22float2(__ldg(tb + grid_index(cx + (k & 1), cy + ((k >> 1) & 1), cz + (k >> 2), res, hs)));
+            const float e = fv.x * d0 + fv.y * d1;
+            const float ax = (k & 1) ? wx : 1.f - wx, ay = (k & 2) ? wy : 1.f - wy, az = (k & 4) ? wz : 1.f - wz;
+            gx += ((k & 1) ? e : -e) * ay * az;
+            gy += ((k & 2) ? e : -e) * ax * az;
+            gz += ((k & 4) ? e : -e) * ax * ay;
+        }
+        g[0] += gx * s; g[1] += gy * s; g[2] += gz * s;
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) g[d] = inside[d] ? g[d] / scale[d] : 0.f;
+}
+
 struct PoseGradArgs {
     SceneDev sd;
     const float* lbs_voxel;   // [24][D][H][W] (reference layout)
@@ -789,39 +828,8 @@ __global__ void __launch_bounds__(256) pose_grad_kernel(const __grid_constant__ 
             int ng = 0;
             const bool ok = broyden_solve(f, fc.bp, fc.Tb[bi], a.xd[p * 3], a.xd[p * 3 + 1], a.xd[p * 3 + 2], x, Ji, ng);
             if (ok) {
-                // ---- g = d loss / d x_c through the hash-grid interpolation weights (ngp.py:75-77 normalisation, clamp) ----
-                float g[3] = {0.f, 0.f, 0.f};
-                float xn[3]; bool inside[3];
-#pragma unroll
-                for (int d = 0; d < 3; d++) {
-                    const float u = (x[d] - fc.net_center[d]) / fc.net_scale[d] + 0.5f;
-                    inside[d] = u >= 0.f && u <= 1.f;
-                    xn[d] = fminf(fmaxf(u, 0.f), 1.f);
-                }
-#pragma unroll 1
-                for (int l = 0; l < kLevels; l++) {
-                    const float s = a.sd.hl.scale[l];
-                    const float px = __fmaf_rn(xn[0], s, 0.5f), py = __fmaf_rn(xn[1], s, 0.5f), pz = __fmaf_rn(xn[2], s, 0.5f);
-                    const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
-                    const uint32_t cx = (uint32_t)flx, cy = (uint32_t)fly, cz = (uint32_t)flz;
-                    const float wx = px - flx, wy = py - fly, wz = pz - flz;
-                    const uint32_t res = a.sd.hl.res[l], hs = a.sd.hl.size[l];
-                    const __half2* tb = table + a.sd.hl.offset[l];
-                    const float d0 = a.denc[(long)p * 32 + 2 * l], d1 = a.denc[(long)p * 32 + 2 * l + 1];
-                    float gx = 0.f, gy = 0.f, gz = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const float2 fv = __half22float2(__ldg(tb + grid_index(cx + (k & 1), cy + ((k >> 1) & 1), cz + (k >> 2), res, hs)));
-                        const float e = fv.x * d0 + fv.y * d1;
-                        const float ax = (k & 1) ? wx : 1.f - wx, ay = (k & 2) ? wy : 1.f - wy, az = (k & 4) ? wz : 1.f - wz;
-                        gx += ((k & 1) ? e : -e) * ay * az;
-                        gy += ((k & 2) ? e : -e) * ax * az;
-                        gz += ((k & 4) ? e : -e) * ax * ay;
-                    }
-                    g[0] += gx * s; g[1] += gy * s; g[2] += gz * s;
-                }
-#pragma unroll
-                for (int d = 0; d < 3; d++) g[d] = inside[d] ? g[d] / fc.net_scale[d] : 0.f;
+                float g[3];
+                hash_input_grad(a.sd.hl, table, fc.net_center, fc.net_scale, x, a.denc + (long)p * 32, g);
                 // ---- v = -J_inv^T g ----
                 v[0] = -(Ji[0] * g[0] + Ji[3] * g[1] + Ji[6] * g[2]);
                 v[1] = -(Ji[1] * g[0] + Ji[4] * g[1] + Ji[7] * g[2]);
@@ -869,6 +877,36 @@ __global__ void __launch_bounds__(256) pose_grad_kernel(const __grid_constant__ 
 }
 
 }  // namespace
+
+namespace {
+struct InputGradArgs { SceneDev sd; const float* x; const float* denc; int n; float* dx; };
+__global__ void __launch_bounds__(256) ngp_input_grad_kernel(const __grid_constant__ InputGradArgs a) {
+    __shared__ float cs[6];
+    if (threadIdx.x < 3) { cs[threadIdx.x] = a.sd.s.net_center[threadIdx.x]; cs[3 + threadIdx.x] = a.sd.s.net_scale[threadIdx.x]; }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n) return;
+    const float x[3] = {a.x[p * 3], a.x[p * 3 + 1], a.x[p * 3 + 2]};
+    float g[3];
+    hash_input_grad(a.sd.hl, reinterpret_cast<const __half2*>(a.sd.s.table_h), cs, cs + 3, x, a.denc + (long)p * 32, g);
+    a.dx[p * 3] = g[0]; a.dx[p * 3 + 1] = g[1]; a.dx[p * 3 + 2] = g[2];
+}
+}  // namespace
+
+extern "C" int ia_ngp_input_grad(const IaScene* scene, const float* x, const float* denc, int n, float* dx, ia_stream_t stream) {
+    IA_REQUIRE(n >= 0);
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(x && denc && dx);
+    IA_REQUIRE(scene && scene->table_h && scene->net_center && scene->net_scale);
+    InputGradArgs a;
+    a.sd.s = *scene;
+    host_hash_levels(a.sd.hl, nullptr);
+    a.sd.filter_thr = 0.f;
+    a.x = x; a.denc = denc; a.n = n; a.dx = dx;
+    ngp_input_grad_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
 
 extern "C" int ia_pose_grad(const IaScene* scene, const float* lbs_voxel, const float* xd, const int8_t* best,
                             const float* denc, const int* count, int capacity, float* grad_tfs, ia_stream_t stream) {
@@ -958,7 +996,9 @@ int ia_ngp_backward(const IaScene* scene, const float* xc, const float* dsigma, 
                     ia_stream_t stream) {
     IA_REQUIRE(capacity >= 0);
     if (capacity == 0) return IA_OK;
-    IA_REQUIRE(xc && dsigma && drgb && count && grad_enc && grad_col && scratch && grad_scale > 0.f);
+    IA_REQUIRE(xc && dsigma && drgb && count && scratch && grad_scale > 0.f);
+    // frozen network (pose refinement, eval.py:67-70): both parameter gradients null, only d loss / d features wanted
+    IA_REQUIRE((grad_enc && grad_col) || (!grad_enc && !grad_col && denc_out));
     IA_REQUIRE(scene && scene->table_h && scene->mlp_h && scene->net_center && scene->net_scale);
     NgpBwdArgs a;
     a.sd.s = *scene;
@@ -977,7 +1017,8 @@ int ia_ngp_backward(const IaScene* scene, const float* xc, const float* dsigma, 
     if (sms <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
     const int n_tiles = (capacity + 31) / 32;
     ngp_backward_kernel<<<min(sms, (n_tiles + kBwdWarps - 1) / kBwdWarps), kBwdWarps * 32, smem, st>>>(a);
-    wgrad_kernel<<<min(sms * 2, (capacity + 31) / 32), 256, 0, st>>>(a.scratch, count, capacity, 1.0f / grad_scale, grad_enc, grad_col);
+    if (grad_enc)
+        wgrad_kernel<<<min(sms * 2, (capacity + 31) / 32), 256, 0, st>>>(a.scratch, count, capacity, 1.0f / grad_scale, grad_enc, grad_col);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

@@ -56,12 +56,21 @@ class DNeRFModel(torch.nn.Module):
         self.pose_optimizer = torch.optim.Adam(group, lr=lr, betas=(0.9, 0.99), eps=1e-15)
         self.is_refine = is_refine
 
+    def freeze_network(self, frozen: bool = True):
+        """eval.py:67-70: pose refinement optimises the SMPL parameters only"""
+        for p in self.net_coarse.parameters():
+            p.requires_grad_(not frozen)
+
+    @property
+    def network_frozen(self):
+        return not self.net_coarse.encoder.params.requires_grad
+
     def forward(self, batch, eval_mode=None, jitter=None, noise_tensor=None):
         """DNeRF.py:61-70"""
         eval_mode = (not self.training) if eval_mode is None else eval_mode
         rays = Rays(o=batch["rays_o"], d=batch["rays_d"], near=batch["near"], far=batch["far"])
         self.deformer.transform_rays_w2s(rays)
-        use_noise = self.global_step < 1000 and not eval_mode
+        use_noise = self.global_step < 1000 and not self.is_refine and not eval_mode  # DNeRF.py:65
         model = BoundModel(self.deformer, self.net_coarse, eval_mode)
         self.renderer.image_width = self.image_width
         if eval_mode:
@@ -137,7 +146,7 @@ class DNeRFModel(torch.nn.Module):
             n = near.numel()
             if jitter is None:
                 jitter = torch.rand((n, 256), device=near.device)
-            if noise_tensor is None and self.global_step < 1000:
+            if noise_tensor is None and self.global_step < 1000 and not self.is_refine:
                 noise_tensor = torch.randn((n, 256), device=near.device)
             bg = batch["bg_color"].reshape(-1, 3).float().contiguous() if batch.get("bg_color", None) is not None else None
             out, saved = ops.train_fwd(scene, o, d, near, far, bg, jitter, noise_tensor)
@@ -151,11 +160,12 @@ class DNeRFModel(torch.nn.Module):
                 l_xc, l_ds, l_dc, l_count, l_xd, l_best = ops.composite_bwd(near, far, bg, noise_tensor, saved, g_rgb, None, g_alpha, g_w,
                                                                             rays=(o, d))
                 denc = torch.empty((l_xc.shape[0], 32), device=o.device, dtype=torch.float32)
-                ops.ngp_backward(scene, l_xc, l_ds, l_dc, l_count, g_enc, g_col, GRAD_SCALE, denc)
+                frozen = self.network_frozen
+                ops.ngp_backward(scene, l_xc, l_ds, l_dc, l_count, None if frozen else g_enc, None if frozen else g_col, GRAD_SCALE, denc)
                 g_tfs = torch.zeros((24, 4, 4), device=o.device, dtype=torch.float32)
                 ops.pose_grad(scene, self.deformer.deformer.lbs_voxel_final, l_xd, l_best, denc, l_count, g_tfs)
                 tfs.backward(g_tfs.reshape(tfs.shape), retain_graph=reg is not None)
-            else:
+            elif not self.network_frozen:
                 l_xc, l_ds, l_dc, l_count = ops.composite_bwd(near, far, bg, noise_tensor, saved, g_rgb, None, g_alpha, g_w)
                 ops.ngp_backward(scene, l_xc, l_ds, l_dc, l_count, g_enc, g_col, GRAD_SCALE)
             if reg is not None and self.is_refine:  # DNeRF.py:139: the regulariser is dropped when refining poses
@@ -174,8 +184,9 @@ class DNeRFModel(torch.nn.Module):
             self.scaler.scale(loss).backward()
         if self.world_size > 1:
             import torch.distributed as dist
-            for g in self.net_coarse.grad_buffers():
-                dist.all_reduce(g)
+            if not self.network_frozen:
+                for g in self.net_coarse.grad_buffers():
+                    dist.all_reduce(g)
         pose_grads = [p.grad for g in self.pose_optimizer.param_groups for p in g["params"] if p.grad is not None] \
             if self.pose_optimizer is not None else []
         if pose_grads:
@@ -185,7 +196,8 @@ class DNeRFModel(torch.nn.Module):
             # GradScaler.unscale_ of the pose group; an overflow anywhere skips the whole step as in scaler.step()
             torch._amp_foreach_non_finite_check_and_unscale_(pose_grads, self.scaler.found_inf,
                                                              (1.0 / (self.scaler.scale_t * self.world_size)).float())
-        self.optimizer.step(self.scaler, self.world_size)
+        if not self.network_frozen:
+            self.optimizer.step(self.scaler, self.world_size)
         if pose_grads and float(self.scaler.found_inf.item()) == 0.0:
             self.pose_optimizer.step()
         self.scaler.update()

@@ -111,10 +111,14 @@ class NeRFNGPNet(nn.Module):
         return self._table_h, self._mlp_h
 
     def forward(self, x, d=None, cond=None):
-        """ngp.py:73-83: canonical points -> (rgb [P,3] f32, sigma [P] f32).  Inference path (the training
-        gradient flows through the fused train kernels, see instantavatar_b200/autograd.py)."""
+        """ngp.py:73-83: canonical points -> (rgb [P,3] f32, sigma [P] f32).  The fused train kernels bypass this entry
+        (instantavatar_b200/autograd.py); called directly it is differentiable w.r.t. the parameters and the points."""
         table_h, mlp_h = self.half_params()
         sc = ops.Scene(table_h=table_h, mlp_h=mlp_h, net_center=self.center.reshape(3).contiguous().float(),
                        net_scale=self.scale.reshape(3).contiguous().float())
+        if torch.is_grad_enabled() and (x.requires_grad or self.encoder.params.requires_grad):
+            from ...autograd import _NGPForward
+            accum = self.grad_buffers() if self.encoder.params.requires_grad else None
+            return _NGPForward.apply(x, self.encoder.params, self.color_net.params, sc, accum)
         rgb, sigma = ops.ngp_forward(sc, x.reshape(-1, 3).float().contiguous())
         return rgb, sigma

@@ -350,3 +350,12 @@ def voxelize_weights(verts, vert_weights, xs, ys, zs, offset, scale, ratio, knn=
                                     ptr(scale.reshape(1).contiguous(), f32), C.c_float(ratio), C.c_int(knn), C.c_int(smooth_passes),
                                     ptr(out), ptr(scratch), stream()))
     return out
+
+
+def ngp_input_grad(scene: Scene, x, denc):
+    """d loss / d x of NeRFNGPNet.forward from d loss / d (hash features)"""
+    x = x.reshape(-1, 3).contiguous()
+    dx = torch.empty_like(x, dtype=f32)
+    s = scene.c_struct()
+    _lib.count(1); check(lib().ia_ngp_input_grad(C.byref(s), ptr(x, f32), ptr(denc, f32), C.c_int(x.shape[0]), ptr(dx), stream()))
+    return dx

@@ -193,10 +193,11 @@ def test_pose_refinement_reduces_pose_error():
         delta[0, 3 * j + 2] = ang
     pose0["body_pose"] = true_pose + delta
     model.enable_pose_optimisation(pose0, lr=3e-3, is_refine=True)
+    model.freeze_network()              # eval.py:67-70: only the SMPL parameters are optimised
+    enc_before = model.net_coarse.encoder.params.detach().clone()
     model.global_step = 0
     errs, losses = [], []
     for step in range(120):
-        model.optimizer.state_t[0:1].fill_(0.0)  # network frozen: only the pose moves
         pick = sel[torch.randint(0, len(sel), (2048,), device="cuda")]
         b = _ray_batch(batch, pick, rgb_gt, alpha_gt, step)
         out = model.training_step(b)
@@ -206,5 +207,55 @@ def test_pose_refinement_reduces_pose_error():
     print("pose error", errs[0], "->", errs[-1], "loss", np.mean(losses[:10]), "->", np.mean(losses[-10:]))
     assert all(np.isfinite(losses)) and all(np.isfinite(errs))
     assert errs[-1] < 0.6 * errs[0], (errs[0], errs[-1], losses[:3], losses[-3:])
+    assert torch.equal(model.net_coarse.encoder.params.detach(), enc_before)   # the frozen network did not move
     # (the mini-batch loss itself is not asserted on: with 2048 random rays and per-pixel random backgrounds its step-to-
     # step noise exceeds the effect of the pose correction, and the unperturbed joints random-walk under Adam)
+
+
+def test_network_forward_is_differentiable_wrt_parameters_and_points():
+    """NeRFNGPNet.forward called directly (custom deformers, SMPLDeformer's `model(pts_cano)`): autograd through
+    ia_ngp_backward / ia_ngp_input_grad against the plain-PyTorch fp32 reference"""
+    import torch
+    from instantavatar_b200.models.networks.ngp import NeRFNGPNet
+    sc = scene_util.oracle_scene(0)
+    net_o = sc["net"]
+    rng = np.random.default_rng(21)
+    v = sc["subj"].verts_cano
+    n = 1500
+    x = (v[rng.integers(0, len(v), n)] * 0.95 + rng.normal(0, 0.01, (n, 3))).astype(np.float32)
+    g_s = (rng.normal(0, 1, n) * 1e-3).astype(np.float32); g_c = (rng.normal(0, 1, (n, 3)) * 1e-2).astype(np.float32)
+    # reference
+    enc = torch.from_numpy(net_o.enc).requires_grad_(True); col = torch.from_numpy(net_o.col).requires_grad_(True)
+    xr = torch.from_numpy(x).requires_grad_(True)
+    s, c = torch_ref.ngp_forward(xr, net_o.center, net_o.scale, enc, col, True, pos_grad=True)
+    ((s * torch.from_numpy(g_s)).sum() + (c * torch.from_numpy(g_c)).sum()).backward()
+    # product
+    net = NeRFNGPNet(None).cuda()
+    net.center = torch.from_numpy(np.asarray(net_o.center, np.float32)).cuda(); net.scale = torch.from_numpy(np.asarray(net_o.scale, np.float32)).cuda()
+    net.bbox = True  # normalisation already set
+    net.load_flat_params(torch.from_numpy(net_o.enc).cuda(), torch.from_numpy(net_o.col).cuda())
+    xg = torch.from_numpy(x).cuda().requires_grad_(True)
+    rgb, sigma = net(xg)
+    assert rgb.requires_grad and sigma.requires_grad
+    ((sigma * torch.from_numpy(g_s).cuda()).sum() + (rgb * torch.from_numpy(g_c).cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    assert np.abs(sigma.detach().cpu().numpy() - s.detach().numpy()).max() < 2e-2 * max(1.0, np.abs(s.detach().numpy()).max())
+    dx, dx_ref = xg.grad.cpu().numpy(), xr.grad.numpy()
+    assert np.linalg.norm(dx_ref) > 0
+    assert rel_err(dx, dx_ref) < 5e-2, rel_err(dx, dx_ref)
+    g_enc = net.encoder.params.grad.cpu().numpy(); g_col = net.color_net.params.grad.cpu().numpy()
+    assert rel_err(g_col, col.grad.numpy()) < 2e-2
+    assert rel_err(g_enc[3072:], enc.grad.numpy()[3072:]) < 2e-2
+    # frozen parameters: only the input gradient is produced
+    net.zero_grad(set_to_none=True)
+    for p_ in net.parameters():
+        p_.requires_grad_(False)
+    xg2 = torch.from_numpy(x).cuda().requires_grad_(True)
+    rgb2, sigma2 = net(xg2)
+    ((sigma2 * torch.from_numpy(g_s).cuda()).sum() + (rgb2 * torch.from_numpy(g_c).cuda()).sum()).backward()
+    np.testing.assert_allclose(xg2.grad.cpu().numpy(), dx, rtol=1e-5, atol=1e-9)
+    assert net.encoder.params.grad is None
+    # no_grad: plain inference
+    with torch.no_grad():
+        r3, s3 = net(torch.from_numpy(x).cuda())
+    assert not r3.requires_grad and torch.equal(s3, sigma.detach())

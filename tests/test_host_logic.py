@@ -1,0 +1,67 @@
+"""CPU: host-side mirror classes that need no GPU -- losses and the SMPL parameter embedding
+(instant_avatar/utils/loss.py, models/structures/body_model_param.py)."""
+import numpy as np
+import pytest
+import torch
+
+from instantavatar_b200.models.structures.body_model_param import SMPLParamEmbedding
+from instantavatar_b200.utils_loss import NeRFLoss, NGPLoss
+from oracle import torch_ref
+
+
+def _predictions(shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    p = {"rgb_coarse": torch.rand(*shape, 3, generator=g), "alpha_coarse": torch.rand(*shape, generator=g),
+         "depth_coarse": torch.rand(*shape, generator=g) * 3, "weight_coarse": torch.rand(*shape, 16, generator=g) * 0.2}
+    t = {"rgb": torch.rand(*shape, 3, generator=g), "alpha": (torch.rand(*shape, generator=g) > 0.4).float()}
+    return p, t
+
+
+def test_nerf_loss_matches_oracle_restatement():
+    p, t = _predictions((1, 512))
+    got = NeRFLoss()(p, t)["loss"]
+    ref = torch_ref.nerf_loss(p["rgb_coarse"], p["alpha_coarse"], p["weight_coarse"], t["rgb"], t["alpha"])
+    assert abs(got.item() - ref.item()) < 1e-6
+
+
+def test_ngp_loss_reduces_to_nerf_loss_and_adds_depth_term_on_patches():
+    p, t = _predictions((1, 4, 8, 8))
+    base = NeRFLoss()(p, t)["loss"]
+    assert abs(NGPLoss()(p, t)["loss"].item() - base.item()) < 1e-6      # SNARF_NGP_refine.yaml weights
+    out = NGPLoss(w_depth_reg=0.01)(p, t)
+    a, d = p["alpha_coarse"], p["depth_coarse"]
+    avg = (d * a).sum(dim=(-1, -2)) / (a.sum(dim=(-1, -2)) + 1e-3)
+    expect = (a * (d - avg[..., None, None]).abs()).mean()
+    assert abs(out["loss_depth_reg"].item() - expect.item()) < 1e-7
+    assert abs(out["loss"].item() - (base + 0.01 * expect).item()) < 1e-6
+    # per-ray (non-patch) predictions skip the patch terms, as in the reference
+    p1, t1 = _predictions((1, 256))
+    assert "loss_depth_reg" not in NGPLoss(w_depth_reg=0.01)(p1, t1)
+    with pytest.raises(RuntimeError):
+        NGPLoss(w_lpips=0.01)
+    stub = lambda x, y: (x - y).abs().mean(dim=(1, 2, 3))
+    out = NGPLoss(w_lpips=0.5, lpips=stub)(p, t)
+    assert out["loss_lpips"].item() > 0 and out["loss"].item() > base.item()
+
+
+def test_smpl_param_embedding_lookup_and_tv_loss():
+    F_ = 5
+    g = torch.Generator().manual_seed(1)
+    init = {"betas": torch.rand(1, 10, generator=g), "global_orient": torch.rand(F_, 3, generator=g),
+            "body_pose": torch.rand(F_, 69, generator=g), "transl": torch.rand(F_, 3, generator=g)}
+    emb = SMPLParamEmbedding(**init)
+    idx = torch.tensor([3])
+    out = emb(idx)
+    assert out["betas"].shape == (1, 10) and torch.equal(out["betas"], init["betas"])
+    for k in ("global_orient", "body_pose", "transl"):
+        assert torch.equal(out[k], init[k][3:4])
+        assert getattr(emb, k).weight.requires_grad
+    # temporal smoothness: squared differences to both neighbours, clamped at the ends
+    expect = sum(((init[k][3] - init[k][2]) ** 2).mean() + ((init[k][4] - init[k][3]) ** 2).mean()
+                 for k in ("global_orient", "body_pose", "transl"))
+    assert abs(emb.tv_loss(idx).item() - expect.item()) < 1e-6
+    end = torch.tensor([F_ - 1])
+    expect_end = sum(((init[k][F_ - 1] - init[k][F_ - 2]) ** 2).mean() for k in ("global_orient", "body_pose", "transl"))
+    assert abs(emb.tv_loss(end).item() - expect_end.item()) < 1e-6
+    out["body_pose"].sum().backward()
+    assert emb.body_pose.weight.grad[3].abs().sum() > 0 and emb.body_pose.weight.grad[0].abs().sum() == 0
