@@ -305,6 +305,65 @@ def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, u
             "scaling": "strong"}
 
 
+def bench_next_rows(model, batch, device, steps=20, warmup=5):
+    """SURVEY.md 8f rows 3 and 4, measured like the hot path (CUDA events after warm-up): one pose-refinement step
+    (frozen network, SMPL parameters optimised through ia_pose_grad; eval.py / SNARF_NGP_refine.yaml) on 4096 rays, and
+    the once-per-subject skinning-weight voxelisation (ia_voxelize_weights, 524 288 voxels x 6890 vertices, K = 30)."""
+    import torch
+    from instantavatar_b200 import ops
+    out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- f4: voxelisation ----
+    d = model.deformer
+    fd = d.deformer
+    dd, hh, ww = fd.lbs_voxel_final.shape[-3:]
+    lin = lambda n: torch.linspace(-1, 1, steps=n, device=device)
+    args_v = (d.vs_template[0].float(), d.body_model.lbs_weights.float(), lin(ww), lin(hh), lin(dd), fd.offset.reshape(3).float(),
+              fd.scale.reshape(1).float(), float(fd.ratio))
+    ops.voxelize_weights(*args_v)
+    torch.cuda.synchronize()
+    ev0.record(); ops.voxelize_weights(*args_v); ev1.record()
+    torch.cuda.synchronize()
+    out["voxelize_weights_ms"] = ev0.elapsed_time(ev1)
+    # ---- f3: pose refinement step ----
+    model.eval()
+    rgb_gt, _, alpha_gt, _ = model.render_image_fast(dict(batch), (H, W))
+    rgb_gt, alpha_gt = rgb_gt.reshape(-1, 3), alpha_gt.reshape(-1)
+    idx = []
+    for (y0, x0) in ((150, 240), (200, 232), (250, 236), (300, 240)):
+        ys, xs = torch.arange(y0, y0 + 32), torch.arange(x0, x0 + 32)
+        idx.append((ys[:, None] * W + xs[None]).reshape(-1))
+    pick = torch.cat(idx).to(device)
+    b = dict(batch)
+    for k in ("rays_o", "rays_d", "near", "far"):
+        b[k] = batch[k][:, pick].contiguous()
+    a = alpha_gt[pick][None]
+    b["bg_color"] = torch.rand((1, len(pick), 3), device=device)
+    b["alpha"] = a
+    b["rgb"] = rgb_gt[pick][None] - (1 - a[..., None]) + (1 - a[..., None]) * b["bg_color"]
+    b["idx"] = torch.zeros(1, dtype=torch.long, device=device)
+    world_before = model.world_size
+    model.world_size = 1
+    model.enable_pose_optimisation({k: batch[k].clone() for k in ("betas", "global_orient", "body_pose", "transl")}, lr=1e-5, is_refine=True)
+    model.freeze_network()
+    model.global_step = 2000
+    for _ in range(warmup):
+        model.training_step(b)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        model.training_step(b)
+    ev1.record()
+    torch.cuda.synchronize()
+    out["pose_refine"] = {"ms_per_step": ev0.elapsed_time(ev1) / steps, "rays_per_step": int(len(pick)), "steps": steps, "cuda_graph": False,
+                          "what": "frozen network; torch SMPL forward/backward (eager launches) + train_fwd + loss + composite_bwd + "
+                                  "ngp_backward (features only) + pose_grad + device Adam on the pose tables; grid refresh amortised"}
+    model.freeze_network(False)
+    model.SMPL_param, model.pose_optimizer, model.is_refine = None, None, False
+    model.world_size = world_before
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -427,6 +486,12 @@ def run_ours(args):
     sharded = bench_frame_sharded(model, batch, device, rank, world, flush) if world > 1 else None
     ref_struct = bench_ref_structure(model, batch, device) if rank == 0 else None
     train = bench_train(model, batch, device, rank, world, flush, use_graph=use_graph)
+    next_rows = None
+    if rank == 0:
+        try:
+            next_rows = bench_next_rows(model, batch, device)
+        except Exception as exc:  # reported, never fatal for the headline numbers
+            next_rows = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank != 0:
         if world > 1:
@@ -465,6 +530,7 @@ def run_ours(args):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
         "train": train,
+        "next_rows": next_rows,
         "ref_structure": ref_struct,
         "frame_sharded": sharded,
         "roofline": {"kernel": "render_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -736,6 +736,24 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float4* __restrict__ p, f
     }
 }
 
+// the last n % 4 elements of a tensor whose length is not a multiple of 4 (small pose tables); same update as above
+__global__ void adam_dev_tail_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int n,
+                                     const float* __restrict__ state, const float* __restrict__ found_inf) {
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    const float gr = g[i];
+    g[i] = 0.f;
+    if (found_inf && *found_inf != 0.f) return;
+    const float lr = state[0], beta1 = state[1], beta2 = state[2], eps = state[3], bc1 = state[5], bc2_sqrt = state[6], inv = state[7];
+    const float gi = gr * inv;
+    const float mm = __fmaf_rn(beta1, m[i], (1.f - beta1) * gi);
+    const float vv = __fmaf_rn(beta2, v[i], (1.f - beta2) * gi * gi);
+    float sq;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(vv));
+    m[i] = mm; v[i] = vv;
+    p[i] = __fmaf_rn(-(lr / bc1), __fdividef(mm, __fmaf_rn(sq, 1.0f / bc2_sqrt, eps)), p[i]);
+}
+
 __global__ void grad_finite_kernel(const float* __restrict__ g, long n, float* __restrict__ found_inf) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     bool bad = false;
@@ -1058,11 +1076,18 @@ int ia_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg
     IA_REQUIRE(n >= 0);
     if (n == 0) return IA_OK;
     IA_REQUIRE(params && grads && exp_avg && exp_avg_sq && state);
-    IA_REQUIRE(n % 4 == 0 && half_skip % 4 == 0);
+    IA_REQUIRE(half_skip % 4 == 0 && (n % 4 == 0 || !half_out));
+    IA_REQUIRE((reinterpret_cast<size_t>(params) | reinterpret_cast<size_t>(grads) | reinterpret_cast<size_t>(exp_avg) |
+                reinterpret_cast<size_t>(exp_avg_sq)) % 16 == 0);
     const long n4 = n / 4;
-    adam_dev_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<float4*>(params), reinterpret_cast<float4*>(grads), reinterpret_cast<float4*>(exp_avg),
-        reinterpret_cast<float4*>(exp_avg_sq), n4, state, found_inf, reinterpret_cast<__half2*>(half_out), half_skip / 4);
+    const int rem = (int)(n % 4);
+    if (n4 > 0)
+        adam_dev_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<float4*>(params), reinterpret_cast<float4*>(grads), reinterpret_cast<float4*>(exp_avg),
+            reinterpret_cast<float4*>(exp_avg_sq), n4, state, found_inf, reinterpret_cast<__half2*>(half_out), half_skip / 4);
+    if (rem)
+        adam_dev_tail_kernel<<<1, 4, 0, (cudaStream_t)stream>>>(params + n4 * 4, grads + n4 * 4, exp_avg + n4 * 4, exp_avg_sq + n4 * 4,
+                                                               rem, state, found_inf);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

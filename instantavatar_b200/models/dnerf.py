@@ -53,7 +53,8 @@ class DNeRFModel(torch.nn.Module):
         dev = self.net_coarse.encoder.params.device
         self.SMPL_param = SMPLParamEmbedding(**{k: torch.as_tensor(v) for k, v in smpl_params.items()}).to(dev)
         group = [p for n, p in self.SMPL_param.named_parameters() if not n.startswith("betas")]
-        self.pose_optimizer = torch.optim.Adam(group, lr=lr, betas=(0.9, 0.99), eps=1e-15)
+        from ..optim import DeviceAdam
+        self.pose_optimizer = DeviceAdam(group, lr=lr, betas=(0.9, 0.99), eps=1e-15)
         self.is_refine = is_refine
 
     def freeze_network(self, frozen: bool = True):
@@ -129,7 +130,7 @@ class DNeRFModel(torch.nn.Module):
             cam_dist = torch.norm(batch["transl"], dim=-1, keepdim=True).detach()
             batch["near"] = torch.zeros_like(batch["near"]) + cam_dist - 1
             batch["far"] = torch.zeros_like(batch["far"]) + cam_dist + 1
-            self.pose_optimizer.zero_grad(set_to_none=True)
+            self.pose_optimizer.zero_grad()
         self.deformer.prepare_deformer(batch)
         self.net_coarse.initialize(self.deformer.bbox)
         g_enc, g_col = self.net_coarse.grad_buffers()  # zeroed at creation and by every fused optimiser step
@@ -187,19 +188,17 @@ class DNeRFModel(torch.nn.Module):
             if not self.network_frozen:
                 for g in self.net_coarse.grad_buffers():
                     dist.all_reduce(g)
-        pose_grads = [p.grad for g in self.pose_optimizer.param_groups for p in g["params"] if p.grad is not None] \
-            if self.pose_optimizer is not None else []
+        pose_grads = self.pose_optimizer.grads() if self.pose_optimizer is not None else []
         if pose_grads:
             if self.world_size > 1:
                 for g in pose_grads:
                     dist.all_reduce(g)
-            # GradScaler.unscale_ of the pose group; an overflow anywhere skips the whole step as in scaler.step()
-            torch._amp_foreach_non_finite_check_and_unscale_(pose_grads, self.scaler.found_inf,
-                                                             (1.0 / (self.scaler.scale_t * self.world_size)).float())
+            # an overflow in any group skips the whole step, as GradScaler.step() does for the reference's single optimizer
+            self.pose_optimizer.check_finite(self.scaler)
         if not self.network_frozen:
             self.optimizer.step(self.scaler, self.world_size)
-        if pose_grads and float(self.scaler.found_inf.item()) == 0.0:
-            self.pose_optimizer.step()
+        if pose_grads:
+            self.pose_optimizer.step(self.scaler, self.world_size)
         self.scaler.update()
         self.global_step += 1
         return losses

@@ -73,3 +73,36 @@ class FusedAdam:
         ops.adam_step_dev(self.params[1].data, g_col, m1, v1, self.state_t, found, None, 0)
         ops.mlp_to_half(self.params[0].data, self.params[1].data, mlp_h)
         self.net.mark_clean()
+
+
+class DeviceAdam:
+    """torch.optim.Adam semantics for a short list of small dense tensors (the SMPL pose embeddings, DNeRF.py:40-51)
+    on the same device-state kernels as FusedAdam: step count, bias corrections and the GradScaler's 1/scale live in an
+    8-float device tensor and an overflow skips the step on the device -- no host read-back, capturable in a CUDA graph."""
+
+    def __init__(self, params, lr=5e-4, betas=(0.9, 0.99), eps=1e-15):
+        self.params = [p for p in params]
+        self.state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in self.params]
+        dev = self.params[0].device
+        self.state_t = torch.tensor([lr, betas[0], betas[1], eps, 0.0, 1.0, 1.0, 1.0], dtype=torch.float32).to(dev)
+        self.param_groups = [{"params": self.params, "lr": lr}]
+
+    def zero_grad(self, set_to_none=False):
+        for p in self.params:
+            if p.grad is not None:
+                p.grad.zero_()
+
+    def grads(self):
+        return [p.grad for p in self.params if p.grad is not None]
+
+    def check_finite(self, scaler: GradScaler):
+        for g in self.grads():
+            ops.grad_check_finite(g, scaler.found_inf)
+
+    def step(self, scaler: GradScaler | None = None, world_size: int = 1):
+        found = scaler.found_inf if scaler is not None else None
+        ops.adam_prepare(self.state_t, 1.0 / world_size, scaler.scale_t if scaler is not None else None, found)
+        for p, (m, v) in zip(self.params, self.state):
+            if p.grad is None:
+                continue
+            ops.adam_step_dev(p.data, p.grad, m, v, self.state_t, found, None, 0)

@@ -114,8 +114,21 @@ def test_pose_gradients_fused_and_autograd_paths_agree():
         b = _ray_batch(batch, sel[:1024], rgb_gt, alpha_gt, 0)
         jitter = torch.rand((1024, 256), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
         gj = torch.rand((64, 64, 64, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+        snap = {}
+        check = model.pose_optimizer.check_finite   # the fused optimiser step zeroes the gradients: snapshot them before it
+        def spy(scaler, check=check, snap=snap):
+            snap.update({k: getattr(model.SMPL_param, k).weight.grad.clone() for k in ("global_orient", "body_pose", "transl")})
+            return check(scaler)
+        model.pose_optimizer.check_finite = spy
+        before = model.SMPL_param.body_pose.weight.detach().clone()
         model.training_step(b, jitter=jitter, noise_tensor=torch.zeros((1024, 256), device="cuda"), grid_jitter=gj)
-        grads.append({k: getattr(model.SMPL_param, k).weight.grad.clone() for k in ("global_orient", "body_pose", "transl")})
+        grads.append(snap)
+        # one Adam step of size lr in the direction of -sign(grad) (first step: m/sqrt(v) = sign), gradients zeroed
+        moved = (model.SMPL_param.body_pose.weight.detach() - before)[0]
+        gsel = snap["body_pose"][0].abs() > 1e-3 * snap["body_pose"][0].abs().max()
+        assert torch.equal(torch.sign(moved[gsel]), -torch.sign(snap["body_pose"][0][gsel]))
+        assert (moved.abs().max() - 5e-4).abs() < 5e-5
+        assert model.SMPL_param.body_pose.weight.grad.abs().max() == 0
     for k in grads[0]:
         a, b_ = grads[0][k].cpu().numpy(), grads[1][k].cpu().numpy()
         if k != "body_pose":
