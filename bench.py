@@ -347,17 +347,30 @@ def bench_next_rows(model, batch, device, steps=20, warmup=5):
     model.enable_pose_optimisation({k: batch[k].clone() for k in ("betas", "global_orient", "body_pose", "transl")}, lr=1e-5, is_refine=True)
     model.freeze_network()
     model.global_step = 2000
-    for _ in range(warmup):
-        model.training_step(b)
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(steps):
-        model.training_step(b)
-    ev1.record()
-    torch.cuda.synchronize()
-    out["pose_refine"] = {"ms_per_step": ev0.elapsed_time(ev1) / steps, "rays_per_step": int(len(pick)), "steps": steps, "cuda_graph": False,
-                          "what": "frozen network; torch SMPL forward/backward (eager launches) + train_fwd + loss + composite_bwd + "
-                                  "ngp_backward (features only) + pose_grad + device Adam on the pose tables; grid refresh amortised"}
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / steps
+
+    eager_ms = timed(lambda: model.training_step(b))
+    graph_ms = None
+    try:  # the refinement step is sync-free (device-state Adam, fused bone-transform backward): capture and replay it
+        from instantavatar_b200.graphs import GraphedTrainStep
+        model.global_step = 2001
+        graphed = GraphedTrainStep(model, b)
+        graph_ms = timed(lambda: graphed())
+    except Exception as exc:
+        print(f"[bench] pose-refinement graph capture failed ({type(exc).__name__}: {exc}), eager number only", file=sys.stderr)
+    out["pose_refine"] = {"ms_per_step": graph_ms if graph_ms is not None else eager_ms, "ms_per_step_eager": eager_ms,
+                          "rays_per_step": int(len(pick)), "steps": steps, "cuda_graph": graph_ms is not None,
+                          "what": "frozen network: fused bone transforms (+ reverse mode), train_fwd, loss, composite_bwd, ngp_backward "
+                                  "(features only), pose_grad, device Adam on the pose tables; grid refresh amortised"}
     model.freeze_network(False)
     model.SMPL_param, model.pose_optimizer, model.is_refine = None, None, False
     model.world_size = world_before

@@ -95,6 +95,14 @@ int ia_voxelize_weights(const float* verts, const float* vert_weights, int n_ver
 int ia_smpl_tfs(const float* global_orient, const float* body_pose, const float* transl, const float* joints,
                 const int* parents, const float* tfs_inv_t, float* tfs, float* w2s, float* A_out, ia_stream_t stream);
 
+/* Reverse mode of ia_smpl_tfs for pose optimisation (what autograd computes through smplx/lbs.py:295-329,345-401 and
+ * snarf_deformer.py:84-86): grad_tfs [24][4][4] -> grad_orient [3] (nullable), grad_pose [69], grad_transl [3]
+ * (nullable).  Values are written, not accumulated.  tfs is relative to the root, so grad_orient / grad_transl come out
+ * as the fp32 residue of an exact cancellation -- as they do in the reference. */
+int ia_smpl_tfs_backward(const float* global_orient, const float* body_pose, const float* transl, const float* joints,
+                         const int* parents, const float* tfs_inv_t, const float* grad_tfs, float* grad_orient,
+                         float* grad_pose, float* grad_transl, ia_stream_t stream);
+
 /* fp32 master parameters -> fp16 working copies (tiny-cuda-nn casts params to fp16 every forward).
  * enc_params [3072 + 2*total] = [W1 64x32 | W2 16x64 | grid]; col_params [6144] = [W3 64x16 | W4 64x64 | W5 16x64]
  * (models/networks/ngp.py:27-57 `encoder.params`, `color_net.params`). */

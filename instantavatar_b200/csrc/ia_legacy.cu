@@ -215,6 +215,170 @@ __global__ void __launch_bounds__(32) smpl_tfs_kernel(const float* __restrict__ 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// reverse mode of smpl_tfs_kernel: d loss / d (global_orient, body_pose, transl) from d loss / d tfs (pose optimisation,
+// DNeRF.py:113-127: what torch autograd computes through smplx's batch_rodrigues / batch_rigid_transform and the tfs
+// algebra of snarf_deformer.py:84-86).  The forward intermediates are recomputed (24 joints); one warp.
+//   tfs_j = W A_j Tinv_j,  W = A_0^-1 = [R0^T | -R0^T t0],  A_j = [C_j.R | C_j.t - C_j.R J_j + transl],
+//   C_j = C_parent(j) L_j,  L_j = [R(theta_j) | J_j - J_parent(j)],  R = I + sin(a) K + (1 - cos(a)) K^2.
+// Only the top 3x4 blocks carry gradient (the bottom rows are constant).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) smpl_tfs_bwd_kernel(const float* __restrict__ global_orient, const float* __restrict__ body_pose,
+                                                          const float* __restrict__ transl, const float* __restrict__ J,
+                                                          const int* __restrict__ parents, const float* __restrict__ tfs_inv_t,
+                                                          const float* __restrict__ g_tfs, float* __restrict__ g_orient,
+                                                          float* __restrict__ g_pose, float* __restrict__ g_transl) {
+    __shared__ float tm[24][16], chain[24][16], A[24][16], w2s[16];
+    __shared__ float gA[24][12], gC[24][12], gW[12], gL[24][9];
+    const int j = threadIdx.x;
+    // ---- forward recomputation (identical expressions to smpl_tfs_kernel) ----
+    float rr[3] = {0.f, 0.f, 0.f}, angle = 1.f;
+    if (j < 24) {
+        const float* r = j == 0 ? global_orient : body_pose + (j - 1) * 3;
+        rr[0] = r[0]; rr[1] = r[1]; rr[2] = r[2];
+        const float ax = r[0] + 1e-8f, ay = r[1] + 1e-8f, az = r[2] + 1e-8f;
+        angle = sqrtf(ax * ax + ay * ay + az * az);
+        const float rx = r[0] / angle, ry = r[1] / angle, rz = r[2] / angle;
+        const float s = sinf(angle), c = 1.f - cosf(angle);
+        const float K[9] = {0.f, -rz, ry, rz, 0.f, -rx, -ry, rx, 0.f};
+        float K2[9];
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) K2[a * 3 + b] = K[a * 3] * K[b] + K[a * 3 + 1] * K[3 + b] + K[a * 3 + 2] * K[6 + b];
+        const int p = parents[j];
+        for (int a = 0; a < 3; a++) {
+            for (int b = 0; b < 3; b++) tm[j][a * 4 + b] = (a == b ? 1.f : 0.f) + s * K[a * 3 + b] + c * K2[a * 3 + b];
+            tm[j][a * 4 + 3] = J[j * 3 + a] - (j > 0 ? J[p * 3 + a] : 0.f);
+        }
+        tm[j][12] = tm[j][13] = tm[j][14] = 0.f; tm[j][15] = 1.f;
+    }
+    __syncwarp();
+    if (j == 0) {
+        for (int e = 0; e < 16; e++) chain[0][e] = tm[0][e];
+        for (int i = 1; i < 24; i++) mat4_mul(chain[parents[i]], tm[i], chain[i]);
+    }
+    __syncwarp();
+    if (j < 24) {
+        for (int e = 0; e < 16; e++) A[j][e] = chain[j][e];
+        for (int a = 0; a < 3; a++) {
+            const float tj = chain[j][a * 4] * J[j * 3] + chain[j][a * 4 + 1] * J[j * 3 + 1] + chain[j][a * 4 + 2] * J[j * 3 + 2];
+            A[j][a * 4 + 3] = chain[j][a * 4 + 3] - tj + (transl ? transl[a] : 0.f);
+        }
+    }
+    __syncwarp();
+    if (j == 0) {
+        for (int a = 0; a < 3; a++) {
+            for (int b = 0; b < 3; b++) w2s[a * 4 + b] = A[0][b * 4 + a];
+            w2s[a * 4 + 3] = -(A[0][a] * A[0][3] + A[0][4 + a] * A[0][7] + A[0][8 + a] * A[0][11]);
+        }
+        w2s[12] = w2s[13] = w2s[14] = 0.f; w2s[15] = 1.f;
+        for (int e = 0; e < 12; e++) gW[e] = 0.f;
+    }
+    __syncwarp();
+    // ---- tfs_j = (W A_j) Tinv_j : gM = g_tfs Tinv^T (top 3 rows), gA_j = W^T gM (rotation part of W), gW += gM A_j^T ----
+    float gM[12];
+    if (j < 24) {
+        const float* Ti = tfs_inv_t + j * 16;
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 4; b++) {
+                float v = 0.f;
+                for (int k = 0; k < 4; k++) v += g_tfs[j * 16 + a * 4 + k] * Ti[b * 4 + k];
+                gM[a * 4 + b] = v;
+            }
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 4; b++) {
+                float v = 0.f;
+                for (int k = 0; k < 3; k++) v += w2s[k * 4 + a] * gM[k * 4 + b];
+                gA[j][a * 4 + b] = v;
+            }
+    }
+    // gW[a][b] = sum_j sum_k gM_j[a][k] A_j[b][k]  (b < 3: rows of A; b == 3: the constant row [0 0 0 1] -> gM[a][3])
+    for (int e = 0; e < 12; e++) {
+        const int a = e >> 2, b = e & 3;
+        float v = 0.f;
+        if (j < 24) {
+            if (b < 3) for (int k = 0; k < 4; k++) v += gM[a * 4 + k] * A[j][b * 4 + k];
+            else v = gM[a * 4 + 3];
+        }
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (j == 0) gW[e] = v;
+    }
+    __syncwarp();
+    if (j == 0) {
+        // W = [R0^T | -R0^T t0]  ->  gA_0.R += gW.R^T - t0 gW.t^T ;  gA_0.t += -R0 gW.t
+        const float t0[3] = {A[0][3], A[0][7], A[0][11]};
+        const float gt[3] = {gW[3], gW[7], gW[11]};
+        for (int a = 0; a < 3; a++) {
+            for (int b = 0; b < 3; b++) gA[0][a * 4 + b] += gW[b * 4 + a] - t0[a] * gt[b];
+            gA[0][a * 4 + 3] += -(A[0][a * 4] * gt[0] + A[0][a * 4 + 1] * gt[1] + A[0][a * 4 + 2] * gt[2]);
+        }
+    }
+    __syncwarp();
+    // ---- A_j = [C.R | C.t - C.R J_j + transl] ----
+    float gtr[3] = {0.f, 0.f, 0.f};
+    if (j < 24) {
+        for (int a = 0; a < 3; a++) {
+            for (int b = 0; b < 3; b++) gC[j][a * 4 + b] = gA[j][a * 4 + b] - gA[j][a * 4 + 3] * J[j * 3 + b];
+            gC[j][a * 4 + 3] = gA[j][a * 4 + 3];
+            gtr[a] = gA[j][a * 4 + 3];
+        }
+    }
+    for (int a = 0; a < 3; a++) {
+        float v = gtr[a];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (j == 0 && g_transl) g_transl[a] = transl ? v : 0.f;
+    }
+    __syncwarp();
+    // ---- chain, children before parents (parents[i] < i): C_i = C_p L_i ----
+    if (j == 0) {
+        for (int i = 23; i >= 1; i--) {
+            const int p = parents[i];
+            const float* Cp = chain[p]; const float* L = tm[i];
+            for (int a = 0; a < 3; a++) {
+                for (int b = 0; b < 3; b++) {
+                    // gL.R = Cp.R^T gC_i.R
+                    gL[i][a * 3 + b] = Cp[a] * gC[i][b] + Cp[4 + a] * gC[i][4 + b] + Cp[8 + a] * gC[i][8 + b];
+                    // gCp.R += gC_i.R L.R^T + gC_i.t L.t^T
+                    gC[p][a * 4 + b] += gC[i][a * 4] * L[b * 4] + gC[i][a * 4 + 1] * L[b * 4 + 1] + gC[i][a * 4 + 2] * L[b * 4 + 2]
+                                        + gC[i][a * 4 + 3] * L[b * 4 + 3];
+                }
+                gC[p][a * 4 + 3] += gC[i][a * 4 + 3];
+            }
+        }
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) gL[0][a * 3 + b] = gC[0][a * 4 + b];
+    }
+    __syncwarp();
+    // ---- Rodrigues: d R / d r_k, contracted with gL ----
+    if (j < 24) {
+        const float a3[3] = {rr[0] + 1e-8f, rr[1] + 1e-8f, rr[2] + 1e-8f};
+        const float th = angle, s = sinf(th), c = cosf(th);
+        const float n[3] = {rr[0] / th, rr[1] / th, rr[2] / th};
+        const float K[9] = {0.f, -n[2], n[1], n[2], 0.f, -n[0], -n[1], n[0], 0.f};
+        float K2[9];
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) K2[a * 3 + b] = K[a * 3] * K[b] + K[a * 3 + 1] * K[3 + b] + K[a * 3 + 2] * K[6 + b];
+        float out[3];
+        for (int k = 0; k < 3; k++) {
+            const float dth = a3[k] / th;
+            float dn[3];
+            for (int d = 0; d < 3; d++) dn[d] = (d == k ? 1.f / th : 0.f) - rr[d] * dth / (th * th);
+            const float dK[9] = {0.f, -dn[2], dn[1], dn[2], 0.f, -dn[0], -dn[1], dn[0], 0.f};
+            float acc = 0.f;
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) {
+                    float dKK = 0.f;  // dK K + K dK
+                    for (int m = 0; m < 3; m++) dKK += dK[a * 3 + m] * K[m * 3 + b] + K[a * 3 + m] * dK[m * 3 + b];
+                    const float dR = c * dth * K[a * 3 + b] + s * dK[a * 3 + b] + s * dth * K2[a * 3 + b] + (1.f - c) * dKK;
+                    acc += gL[j][a * 3 + b] * dR;
+                }
+            out[k] = acc;
+        }
+        float* dst = j == 0 ? g_orient : g_pose + (j - 1) * 3;
+        if (dst) { dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; }
+    }
+}
+
 }  // namespace
 
 extern "C" int ia_smpl_tfs(const float* global_orient, const float* body_pose, const float* transl, const float* joints,
@@ -222,6 +386,16 @@ extern "C" int ia_smpl_tfs(const float* global_orient, const float* body_pose, c
                            ia_stream_t stream) {
     IA_REQUIRE(global_orient && body_pose && joints && parents && tfs_inv_t && tfs && w2s);
     smpl_tfs_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(global_orient, body_pose, transl, joints, parents, tfs_inv_t, tfs, w2s, A_out);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+extern "C" int ia_smpl_tfs_backward(const float* global_orient, const float* body_pose, const float* transl, const float* joints,
+                                    const int* parents, const float* tfs_inv_t, const float* grad_tfs, float* grad_orient,
+                                    float* grad_pose, float* grad_transl, ia_stream_t stream) {
+    IA_REQUIRE(global_orient && body_pose && joints && parents && tfs_inv_t && grad_tfs && grad_pose);
+    smpl_tfs_bwd_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(global_orient, body_pose, transl, joints, parents, tfs_inv_t, grad_tfs,
+                                                            grad_orient, grad_pose, grad_transl);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

@@ -51,6 +51,26 @@ def get_bbox_from_smpl(vs, factor=1.2):
     return torch.cat([c - s[:, None], c + s[:, None]], dim=0)
 
 
+class _SmplTfs(torch.autograd.Function):
+    """bone transforms of one frame (ia_smpl_tfs) with the hand-written reverse mode (ia_smpl_tfs_backward): pose
+    optimisation differentiates Rodrigues + the kinematic chain + the tfs algebra in one launch instead of ~150
+    autograd nodes of the torch SMPL forward.  w2s is returned detached (the root search runs under no_grad in the
+    reference, so the ray transform carries no gradient to a consumer)."""
+
+    @staticmethod
+    def forward(ctx, global_orient, body_pose, transl, joints, parents_i32, tfs_inv_t):
+        tfs, w2s, _ = ops.smpl_tfs(global_orient, body_pose, transl, joints, parents_i32, tfs_inv_t)
+        ctx.save_for_backward(global_orient, body_pose, transl, joints, parents_i32, tfs_inv_t)
+        ctx.mark_non_differentiable(w2s)
+        return tfs, w2s
+
+    @staticmethod
+    def backward(ctx, g_tfs, _g_w2s):
+        global_orient, body_pose, transl, joints, parents_i32, tfs_inv_t = ctx.saved_tensors
+        g_o, g_p, g_t = ops.smpl_tfs_backward(global_orient, body_pose, transl, joints, parents_i32, tfs_inv_t, g_tfs.float())
+        return g_o.reshape(global_orient.shape), g_p.reshape(body_pose.shape), g_t.reshape(transl.shape), None, None, None
+
+
 class ForwardDeformer(torch.nn.Module):
     """deformers/fast_snarf/deformer_torch.py::ForwardDeformer -- state holder for the voxelised skinning field."""
 
@@ -141,10 +161,15 @@ class SNARFDeformer:
         if not self.initialized:
             self.initialize(smpl_params["betas"], device)
             self.initialized = True
-        if self.fast_prepare and smpl_params["body_pose"].shape[0] == 1 and not smpl_params["body_pose"].requires_grad:
+        if self.fast_prepare and smpl_params["body_pose"].shape[0] == 1:
             # one launch: Rodrigues + kinematic chain + w2s + tfs (vertices are not needed by the renderer)
-            self.tfs, self.w2s, _ = ops.smpl_tfs(smpl_params["global_orient"], smpl_params["body_pose"], smpl_params["transl"],
-                                                 self.joints_rest, self.parents_i32, self.tfs_inv_t)
+            needs_grad = torch.is_grad_enabled() and any(smpl_params[k].requires_grad for k in ("global_orient", "body_pose", "transl"))
+            if needs_grad:
+                self.tfs, self.w2s = _SmplTfs.apply(smpl_params["global_orient"], smpl_params["body_pose"], smpl_params["transl"],
+                                                    self.joints_rest, self.parents_i32, self.tfs_inv_t)
+            else:
+                self.tfs, self.w2s, _ = ops.smpl_tfs(smpl_params["global_orient"], smpl_params["body_pose"], smpl_params["transl"],
+                                                     self.joints_rest, self.parents_i32, self.tfs_inv_t)
             self.deformer.precompute(self.tfs)
             self.smpl_params = smpl_params
             self.smpl_outputs = None

@@ -359,3 +359,15 @@ def ngp_input_grad(scene: Scene, x, denc):
     s = scene.c_struct()
     _lib.count(1); check(lib().ia_ngp_input_grad(C.byref(s), ptr(x, f32), ptr(denc, f32), C.c_int(x.shape[0]), ptr(dx), stream()))
     return dx
+
+
+def smpl_tfs_backward(global_orient, body_pose, transl, joints, parents_i32, tfs_inv_t, grad_tfs):
+    """reverse mode of smpl_tfs -> (grad_global_orient [1,3], grad_body_pose [1,69], grad_transl [1,3])"""
+    dev = body_pose.device
+    g_o = torch.empty((1, 3), device=dev, dtype=f32); g_p = torch.empty((1, 69), device=dev, dtype=f32); g_t = torch.empty((1, 3), device=dev, dtype=f32)
+    _lib.count(1); check(lib().ia_smpl_tfs_backward(ptr(global_orient.reshape(-1).contiguous(), f32), ptr(body_pose.reshape(-1).contiguous(), f32),
+                                                    ptr(transl.reshape(-1).contiguous(), f32) if transl is not None else None,
+                                                    ptr(joints.reshape(-1).contiguous(), f32), ptr(parents_i32, torch.int32),
+                                                    ptr(tfs_inv_t.reshape(-1).contiguous(), f32), ptr(grad_tfs.reshape(-1).contiguous(), f32),
+                                                    ptr(g_o), ptr(g_p), ptr(g_t), stream()))
+    return g_o, g_p, g_t

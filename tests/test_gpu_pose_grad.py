@@ -272,3 +272,38 @@ def test_network_forward_is_differentiable_wrt_parameters_and_points():
     with torch.no_grad():
         r3, s3 = net(torch.from_numpy(x).cuda())
     assert not r3.requires_grad and torch.equal(s3, sigma.detach())
+
+
+def test_smpl_tfs_backward_matches_torch_autograd():
+    """ia_smpl_tfs_backward (Rodrigues + kinematic chain + tfs algebra, one launch) against torch autograd through the
+    full SMPL forward (the reference's path: smplx/lbs.py + snarf_deformer.py:79-86)"""
+    import torch
+    from test_gpu_model import make_model
+    model, batch, _ = make_model(0)
+    d = model.deformer
+    d.prepare_deformer(batch)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    G = torch.randn((1, 24, 4, 4), device="cuda", generator=g)
+    G[:, :, 3, :] = 0
+    grads = []
+    for fast in (True, False):
+        d.fast_prepare = fast
+        p = {k: batch[k].clone() for k in ("betas", "global_orient", "body_pose", "transl")}
+        p["body_pose"] = p["body_pose"] + 0.2 * torch.randn(p["body_pose"].shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+        p["body_pose"][0, 6:9] = 0.0   # a joint at the Rodrigues singularity (angle -> |1e-8|)
+        for k in ("global_orient", "body_pose", "transl"):
+            p[k].requires_grad_(True)
+        d.prepare_deformer(p)
+        assert d.tfs.requires_grad
+        (d.tfs * G).sum().backward()
+        grads.append({k: p[k].grad.clone() for k in ("global_orient", "body_pose", "transl")})
+        tfs_val = d.tfs.detach().clone()
+        grads[-1]["tfs"] = tfs_val
+    np.testing.assert_allclose(grads[0]["tfs"].cpu().numpy(), grads[1]["tfs"].cpu().numpy(), atol=5e-6)
+    a, b = grads[0]["body_pose"].cpu().numpy(), grads[1]["body_pose"].cpu().numpy()
+    assert np.linalg.norm(b) > 1.0
+    assert rel_err(a, b) < 1e-4, rel_err(a, b)
+    assert np.isfinite(a).all()
+    for k in ("global_orient", "transl"):   # exact cancellation (tfs is relative to the root): fp32 residue only
+        assert np.abs(grads[0][k].cpu().numpy()).max() < 1e-4 * np.abs(b).max()
+        assert np.abs(grads[1][k].cpu().numpy()).max() < 1e-4 * np.abs(b).max()
