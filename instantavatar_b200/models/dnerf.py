@@ -124,13 +124,20 @@ class DNeRFModel(torch.nn.Module):
         if self.SMPL_param is not None:  # DNeRF.py:113-127
             batch = dict(batch)
             idx = torch.as_tensor(batch.get("idx", 0), device=batch["rays_o"].device).reshape(-1)[:1].long()
-            body = self.SMPL_param(idx)
+            # steps whose only pose-dependent loss is the ray loss (all steps when refining, else those without the grid
+            # regulariser) run without an autograd graph: ia_pose_grad -> ia_smpl_tfs_backward -> index_add_ into the
+            # embedding gradients; the whole step is then a fixed launch sequence (CUDA-graph capturable)
+            manual_pose = self.fused_loss and self.deformer.fast_prepare and (self.is_refine or self.global_step % 20 != 0)
+            with torch.set_grad_enabled(not manual_pose):
+                body = self.SMPL_param(idx)
             for k in ("global_orient", "body_pose", "transl"):
                 batch[k] = body[k]
             cam_dist = torch.norm(batch["transl"], dim=-1, keepdim=True).detach()
             batch["near"] = torch.zeros_like(batch["near"]) + cam_dist - 1
             batch["far"] = torch.zeros_like(batch["far"]) + cam_dist + 1
             self.pose_optimizer.zero_grad()
+        else:
+            manual_pose = False
         self.deformer.prepare_deformer(batch)
         self.net_coarse.initialize(self.deformer.bbox)
         g_enc, g_col = self.net_coarse.grad_buffers()  # zeroed at creation and by every fused optimiser step
@@ -155,7 +162,7 @@ class DNeRFModel(torch.nn.Module):
                                                         self.loss_fn.w_reg, self.scaler.scale_t)
             from ..autograd import GRAD_SCALE
             tfs = self.deformer.tfs
-            if tfs.requires_grad:
+            if tfs.requires_grad or manual_pose:
                 # pose optimisation: d loss / d tfs by implicit differentiation of the roots (deformer_torch.py:50-67),
                 # handed to autograd at `tfs` so that the SMPL forward kinematics are differentiated by torch
                 l_xc, l_ds, l_dc, l_count, l_xd, l_best = ops.composite_bwd(near, far, bg, noise_tensor, saved, g_rgb, None, g_alpha, g_w,
@@ -165,7 +172,17 @@ class DNeRFModel(torch.nn.Module):
                 ops.ngp_backward(scene, l_xc, l_ds, l_dc, l_count, None if frozen else g_enc, None if frozen else g_col, GRAD_SCALE, denc)
                 g_tfs = torch.zeros((24, 4, 4), device=o.device, dtype=torch.float32)
                 ops.pose_grad(scene, self.deformer.deformer.lbs_voxel_final, l_xd, l_best, denc, l_count, g_tfs)
-                tfs.backward(g_tfs.reshape(tfs.shape), retain_graph=reg is not None)
+                if manual_pose:
+                    d_ = self.deformer
+                    grads = ops.smpl_tfs_backward(batch["global_orient"], batch["body_pose"], batch["transl"], d_.joints_rest,
+                                                  d_.parents_i32, d_.tfs_inv_t, g_tfs)
+                    for name, g in zip(("global_orient", "body_pose", "transl"), grads):
+                        w = getattr(self.SMPL_param, name).weight
+                        if w.grad is None:
+                            w.grad = torch.zeros_like(w)
+                        w.grad.index_add_(0, idx, g)
+                else:
+                    tfs.backward(g_tfs.reshape(tfs.shape), retain_graph=reg is not None)
             elif not self.network_frozen:
                 l_xc, l_ds, l_dc, l_count = ops.composite_bwd(near, far, bg, noise_tensor, saved, g_rgb, None, g_alpha, g_w)
                 ops.ngp_backward(scene, l_xc, l_ds, l_dc, l_count, g_enc, g_col, GRAD_SCALE)
