@@ -347,7 +347,7 @@ def bench_next_rows(model, batch, device, steps=20, warmup=5):
     model.enable_pose_optimisation({k: batch[k].clone() for k in ("betas", "global_orient", "body_pose", "transl")}, lr=1e-5, is_refine=True)
     model.freeze_network()
     model.global_step = 2000
-    def timed(fn):
+    def timed(fn, warmup, steps):
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
@@ -358,17 +358,17 @@ def bench_next_rows(model, batch, device, steps=20, warmup=5):
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / steps
 
-    eager_ms = timed(lambda: model.training_step(b))
+    eager_ms = timed(lambda: model.training_step(b), warmup, steps)
     graph_ms = None
     try:  # the refinement step is sync-free (device-state Adam, fused bone-transform backward): capture and replay it
         from instantavatar_b200.graphs import GraphedTrainStep
-        model.global_step = 2001
+        model.global_step = 2000
         graphed = GraphedTrainStep(model, b)
-        graph_ms = timed(lambda: graphed())
+        graph_ms = timed(lambda: graphed(), 25, 40)  # warm-up captures both variants (with / without the grid refresh)
     except Exception as exc:
         print(f"[bench] pose-refinement graph capture failed ({type(exc).__name__}: {exc}), eager number only", file=sys.stderr)
     out["pose_refine"] = {"ms_per_step": graph_ms if graph_ms is not None else eager_ms, "ms_per_step_eager": eager_ms,
-                          "rays_per_step": int(len(pick)), "steps": steps, "cuda_graph": graph_ms is not None,
+                          "rays_per_step": int(len(pick)), "steps": 40 if graph_ms is not None else steps, "cuda_graph": graph_ms is not None,
                           "what": "frozen network: fused bone transforms (+ reverse mode), train_fwd, loss, composite_bwd, ngp_backward "
                                   "(features only), pose_grad, device Adam on the pose tables; grid refresh amortised"}
     model.freeze_network(False)

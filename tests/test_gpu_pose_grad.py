@@ -210,9 +210,10 @@ def test_pose_refinement_reduces_pose_error():
     enc_before = model.net_coarse.encoder.params.detach().clone()
     model.global_step = 0
     errs, losses = [], []
-    for step in range(120):
-        pick = sel[torch.randint(0, len(sel), (2048,), device="cuda")]
-        b = _ray_batch(batch, pick, rgb_gt, alpha_gt, step)
+    for step in range(150):
+        # a fixed ray set and background: the loss is a deterministic function of the pose up to the sampling jitter, so
+        # the descent is not at the mercy of mini-batch noise (Adam with eps 1e-15 normalises every component)
+        b = _ray_batch(batch, sel, rgb_gt, alpha_gt, 0)
         out = model.training_step(b)
         losses.append(out["loss"].item())
         # error of the perturbed joints (Adam with eps 1e-15 random-walks the parameters that only see gradient noise)
