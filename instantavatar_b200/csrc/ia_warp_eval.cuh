@@ -63,10 +63,10 @@ __device__ __forceinline__ void warp_eval_samples(const EvalCtx& ctx, WarpScratc
     unsigned vmask = 0;
 #pragma unroll 1
     for (int b = 0; b < kNumInit; b++) {
-        float x[3];
-        int ng = 0;
-        const bool ok = broyden_solve_warp(ctx.field, fc.bp, fc.Tb[b], active, xd0, xd1, xd2, x, ng, lane);
         if (active) {
+            float x[3];
+            int ng = 0;
+            const bool ok = broyden_solve(ctx.field, fc.bp, fc.Tb[b], xd0, xd1, xd2, x, nullptr, ng);
             ngather += ng;
             ws.cand[0][b][lane] = x[0];
             ws.cand[1][b][lane] = x[1];
