@@ -34,7 +34,7 @@ typedef void* ia_stream_t; /* cudaStream_t */
 
 /* Per-frame read-only state of the fused kernels. */
 typedef struct IaScene {
-    const float* field;      /* [D][H][W][16] fp32: blended 3x4 LBS transform per voxel + 4 pad (64-B records; ia_precompute) */
+    const float* field;      /* [D][H][W][24] fp32: blended 3x4 LBS transform of voxel x followed by that of voxel x+1 (zeros at x = W-1); 96-B records written by ia_precompute */
     int32_t D, H, W;
     const float* offset_k;   /* [3] ForwardDeformer.offset_kernel (deformer_torch.py:154) */
     const float* scale_k;    /* [3] ForwardDeformer.scale_kernel  (deformer_torch.py:155-158) */
@@ -70,7 +70,7 @@ int ia_hashgrid_layout(uint32_t res[IA_NUM_LEVELS], float scale[IA_NUM_LEVELS], 
 
 /* Replaces precompute_cuda.precompute (deformers/fast_snarf/cuda/precompute/precompute.cpp:7-13,
  * precompute.cu:24-103).  voxel_w [24][D][H][W] skinning weights, tfs [24][4][4].
- * field_out [D][H][W][16] (12 used, 32-byte aligned); voxel_d_out [3][D][H][W] (nullable; reference layout, deformer.voxel_d);
+ * field_out [D][H][W][24] (x-pair records: row-major 3x4 of voxel x, then of voxel x+1; 32-byte aligned); voxel_d_out [3][D][H][W] (nullable; reference layout, deformer.voxel_d);
  * aabb_out [6] = min/max of voxel_d (nullable; SNARFDeformer.get_bbox_deformed, snarf_deformer.py:105-107). */
 int ia_precompute(const float* voxel_w, const float* tfs, const float* offset_k, const float* scale_k, int D, int H,
                   int W, float* field_out, float* voxel_d_out, float* aabb_out, ia_stream_t stream);

@@ -559,7 +559,7 @@ __device__ __forceinline__ void atomic_max_f(float* addr, float v) {
 }
 
 // precompute.cu:24-71 with a voxel-major output layout; one thread per voxel, weights read coalesced
-// (channel-major input), output written as 3 x float4.
+// (channel-major input), output written as float4s.
 __global__ void __launch_bounds__(256) precompute_kernel(const float* __restrict__ voxel_w, const float* __restrict__ tfs,
                                                          const float* __restrict__ offset_k,
                                                          const float* __restrict__ scale_k, int D, int H, int W,
@@ -590,10 +590,21 @@ __global__ void __launch_bounds__(256) precompute_kernel(const float* __restrict
 #pragma unroll
             for (int c = 0; c < 12; c++) J[c] = __fmaf_rn(w, T[j][c], J[c]);
         }
-        field[index * 4 + 0] = make_float4(J[0], J[1], J[2], J[3]);
-        field[index * 4 + 1] = make_float4(J[4], J[5], J[6], J[7]);
-        field[index * 4 + 2] = make_float4(J[8], J[9], J[10], J[11]);
-        field[index * 4 + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // x-pair records (ia_device.cuh): slot A of this voxel's record, slot B of its -x neighbour's record; the last
+        // voxel of a row has a zero-filled slot B (the padding neighbour, weight 0 in the sampler)
+        field[index * 6 + 0] = make_float4(J[0], J[1], J[2], J[3]);
+        field[index * 6 + 1] = make_float4(J[4], J[5], J[6], J[7]);
+        field[index * 6 + 2] = make_float4(J[8], J[9], J[10], J[11]);
+        if (idx_w > 0) {
+            field[(index - 1) * 6 + 3] = make_float4(J[0], J[1], J[2], J[3]);
+            field[(index - 1) * 6 + 4] = make_float4(J[4], J[5], J[6], J[7]);
+            field[(index - 1) * 6 + 5] = make_float4(J[8], J[9], J[10], J[11]);
+        }
+        if (idx_w == W - 1) {
+            field[index * 6 + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+            field[index * 6 + 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            field[index * 6 + 5] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int i0 = 0; i0 < 3; i0++) {
             vd[i0] = aff3f(J[i0 * 4 + 0], cx, J[i0 * 4 + 1], cy, J[i0 * 4 + 2], cz, J[i0 * 4 + 3]);

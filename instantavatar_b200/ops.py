@@ -16,11 +16,11 @@ f32 = torch.float32
 def precompute(voxel_w: torch.Tensor, tfs: torch.Tensor, offset_k: torch.Tensor, scale_k: torch.Tensor,
                want_voxel_d: bool = True):
     """precompute_cuda.precompute (deformer_torch.py:77-83).  voxel_w [1|,24,D,H,W]; tfs [1|,24,4,4].
-    Returns (field [D,H,W,16] (12 used), voxel_d [3,D,H,W] | None, aabb [6])."""
+    Returns (field [D,H,W,24] (x-pair records), voxel_d [3,D,H,W] | None, aabb [6])."""
     voxel_w = voxel_w.reshape(24, *voxel_w.shape[-3:]).contiguous()
     D, H, W = voxel_w.shape[-3:]
     dev = voxel_w.device
-    fld = torch.empty((D, H, W, 16), device=dev, dtype=f32)
+    fld = torch.empty((D, H, W, 24), device=dev, dtype=f32)
     vd = torch.empty((3, D, H, W), device=dev, dtype=f32) if want_voxel_d else None
     aabb = torch.empty(6, device=dev, dtype=f32)  # initialised by the library
     _lib.count(1); check(lib().ia_precompute(ptr(voxel_w, f32), ptr(tfs.reshape(24, 4, 4).contiguous(), f32),
@@ -82,7 +82,7 @@ def occupancy_query(scene, jitters: torch.Tensor, aabb6: torch.Tensor, density=N
 @dataclass
 class Scene:
     """Per-frame read-only state (IaScene) with the tensors that keep it alive."""
-    field: torch.Tensor | None = None     # [D,H,W,16]
+    field: torch.Tensor | None = None     # [D,H,W,24]
     offset_k: torch.Tensor | None = None  # [3]
     scale_k: torch.Tensor | None = None   # [3]
     tfs: torch.Tensor | None = None       # [24,4,4]

@@ -40,9 +40,11 @@ def sample_points(sc, n, seed=0):
 def test_precompute_bit_exact(sc, dev):
     scene, extra = dev
     vJ = sc["frame"]["voxel_J"]  # [12,D,H,W]
-    fld = scene.field.cpu().numpy()  # [D,H,W,16], 12 used
-    np.testing.assert_array_equal(fld[..., :12], np.moveaxis(vJ, 0, -1))
-    assert not fld[..., 12:].any()
+    fld = scene.field.cpu().numpy()  # [D,H,W,24]: coefficients of voxel x, then of voxel x+1 (zeros in the last column)
+    ref = np.moveaxis(vJ, 0, -1)
+    np.testing.assert_array_equal(fld[..., :12], ref)
+    np.testing.assert_array_equal(fld[:, :, :-1, 12:], ref[:, :, 1:])
+    assert not fld[:, :, -1, 12:].any()
     np.testing.assert_array_equal(extra["voxel_d"].cpu().numpy(), sc["frame"]["voxel_d"])
     np.testing.assert_array_equal(extra["aabb"].cpu().numpy(), sc["frame"]["bbox_deformed"].reshape(6))
 
