@@ -60,55 +60,20 @@ __device__ __forceinline__ void warp_eval_samples(const EvalCtx& ctx, WarpScratc
                                                   unsigned& ngather, unsigned& nroots) {
     const FrameConst& fc = *ctx.fc;
     // ---- 1. Broyden from the 13 bone initialisations ------------------------------------------------
-    // (a) classify: an initial guess outside the skinning volume ends at the reference's first divergence test without
-    //     touching memory (see broyden_solve) -- 44 % of the (point, bone) pairs of an occupancy pass, fewer near the
-    //     body.  Only the remaining pairs are real solves.
-    unsigned work = 0;
-    if (active) {
-        const bool far_enough = dot3f(xd0, xd0, xd1, xd1, xd2, xd2) > fc.bp.dvg2;
+    unsigned vmask = 0;
 #pragma unroll 1
-        for (int b = 0; b < kNumInit; b++) {
-            const float* Tb = fc.Tb[b];
-            const float dx = xd0 - Tb[3], dy = xd1 - Tb[7], dz = xd2 - Tb[11];
-            const float x0 = dot3f(dx, Tb[0], dy, Tb[4], dz, Tb[8]);
-            const float x1 = dot3f(dx, Tb[1], dy, Tb[5], dz, Tb[9]);
-            const float x2 = dot3f(dx, Tb[2], dy, Tb[6], dz, Tb[10]);
-            if (far_enough && field_miss(ctx.field, fc.bp.scl[0] * (x0 + fc.bp.off[0]), fc.bp.scl[1] * (x1 + fc.bp.off[1]),
-                                         fc.bp.scl[2] * (x2 + fc.bp.off[2])))
-                ngather += 2;  // the two (empty) samples the reference takes before it leaves the loop
-            else
-                work |= 1u << b;
-        }
-    }
-    // (b) compact the real solves of the warp's <= 32 samples into a list and run them 32 at a time, lane = solve: the
-    //     lanes that would idle next to a trivial solve carry another sample's solve instead
-    int n_work;
-    {
-        int pos = warp_excl_scan(__popc(work), lane, n_work);
-        for (unsigned m = work; m; m &= m - 1) ws.roots[pos++] = (uint16_t)(lane | ((__ffs(m) - 1) << 5));
-        ws.res[lane][0] = xd0; ws.res[lane][1] = xd1; ws.res[lane][2] = xd2;
-        reinterpret_cast<unsigned*>(&ws.res[lane][3])[0] = 0u;  // validity bits of this lane's sample
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (int base = 0; base < n_work; base += 32) {
-        const int r = base + lane;
-        if (r < n_work) {
-            const int src = ws.roots[r];
-            const int sl = src & 31, sb = src >> 5;
+    for (int b = 0; b < kNumInit; b++) {
+        if (active) {
             float x[3];
             int ng = 0;
-            const bool ok = broyden_solve(ctx.field, fc.bp, fc.Tb[sb], ws.res[sl][0], ws.res[sl][1], ws.res[sl][2], x, nullptr, ng);
+            const bool ok = broyden_solve(ctx.field, fc.bp, fc.Tb[b], xd0, xd1, xd2, x, nullptr, ng);
             ngather += ng;
-            ws.cand[0][sb][sl] = x[0];
-            ws.cand[1][sb][sl] = x[1];
-            ws.cand[2][sb][sl] = x[2];
-            if (ok) atomicOr(reinterpret_cast<unsigned*>(&ws.res[sl][3]), 1u << sb);
+            ws.cand[0][b][lane] = x[0];
+            ws.cand[1][b][lane] = x[1];
+            ws.cand[2][b][lane] = x[2];
+            if (ok) vmask |= 1u << b;
         }
     }
-    __syncwarp();
-    const unsigned vmask = active ? reinterpret_cast<const unsigned*>(&ws.res[lane][3])[0] : 0u;
-    __syncwarp();
     // ---- 2. duplicate filter (filter.cu:25-52): drop root i if a later valid root is within 1e-4 ------
     unsigned kept = vmask;
     if (vmask & (vmask - 1)) {  // at least two valid roots
