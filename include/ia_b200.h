@@ -86,6 +86,11 @@ int ia_voxelize_weights(const float* verts, const float* vert_weights, int n_ver
                         const float* zs, int D, int H, int W, const float* offset, const float* scale, float ratio,
                         int knn, int smooth_passes, float* lbs_voxel, float* scratch, ia_stream_t stream);
 
+/* Nearest vertex of every point: SMPLDeformer.deform's ops.knn_points(pts, vertices, K=1)
+ * (deformers/smpl_deformer.py:94-95; third_parties/pytorch3d/ops.py:123-206 contract: squared distance, ties keep the
+ * earlier vertex).  pts [n][3], verts [n_verts][3] -> idx_out [n] int32, dist2_out [n]. */
+int ia_knn1(const float* pts, int n, const float* verts, int n_verts, int* idx_out, float* dist2_out, ia_stream_t stream);
+
 /* Per-frame bone transforms in one launch.  Replaces, for everything the renderer consumes, the SMPL forward + tfs
  * algebra of SNARFDeformer.prepare_deformer (deformers/snarf_deformer.py:79-86; smplx/lbs.py:295-329 Rodrigues,
  * :345-401 kinematic chain; body_models.py:353-360 transl): global_orient [3], body_pose [69], transl [3] (nullable),

@@ -105,7 +105,50 @@ __global__ void __launch_bounds__(256) smooth_pass_kernel(const float* __restric
     for (int c = 0; c < 24; c++) dst[(long)c * V + vox] = v[c] / total;
 }
 
+// Nearest posed vertex of every sample point (SMPLDeformer.deform, deformers/smpl_deformer.py:87-110: pytorch3d
+// knn_points with K = 1): squared distance and index; strict `<` keeps the earlier vertex on ties.  One thread per point,
+// vertices staged through shared memory; the per-frame cost is n x 6890 distance evaluations.
+__global__ void __launch_bounds__(256) knn1_kernel(const float* __restrict__ pts, int n, const float* __restrict__ verts, int n_verts,
+                                                   int* __restrict__ idx_out, float* __restrict__ d2_out) {
+    extern __shared__ float sv[];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < n;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (live) { px = pts[p * 3]; py = pts[p * 3 + 1]; pz = pts[p * 3 + 2]; }
+    float best = FLT_MAX;
+    int bi = 0;
+    for (int base = 0; base < n_verts; base += kVertTile) {
+        const int nt = min(kVertTile, n_verts - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt * 3; i += blockDim.x) sv[i] = verts[(long)base * 3 + i];
+        __syncthreads();
+        if (!live) continue;
+#pragma unroll 4
+        for (int j = 0; j < nt; j++) {
+            const float dx = px - sv[j * 3], dy = py - sv[j * 3 + 1], dz = pz - sv[j * 3 + 2];
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < best) { best = d2; bi = base + j; }
+        }
+    }
+    if (live) { idx_out[p] = bi; d2_out[p] = best; }
+}
+
 }  // namespace
+
+extern "C" int ia_knn1(const float* pts, int n, const float* verts, int n_verts, int* idx_out, float* dist2_out, ia_stream_t stream) {
+    IA_REQUIRE(n >= 0 && n_verts > 0);
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(pts && verts && idx_out && dist2_out);
+    const size_t smem = (size_t)(n_verts < kVertTile ? n_verts : kVertTile) * 3 * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(knn1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kVertTile * 3 * (int)sizeof(float)));
+        attr_set = true;
+    }
+    knn1_kernel<<<(n + 255) / 256, 256, smem, (cudaStream_t)stream>>>(pts, n, verts, n_verts, idx_out, dist2_out);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
 
 extern "C" int ia_voxelize_weights(const float* verts, const float* vert_weights, int n_verts, const float* xs, const float* ys,
                                    const float* zs, int D, int H, int W, const float* offset, const float* scale, float ratio,

@@ -25,6 +25,8 @@ class SMPLOutput:
     betas: torch.Tensor
     body_pose: torch.Tensor
     global_orient: torch.Tensor
+    pose_offsets: torch.Tensor = None    # [B,V,3] pose blend-shape displacements (the vendored smplx exposes them)
+    shape_offsets: torch.Tensor = None   # [B,V,3] shape blend-shape displacements
 
 
 def _chain_levels(parents: np.ndarray):
@@ -88,12 +90,14 @@ class SMPL(nn.Module):
             global_orient = torch.zeros((B, 3), device=dev, dtype=dt)
         betas = betas.expand(B, -1)
         full_pose = torch.cat([global_orient, body_pose], dim=1)
-        v_shaped = self.v_template + torch.einsum("bl,mkl->bmk", betas, self.shapedirs)
+        shape_offsets = torch.einsum("bl,mkl->bmk", betas, self.shapedirs)
+        v_shaped = self.v_template + shape_offsets
         J = torch.einsum("jv,bvk->bjk", self.J_regressor, v_shaped)
         rot = self.rodrigues(full_pose.reshape(-1, 3)).view(B, 24, 3, 3)
         ident = torch.eye(3, dtype=dt, device=dev)
         pose_feature = (rot[:, 1:] - ident).reshape(B, -1)
-        v_posed = v_shaped + torch.matmul(pose_feature, self.posedirs).view(B, -1, 3)
+        pose_offsets = torch.matmul(pose_feature, self.posedirs).view(B, -1, 3)
+        v_posed = v_shaped + pose_offsets
         # kinematic chain, level by level
         rel = J.clone()
         rel[:, 1:] = J[:, 1:] - J[:, self._par1]
@@ -119,4 +123,4 @@ class SMPL(nn.Module):
             A = A.clone(); A[..., :3, 3] += transl[:, None]
             T = T.clone(); T[..., :3, 3] += transl[:, None]
         return SMPLOutput(vertices=verts, joints=posed_joints, A=A, T=T, betas=betas, body_pose=body_pose,
-                          global_orient=global_orient)
+                          global_orient=global_orient, pose_offsets=pose_offsets, shape_offsets=shape_offsets)

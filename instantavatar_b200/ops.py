@@ -371,3 +371,13 @@ def smpl_tfs_backward(global_orient, body_pose, transl, joints, parents_i32, tfs
                                                     ptr(tfs_inv_t.reshape(-1).contiguous(), f32), ptr(grad_tfs.reshape(-1).contiguous(), f32),
                                                     ptr(g_o), ptr(g_p), ptr(g_t), stream()))
     return g_o, g_p, g_t
+
+
+def knn1(pts, verts):
+    """ops.knn_points(pts, verts, K=1) of SMPLDeformer.deform (smpl_deformer.py:94-95) -> (dist_sq [n], idx [n] int64)"""
+    pts = pts.reshape(-1, 3).contiguous(); verts = verts.reshape(-1, 3).contiguous()
+    n = pts.shape[0]
+    idx = torch.empty(n, device=pts.device, dtype=torch.int32); d2 = torch.empty(n, device=pts.device, dtype=f32)
+    _lib.count(1); check(lib().ia_knn1(ptr(pts, f32), C.c_int(n), ptr(verts, f32), C.c_int(verts.shape[0]), ptr(idx, torch.int32), ptr(d2),
+                                       stream()))
+    return d2, idx.long()

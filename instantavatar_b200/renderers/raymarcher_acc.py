@@ -25,14 +25,20 @@ class BoundModel:
 
 
 def _unwrap(model):
-    """find (deformer, net) behind a model callable; None if it is a foreign model"""
+    """find (deformer, net) behind a model callable; None if it is not a SNARFDeformer + NeRFNGPNet pair (the fused
+    kernels implement exactly that pair; anything else goes through the kernel-for-kernel legacy path)"""
+    pair = None
     if hasattr(model, "deformer") and hasattr(model, "net"):
-        return model.deformer, model.net
-    for cell in getattr(model, "__closure__", None) or ():
-        obj = cell.cell_contents
-        if hasattr(obj, "deformer") and hasattr(obj, "net_coarse"):
-            return obj.deformer, obj.net_coarse
-    return None
+        pair = (model.deformer, model.net)
+    else:
+        for cell in getattr(model, "__closure__", None) or ():
+            obj = cell.cell_contents
+            if hasattr(obj, "deformer") and hasattr(obj, "net_coarse"):
+                pair = (obj.deformer, obj.net_coarse)
+                break
+    if pair is None or not hasattr(pair[0], "scene") or not hasattr(pair[1], "half_params"):
+        return None
+    return pair
 
 
 class Raymarcher(torch.nn.Module):
@@ -120,10 +126,50 @@ class Raymarcher(torch.nn.Module):
             "counter_coarse": out["counter"].reshape(rays.near.shape),
         }
 
+    def render_train_legacy(self, rays, model, noise, bg_color, jitter=None, noise_tensor=None):
+        """raymarcher_acc.py:140-186 on the kernel-for-kernel march operator and torch compositing (autograd), for any
+        differentiable `model(pts, None)` callable (e.g. SMPLDeformer + NeRFNGPNet)."""
+        rays_o = rays.o.reshape(-1, 3).float().contiguous()
+        rays_d = rays.d.reshape(-1, 3).float().contiguous()
+        near = rays.near.reshape(-1).float().contiguous()
+        far = rays.far.reshape(-1).float().contiguous()
+        N_step = self.MAX_SAMPLES
+        step_size = ((far - near) / N_step).contiguous()
+        grid = self.density_grid_train
+        offset = grid.min_corner.float().contiguous(); scale = (grid.max_corner - grid.min_corner).float().contiguous()
+        with torch.no_grad():
+            z_vals = ops.raymarch_train(rays_o.detach(), rays_d.detach(), near.detach(), far.detach(), grid.density_field, scale, offset,
+                                        step_size.detach(), N_step)
+        mask = z_vals > 0
+        z_vals = z_vals + (torch.rand_like(z_vals) if jitter is None else jitter) * step_size[:, None]
+        pts = z_vals[..., None] * rays_d[:, None] + rays_o[:, None]
+        rgb_vals = torch.zeros_like(pts, dtype=torch.float32)
+        sigma_vals = -torch.ones_like(rgb_vals[..., 0]) * 1e3
+        if mask.any():
+            r, s = model(pts[mask], None)
+            mi = mask.nonzero(as_tuple=True)
+            rgb_vals = rgb_vals.index_put(mi, r.float())
+            sigma_vals = sigma_vals.index_put(mi, s.float())
+        if noise_tensor is not None:
+            sigma_vals = sigma_vals + noise_tensor
+        elif noise > 0:
+            sigma_vals = sigma_vals + noise * torch.randn_like(sigma_vals)
+        dists = torch.ones_like(sigma_vals) * step_size[:, None]
+        # composite (raymarcher_acc.py:25-36)
+        alpha = 1.0 - torch.exp(-torch.relu(sigma_vals) * dists)
+        trans = torch.cat([torch.ones_like(alpha[..., 0:1]), torch.cumprod(1 - alpha + 1e-10, dim=-1)], dim=-1)
+        weights = alpha * trans[..., :-1]
+        no_hit = trans[..., -1]
+        color = (weights[..., None] * rgb_vals).sum(dim=-2)
+        color = color + no_hit[..., None] * (bg_color.reshape(-1, 3) if bg_color is not None else 1.0)
+        depth = (weights * z_vals).sum(dim=-1)
+        return {"rgb_coarse": color.reshape(rays.o.shape), "depth_coarse": depth.reshape(rays.near.shape),
+                "alpha_coarse": weights.sum(-1).reshape(rays.near.shape), "weight_coarse": weights.reshape(*rays.near.shape, -1)}
+
     def render_train(self, rays, model, noise, bg_color, jitter=None, noise_tensor=None):
         bound = _unwrap(model)
         if bound is None:
-            raise NotImplementedError("Raymarcher.render_train: only SNARFDeformer + NeRFNGPNet models are fused")
+            return self.render_train_legacy(rays, model, noise, bg_color, jitter, noise_tensor)
         from ..autograd import render_train_fused
         deformer, net = bound
         return render_train_fused(self, deformer, net, rays, noise, bg_color, jitter, noise_tensor)
