@@ -65,3 +65,23 @@ def test_smpl_param_embedding_lookup_and_tv_loss():
     assert abs(emb.tv_loss(end).item() - expect_end.item()) < 1e-6
     out["body_pose"].sum().backward()
     assert emb.body_pose.weight.grad[3].abs().sum() > 0 and emb.body_pose.weight.grad[0].abs().sum() == 0
+
+
+def test_smpl_deformer_inverse_transforms_map_posed_vertices_to_the_template():
+    """SMPLDeformer.prepare_deformer (smpl_deformer.py:50-76) on the CPU: T_inv of vertex i takes the posed vertex (root
+    frame) to the template-pose vertex, blend shapes removed and re-applied; the ray transform is the inverse root
+    transform"""
+    from instantavatar_b200 import synthetic
+    from instantavatar_b200.deformers.smpl_deformer import SMPLDeformer
+    d = SMPLDeformer(smpl_data=synthetic.smpl_dict_cached(0))
+    pose = {k: torch.from_numpy(v) for k, v in synthetic.load_pose(3).items()}
+    d.prepare_deformer(pose)
+    v = d.vertices[0]
+    cano = (d.T_inv[0][:, :3, :3] @ v[..., None]).squeeze(-1) + d.T_inv[0][:, :3, 3]
+    assert (cano - d.vs_template[0]).abs().max() < 1e-5
+    out = d.body_model(betas=pose["betas"], body_pose=pose["body_pose"], global_orient=pose["global_orient"], transl=pose["transl"])
+    assert torch.allclose(d.w2s @ out.A[:, 0], torch.eye(4)[None], atol=1e-5)
+    bb = d.get_bbox_deformed()
+    assert bb.shape == (2, 3) and (bb[1] > bb[0]).all()
+    with pytest.raises(ValueError):
+        SMPLDeformer(smpl_data=synthetic.smpl_dict_cached(0), k=3)
