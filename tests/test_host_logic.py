@@ -74,7 +74,7 @@ def test_smpl_deformer_inverse_transforms_map_posed_vertices_to_the_template():
     from instantavatar_b200 import synthetic
     from instantavatar_b200.deformers.smpl_deformer import SMPLDeformer
     d = SMPLDeformer(smpl_data=synthetic.smpl_dict_cached(0))
-    pose = {k: torch.from_numpy(v) for k, v in synthetic.load_pose(3).items()}
+    pose = {k: torch.from_numpy(v) for k, v in synthetic.load_pose(57).items()}
     d.prepare_deformer(pose)
     v = d.vertices[0]
     cano = (d.T_inv[0][:, :3, :3] @ v[..., None]).squeeze(-1) + d.T_inv[0][:, :3, 3]
