@@ -521,9 +521,10 @@ def run_ours(args):
     # R*(24+16) + gathers*384 + P*512 + one compulsory read of the tables
     algo_bytes = N_RAYS * 40 + st["gathers"] * 384 + st["net_evals"] * 512 + field_bytes + table_bytes + 32768 + 22016
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, limiter = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "render_traffic.json")))["dram_bytes_per_launch"]
+        prof = json.load(open(os.path.join(ROOT, "profiles", "render_traffic.json")))
+        traffic, limiter = prof["dram_bytes_per_launch"], prof.get("limiter")
     except Exception:
         pass
     value = world * N_RAYS * args.steps / (total_ms * 1e-3)
@@ -550,7 +551,8 @@ def run_ours(args):
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": algo_bytes,
                      "note": "no-reuse gather model (SURVEY.md 8d): most gathers are served by L1/L2, so frac can exceed 1; "
-                             "traffic = measured DRAM bytes (ncu)"},
+                             "traffic = measured DRAM bytes (ncu)",
+                     "limiter_from_ncu": limiter},
     }
     if not args.no_cpu_baseline:
         cf = CpuFrame(frame)
