@@ -1,10 +1,11 @@
-"""Host-side mirror of instant_avatar/deformers/smpl_deformer.py::SMPLDeformer (`fit.py deformer=smpl`,
-bash/run-neuman-demo.sh): every sample point takes the inverse skinning transform of its nearest posed SMPL vertex.
+"""Nearest-vertex deformer -- the capability of instant_avatar/deformers/smpl_deformer.py::SMPLDeformer
+(`fit.py deformer=smpl`, bash/run-neuman-demo.sh) on this library's operators.
 
-The nearest-vertex search (pytorch3d `knn_points`, K = 1, per sample per frame) is `ia_knn1`; the per-vertex inverse
-transforms are assembled with torch exactly as the reference does (`:60-76`), once per frame.  The network is called
-through `model(pts_cano, None)`; `NeRFNGPNet.forward` is differentiable w.r.t. parameters and points, so the pose
-gradients of `optimize_SMPL` flow through `T_inv`.
+A sample takes the inverse skinning transform of its nearest posed SMPL vertex.  Per frame the 6890 inverse transforms
+are assembled once (batched 3x4 `rot` / `shift` tables, blend-shape offsets removed and re-applied as in the reference,
+smpl_deformer.py:60-76); per sample the search is `ia_knn1` (pytorch3d knn_points K = 1 contract) and the transform is one
+gathered batched product.  The network is any `model(points, None)` callable; `NeRFNGPNet.forward` is differentiable
+w.r.t. parameters and points, so pose gradients flow through the gathered tables.
 """
 from __future__ import annotations
 
@@ -14,104 +15,89 @@ import torch
 
 from .. import ops
 from .smpl import SMPL
-from .snarf_deformer import get_bbox_from_smpl
+from .snarf_deformer import get_bbox_from_smpl, rays_to_root_frame
+
+TEMPLATE_SPREAD = math.pi / 6  # hip abduction of the canonical template (T-pose legs are too close, smpl_deformer.py:29-39)
+
+
+def _template_pose(n, device):
+    pose = torch.zeros((n, 69), device=device)
+    pose[:, 2], pose[:, 5] = TEMPLATE_SPREAD, -TEMPLATE_SPREAD
+    return pose
 
 
 class SMPLDeformer:
     def __init__(self, model_path=None, gender="male", threshold=0.05, k=1, smpl_data=None) -> None:
         if k != 1:
-            raise ValueError("SMPLDeformer: the nearest-neighbour strategy uses k = 1 (smpl_deformer.py:26,102-103)")
+            raise ValueError("SMPLDeformer: the nearest-neighbour strategy is defined for k = 1")
         self.body_model = SMPL(model_path, gender=gender, data_struct=smpl_data)
-        self.k = k
-        self.threshold = threshold
-        self.strategy = "nearest_neighbor"
-        self.initialized = False
+        self.k, self.threshold, self.strategy = k, threshold, "nearest_neighbor"
+        self.initialized = False  # the reference re-initialises every frame (betas may be optimised); kept
 
+    # ---- canonical template ------------------------------------------------------------------------
     def initialize(self, betas, device):
-        """smpl_deformer.py:33-45: the canonical template is a 30-degree A-pose"""
-        batch_size = betas.shape[0]
-        body_pose_t = torch.zeros((batch_size, 69), device=device)
-        body_pose_t[:, 2] = math.pi / 6
-        body_pose_t[:, 5] = -math.pi / 6
-        out = self.body_model(betas=betas, body_pose=body_pose_t)
-        self.bbox = get_bbox_from_smpl(out.vertices[0:1].detach())
-        self.T_template = out.T
-        self.vs_template = out.vertices
-        self.pose_offset_t = out.pose_offsets
-        self.shape_offset_t = out.shape_offsets
+        tpl = self.body_model(betas=betas, body_pose=_template_pose(betas.shape[0], device))
+        self.bbox = get_bbox_from_smpl(tpl.vertices[0:1].detach())
+        self.T_template, self.vs_template = tpl.T, tpl.vertices
+        self.pose_offset_t, self.shape_offset_t = tpl.pose_offsets, tpl.shape_offsets
+
+    # ---- per frame ----------------------------------------------------------------------------------
+    def prepare_deformer(self, smpl_params):
+        dev = smpl_params["betas"].device
+        if self.body_model.v_template.device != dev:
+            self.body_model = self.body_model.to(dev)
+        if not self.initialized:
+            self.initialize(smpl_params["betas"], dev)
+        posed = self.body_model(**{k: smpl_params[k] for k in ("betas", "body_pose", "global_orient", "transl")})
+        root = posed.A[:, 0]
+        self.w2s = torch.inverse(root)
+        # root frame -> world -> un-posed (T^-1) -> swap this frame's blend shapes for the template's -> template pose
+        unpose = torch.inverse(posed.T.float()) @ root[:, None]
+        swap = (self.pose_offset_t - posed.pose_offsets) + (self.shape_offset_t - posed.shape_offsets)
+        unpose = torch.cat([unpose[..., :3, :3], (unpose[..., :3, 3] + swap)[..., None]], dim=-1)       # [B,V,3,4]
+        bottom = torch.zeros_like(unpose[..., :1, :]); bottom[..., 0, 3] = 1.0
+        self.T_inv = self.T_template @ torch.cat([unpose, bottom], dim=-2)
+        self.rot, self.shift = self.T_inv[..., :3, :3], self.T_inv[..., :3, 3]
+        self.vertices = torch.baddbmm(self.w2s[:, None, :3, 3], posed.vertices, self.w2s[:, :3, :3].transpose(1, 2))
 
     def get_bbox_deformed(self):
         return get_bbox_from_smpl(self.vertices[0:1].detach())
 
-    def prepare_deformer(self, smpl_params):
-        """smpl_deformer.py:50-76"""
-        device = smpl_params["betas"].device
-        if self.body_model.v_template.device != device:
-            self.body_model = self.body_model.to(device)
-        if not self.initialized:
-            self.initialize(smpl_params["betas"], device)  # every frame, as in the reference (betas may change)
-        out = self.body_model(betas=smpl_params["betas"], body_pose=smpl_params["body_pose"],
-                              global_orient=smpl_params["global_orient"], transl=smpl_params["transl"])
-        s2w = out.A[:, 0]
-        w2s = torch.inverse(s2w)
-        # remove and re-apply the blend shapes: posed -> T pose -> template pose
-        T_inv = torch.inverse(out.T.float()).clone() @ s2w[:, None]
-        T_inv[..., :3, 3] += self.pose_offset_t - out.pose_offsets
-        T_inv[..., :3, 3] += self.shape_offset_t - out.shape_offsets
-        T_inv = self.T_template @ T_inv
-        self.T_inv = T_inv
-        self.vertices = (out.vertices @ w2s[:, :3, :3].permute(0, 2, 1)) + w2s[:, None, :3, 3]
-        self.w2s = w2s
-
     def transform_rays_w2s(self, rays):
-        """smpl_deformer.py:78-85"""
-        w2s = self.w2s
-        rays.o = (rays.o @ w2s[:, :3, :3].permute(0, 2, 1)) + w2s[:, None, :3, 3]
-        rays.d = (rays.d @ w2s[:, :3, :3].permute(0, 2, 1)).to(rays.d)
-        d = torch.norm(rays.o, dim=-1)
-        rays.near = d - 1
-        rays.far = d + 1
+        rays_to_root_frame(rays, self.w2s)
 
+    # ---- per sample ---------------------------------------------------------------------------------
     def deform(self, pts):
-        """smpl_deformer.py:87-110: canonical point = T_inv[nearest vertex] . pts, valid if the vertex is within `threshold`"""
-        batch_size = self.vertices.shape[0]
-        pts = pts.reshape(batch_size, -1, 3)
-        pts_cano = torch.zeros_like(pts, dtype=torch.float32)
-        valid = torch.zeros(pts.shape[:2], device=pts.device, dtype=torch.bool)
-        for i in range(batch_size):
+        """-> (canonical points [P,3], valid [P]): valid when the nearest vertex lies within `threshold`"""
+        clouds = pts.reshape(self.vertices.shape[0], -1, 3)
+        cano, ok = [], []
+        for b, cloud in enumerate(clouds):
             with torch.no_grad():
-                dist_sq, idx = ops.knn1(pts[i].detach().float(), self.vertices[i].detach().float())
-            valid[i] = dist_sq < self.threshold ** 2
-            Tv_inv = self.T_inv[i][idx]
-            pts_cano[i] = (Tv_inv[..., :3, :3] @ pts[i][..., None]).squeeze(-1) + Tv_inv[..., :3, 3]
-        return pts_cano.reshape(-1, 3), valid.reshape(-1)
+                dist_sq, nearest = ops.knn1(cloud.detach().float(), self.vertices[b].detach().float())
+            ok.append(dist_sq < self.threshold ** 2)
+            cano.append(torch.einsum("pij,pj->pi", self.rot[b][nearest], cloud.float()) + self.shift[b][nearest])
+        return torch.cat(cano), torch.cat(ok)
+
+    def _query(self, pts, model, empty_sigma, sanitise):
+        cano, ok = self.deform(pts)
+        rgb = torch.zeros((cano.shape[0], 3), device=cano.device)
+        sigma = torch.full((cano.shape[0],), float(empty_sigma), device=cano.device)
+        if bool(ok.any()):
+            where = ok.nonzero(as_tuple=True)
+            c, s = model(cano[ok], None)
+            rgb, sigma = rgb.index_put(where, c.float()), sigma.index_put(where, s.float())
+            if sanitise:  # training: non-finite network outputs count as empty space (smpl_deformer.py:119-122)
+                good = torch.isfinite(rgb).all(-1) & torch.isfinite(sigma)
+                rgb = torch.where(good[:, None], rgb, torch.zeros_like(rgb))
+                sigma = torch.where(good, sigma, torch.full_like(sigma, float(empty_sigma)))
+        return rgb, sigma
 
     def deform_train(self, pts, model):
-        """smpl_deformer.py:112-123"""
-        pts_cano, valid = self.deform(pts)
-        rgb_cano = torch.zeros_like(pts, dtype=torch.float32)
-        sigma_cano = torch.ones_like(pts[..., 0]) * -1e5
-        if valid.any():
-            r, s = model(pts_cano[valid], None)
-            rgb_cano = rgb_cano.index_put((valid.nonzero(as_tuple=True)[0],), r.float())
-            sigma_cano = sigma_cano.index_put((valid.nonzero(as_tuple=True)[0],), s.float())
-            finite = torch.isfinite(rgb_cano).all(-1) & torch.isfinite(sigma_cano)
-            rgb_cano = torch.where(finite[:, None], rgb_cano, torch.zeros_like(rgb_cano))
-            sigma_cano = torch.where(finite, sigma_cano, torch.full_like(sigma_cano, -1e5))
-        return rgb_cano, sigma_cano
+        return self._query(pts, model, empty_sigma=-1e5, sanitise=True)
 
     def deform_test(self, pts, model):
-        """smpl_deformer.py:125-132"""
-        pts_cano, valid = self.deform(pts)
-        rgb_cano = torch.zeros_like(pts, dtype=torch.float32)
-        sigma_cano = torch.zeros_like(pts[..., 0])
-        if valid.any():
-            r, s = model(pts_cano[valid], None)
-            rgb_cano[valid], sigma_cano[valid] = r.float(), s.float()
-        return rgb_cano, sigma_cano
+        return self._query(pts, model, empty_sigma=0.0, sanitise=False)
 
     def __call__(self, pts, model, eval_mode=True):
         pts = pts.reshape(-1, 3)
-        if eval_mode:
-            return self.deform_test(pts, model)
-        return self.deform_train(pts, model)
+        return self.deform_test(pts, model) if eval_mode else self.deform_train(pts, model)

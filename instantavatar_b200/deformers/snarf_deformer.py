@@ -51,6 +51,16 @@ def get_bbox_from_smpl(vs, factor=1.2):
     return torch.cat([c - s[:, None], c + s[:, None]], dim=0)
 
 
+def rays_to_root_frame(rays, w2s):
+    """world -> SMPL-root frame for ray origins / directions, and the [|o| - 1, |o| + 1] marching interval both deformers
+    use (snarf_deformer.py:95-103, smpl_deformer.py:78-85); in place on the `Rays` record"""
+    rot_t, shift = w2s[:, :3, :3].transpose(1, 2), w2s[:, None, :3, 3]
+    rays.o = rays.o @ rot_t + shift
+    rays.d = (rays.d @ rot_t).to(rays.d)
+    dist = rays.o.norm(dim=-1)
+    rays.near, rays.far = dist - 1, dist + 1
+
+
 class _SmplTfs(torch.autograd.Function):
     """bone transforms of one frame (ia_smpl_tfs) with the hand-written reverse mode (ia_smpl_tfs_backward): pose
     optimisation differentiates Rodrigues + the kinematic chain + the tfs algebra in one launch instead of ~150
@@ -204,12 +214,7 @@ class SNARFDeformer:
 
     def transform_rays_w2s(self, rays):
         """snarf_deformer.py:95-103"""
-        w2s = self.w2s
-        rays.o = (rays.o @ w2s[:, :3, :3].permute(0, 2, 1)) + w2s[:, None, :3, 3]
-        rays.d = (rays.d @ w2s[:, :3, :3].permute(0, 2, 1)).to(rays.d)
-        d = torch.norm(rays.o, dim=-1)
-        rays.near = d - 1
-        rays.far = d + 1
+        rays_to_root_frame(rays, self.w2s)
 
     def get_bbox_deformed(self):
         """snarf_deformer.py:105-107 (computed by the precompute kernel)"""

@@ -67,42 +67,44 @@ class Raymarcher(torch.nn.Module):
             return self.render_test(rays, model, bg_color)
         return self.render_train(rays, model, noise, bg_color)
 
+    # ---- kernel-for-kernel paths: any `model(points, None)` callable (foreign deformers / networks) -----------------
+    def _flat_rays(self, rays):
+        f = lambda t, k: t.reshape(-1, k).float().contiguous() if k > 1 else t.reshape(-1).float().contiguous()
+        return f(rays.o, 3), f(rays.d, 3), f(rays.near, 1), f(rays.far, 1)
+
     @torch.no_grad()
     def render_test_legacy(self, rays, model, bg_color):
-        """raymarcher_acc.py:82-138 verbatim control flow on the kernel-for-kernel operators, for any `model(pts, None)`
-        callable (host-synchronous window loop, as in the reference)."""
-        device = rays.o.device
-        rays_o = rays.o.reshape(-1, 3).float().contiguous()
-        rays_d = rays.d.reshape(-1, 3).float().contiguous()
-        near = rays.near.reshape(-1).float().clone()
-        far = rays.far.reshape(-1).float().contiguous()
-        N = rays_o.shape[0]
-        color = torch.zeros(N, 3, device=device); depth = torch.zeros(N, device=device)
-        no_hit = torch.ones(N, device=device); counter = torch.zeros_like(depth)
-        alive = torch.arange(N, device=device)
-        step_size = ((far - near) / self.MAX_SAMPLES).contiguous()
+        """Inference with a foreign model: the reference's windowed schedule (raymarcher_acc.py:82-138 -- every pass marches
+        the surviving rays by as many occupied steps as fit MAX_BATCH_SIZE samples, queries the model on the occupied
+        ones, composites in place and retires saturated / finished rays) on `ia_raymarch_test` / `ia_composite_test`."""
+        origins, dirs, near, far = self._flat_rays(rays)
+        near = near.clone()  # advanced in place by the march operator
+        n_rays, S = origins.shape[0], self.MAX_SAMPLES
+        dev = origins.device
+        acc = {"color": torch.zeros(n_rays, 3, device=dev), "depth": torch.zeros(n_rays, device=dev),
+               "no_hit": torch.ones(n_rays, device=dev), "counter": torch.zeros(n_rays, device=dev)}
+        dt = ((far - near) / S).contiguous()
         grid = self.density_grid_test
-        offset = grid.min_corner.float().contiguous(); scale = (grid.max_corner - grid.min_corner).float().contiguous()
-        k = 0
-        while k < self.MAX_SAMPLES:
-            N_alive = len(alive)
-            if N_alive == 0:
-                break
-            N_step = max(min(self.MAX_BATCH_SIZE // N_alive, self.MAX_SAMPLES), 1)
-            pts, d_new, z_new = ops.raymarch_test(rays_o, rays_d, near, far, alive, grid.density_field, scale, offset, step_size, N_step)
-            counter[alive] += (d_new > 0).sum(dim=-1)
-            mask = d_new > 0
-            rgb_vals = torch.zeros_like(pts); sigma_vals = torch.zeros_like(rgb_vals[..., 0])
-            if mask.any():
-                r, s = model(pts[mask], None)
-                rgb_vals[mask], sigma_vals[mask] = r.float(), s.float()
-            ops.composite_test(rgb_vals, sigma_vals, d_new, z_new, alive, color, depth, no_hit, 0.01)
-            alive = alive[(no_hit[alive] > 1e-4) & (z_new[:, -1] > 0)]
-            k += N_step
-        bg = bg_color.reshape(-1, 3) if bg_color is not None else 1.0
-        color = color + no_hit[..., None] * bg
-        return {"rgb_coarse": color.reshape(rays.o.shape), "depth_coarse": depth.reshape(rays.near.shape),
-                "alpha_coarse": (1 - no_hit).reshape(rays.near.shape), "counter_coarse": counter.reshape(rays.near.shape)}
+        lo = grid.min_corner.float().contiguous(); extent = (grid.max_corner - grid.min_corner).float().contiguous()
+        live = torch.arange(n_rays, device=dev)
+        marched = 0
+        while marched < S and live.numel() > 0:
+            window = min(max(self.MAX_BATCH_SIZE // live.numel(), 1), S)
+            pts, delta, z = ops.raymarch_test(origins, dirs, near, far, live, grid.density_field, extent, lo, dt, window)
+            occupied = delta > 0
+            acc["counter"].index_add_(0, live, occupied.sum(dim=-1).float())
+            rgb = torch.zeros_like(pts); sigma = torch.zeros(pts.shape[:2], device=dev)
+            if bool(occupied.any()):
+                c, s = model(pts[occupied], None)
+                rgb[occupied], sigma[occupied] = c.float(), s.float()
+            ops.composite_test(rgb, sigma, delta, z, live, acc["color"], acc["depth"], acc["no_hit"], 0.01)
+            live = live[(acc["no_hit"][live] > 1e-4) & (z[:, -1] > 0)]
+            marched += window
+        background = bg_color.reshape(-1, 3) if bg_color is not None else 1.0
+        image = acc["color"] + acc["no_hit"][:, None] * background
+        like = rays.near.shape
+        return {"rgb_coarse": image.reshape(rays.o.shape), "depth_coarse": acc["depth"].reshape(like),
+                "alpha_coarse": (1 - acc["no_hit"]).reshape(like), "counter_coarse": acc["counter"].reshape(like)}
 
     @torch.no_grad()
     def render_test(self, rays, model, bg_color, stats=None):
@@ -127,44 +129,39 @@ class Raymarcher(torch.nn.Module):
         }
 
     def render_train_legacy(self, rays, model, noise, bg_color, jitter=None, noise_tensor=None):
-        """raymarcher_acc.py:140-186 on the kernel-for-kernel march operator and torch compositing (autograd), for any
-        differentiable `model(pts, None)` callable (e.g. SMPLDeformer + NeRFNGPNet)."""
-        rays_o = rays.o.reshape(-1, 3).float().contiguous()
-        rays_d = rays.d.reshape(-1, 3).float().contiguous()
-        near = rays.near.reshape(-1).float().contiguous()
-        far = rays.far.reshape(-1).float().contiguous()
-        N_step = self.MAX_SAMPLES
-        step_size = ((far - near) / N_step).contiguous()
+        """Training with a foreign, differentiable model (semantics of raymarcher_acc.py:140-186): `ia_raymarch_train` lists
+        the occupied steps of every ray, the model is queried on the jittered samples, and relu / cumprod(1 - alpha +
+        1e-10) compositing runs in torch so that autograd reaches the model."""
+        origins, dirs, near, far = self._flat_rays(rays)
+        S = self.MAX_SAMPLES
+        dt = ((far - near) / S).contiguous()
         grid = self.density_grid_train
-        offset = grid.min_corner.float().contiguous(); scale = (grid.max_corner - grid.min_corner).float().contiguous()
+        lo = grid.min_corner.float().contiguous(); extent = (grid.max_corner - grid.min_corner).float().contiguous()
         with torch.no_grad():
-            z_vals = ops.raymarch_train(rays_o.detach(), rays_d.detach(), near.detach(), far.detach(), grid.density_field, scale, offset,
-                                        step_size.detach(), N_step)
-        mask = z_vals > 0
-        z_vals = z_vals + (torch.rand_like(z_vals) if jitter is None else jitter) * step_size[:, None]
-        pts = z_vals[..., None] * rays_d[:, None] + rays_o[:, None]
-        rgb_vals = torch.zeros_like(pts, dtype=torch.float32)
-        sigma_vals = -torch.ones_like(rgb_vals[..., 0]) * 1e3
-        if mask.any():
-            r, s = model(pts[mask], None)
-            mi = mask.nonzero(as_tuple=True)
-            rgb_vals = rgb_vals.index_put(mi, r.float())
-            sigma_vals = sigma_vals.index_put(mi, s.float())
+            starts = ops.raymarch_train(origins.detach(), dirs.detach(), near.detach(), far.detach(), grid.density_field, extent, lo,
+                                        dt.detach(), S)
+        occupied = starts > 0
+        u = torch.rand_like(starts) if jitter is None else jitter
+        z = starts + u * dt[:, None]                                   # empty slots keep z = u * dt and get weight 0 below
+        samples = z[..., None] * dirs[:, None] + origins[:, None]
+        rgb = torch.zeros_like(samples)
+        sigma = torch.full(starts.shape, -1e3, device=starts.device)
+        if bool(occupied.any()):
+            where = occupied.nonzero(as_tuple=True)
+            c, s = model(samples[occupied], None)
+            rgb, sigma = rgb.index_put(where, c.float()), sigma.index_put(where, s.float())
         if noise_tensor is not None:
-            sigma_vals = sigma_vals + noise_tensor
+            sigma = sigma + noise_tensor
         elif noise > 0:
-            sigma_vals = sigma_vals + noise * torch.randn_like(sigma_vals)
-        dists = torch.ones_like(sigma_vals) * step_size[:, None]
-        # composite (raymarcher_acc.py:25-36)
-        alpha = 1.0 - torch.exp(-torch.relu(sigma_vals) * dists)
-        trans = torch.cat([torch.ones_like(alpha[..., 0:1]), torch.cumprod(1 - alpha + 1e-10, dim=-1)], dim=-1)
-        weights = alpha * trans[..., :-1]
-        no_hit = trans[..., -1]
-        color = (weights[..., None] * rgb_vals).sum(dim=-2)
-        color = color + no_hit[..., None] * (bg_color.reshape(-1, 3) if bg_color is not None else 1.0)
-        depth = (weights * z_vals).sum(dim=-1)
-        return {"rgb_coarse": color.reshape(rays.o.shape), "depth_coarse": depth.reshape(rays.near.shape),
-                "alpha_coarse": weights.sum(-1).reshape(rays.near.shape), "weight_coarse": weights.reshape(*rays.near.shape, -1)}
+            sigma = sigma + noise * torch.randn_like(sigma)
+        alpha = 1.0 - torch.exp(-torch.relu(sigma) * dt[:, None])
+        through = torch.cumprod(1 - alpha + 1e-10, dim=-1)            # transmittance after each sample
+        weights = alpha * torch.cat([torch.ones_like(through[:, :1]), through[:, :-1]], dim=-1)
+        background = bg_color.reshape(-1, 3) if bg_color is not None else 1.0
+        image = (weights[..., None] * rgb).sum(dim=-2) + through[:, -1:] * background
+        like = rays.near.shape
+        return {"rgb_coarse": image.reshape(rays.o.shape), "depth_coarse": (weights * z).sum(dim=-1).reshape(like),
+                "alpha_coarse": weights.sum(dim=-1).reshape(like), "weight_coarse": weights.reshape(*like, -1)}
 
     def render_train(self, rays, model, noise, bg_color, jitter=None, noise_tensor=None):
         bound = _unwrap(model)
