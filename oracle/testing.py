@@ -7,6 +7,22 @@ from . import scene as oscene
 
 _CACHE = {}
 
+# every 4th pixel of the 512x512 demo camera: the ray set of tests/golden/oracle_frames_golden.npz
+GOLDEN_PIXELS = (np.arange(0, 512, 4)[:, None] * 512 + np.arange(0, 512, 4)[None]).ravel()
+
+
+def load_golden_frame(frame_idx):
+    """committed end-to-end oracle image of one pose (tests/golden/make_oracle_frames_golden.py) -> dict like
+    oracle.render.render_test's result, plus the occupancy field it was rendered with"""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "oracle_frames_golden.npz")
+    z = np.load(path)
+    assert frame_idx in list(z["frames"]), (frame_idx, z["frames"])
+    assert np.array_equal(z["pixel_index"], GOLDEN_PIXELS)
+    ref = {k: z[f"{frame_idx}/{k}"] for k in ("rgb", "alpha", "depth", "counter")}
+    ref["occ"] = np.unpackbits(z[f"{frame_idx}/occ_bits"])[:64 ** 3].reshape(64, 64, 64).astype(bool)
+    return ref
+
 
 def oracle_scene(frame_idx=0, track="male-3-casual", sigma_in=100.0):
     key = (frame_idx, track, sigma_in)
