@@ -85,3 +85,61 @@ def test_smpl_deformer_inverse_transforms_map_posed_vertices_to_the_template():
     assert bb.shape == (2, 3) and (bb[1] > bb[0]).all()
     with pytest.raises(ValueError):
         SMPLDeformer(smpl_data=synthetic.smpl_dict_cached(0), k=3)
+
+
+def test_smpl_deformer_host_logic_against_literal_restatement(monkeypatch):
+    """SMPLDeformer.deform / __call__ with the CUDA nearest-vertex kernel replaced by a brute-force torch search: the
+    gathered inverse transforms, the validity rule, the train / eval fill values and the gradient path to the pose equal
+    a literal restatement of smpl_deformer.py:60-132"""
+    from instantavatar_b200 import ops, synthetic
+    from instantavatar_b200.deformers.smpl_deformer import SMPLDeformer
+
+    def knn1_bruteforce(pts, verts):
+        diff = pts[:, None, :] - verts[None]
+        return (diff * diff).sum(-1).min(dim=1)
+
+    monkeypatch.setattr(ops, "knn1", knn1_bruteforce)
+    d = SMPLDeformer(smpl_data=synthetic.smpl_dict_cached(0), threshold=0.05)
+    pose = {k: torch.from_numpy(v) for k, v in synthetic.load_pose(20).items()}
+    pose["body_pose"].requires_grad_(True)
+    d.prepare_deformer(pose)
+    # literal restatement of prepare_deformer
+    out = d.body_model(betas=pose["betas"], body_pose=pose["body_pose"], global_orient=pose["global_orient"], transl=pose["transl"])
+    s2w = out.A[:, 0]
+    w2s = torch.inverse(s2w)
+    T_inv = torch.inverse(out.T.float()).clone() @ s2w[:, None]
+    T_inv[..., :3, 3] += d.pose_offset_t - out.pose_offsets
+    T_inv[..., :3, 3] += d.shape_offset_t - out.shape_offsets
+    T_inv = d.T_template @ T_inv
+    verts = (out.vertices @ w2s[:, :3, :3].permute(0, 2, 1)) + w2s[:, None, :3, 3]
+    assert torch.allclose(d.T_inv, T_inv, atol=1e-6) and torch.allclose(d.vertices, verts, atol=1e-6)
+    g = torch.Generator().manual_seed(0)
+    v = verts[0].detach()
+    pts = torch.cat([v[torch.randint(0, v.shape[0], (400,), generator=g)] + 0.01 * torch.randn(400, 3, generator=g),
+                     torch.rand(100, 3, generator=g) * 2 - 1])
+    # literal deform
+    dist_sq, idx = knn1_bruteforce(pts, v)
+    valid_ref = dist_sq < 0.05 ** 2
+    Tv = T_inv[0][idx]
+    cano_ref = (Tv[..., :3, :3] @ pts[..., None]).squeeze(-1) + Tv[..., :3, 3]
+    cano, valid = d.deform(pts)
+    assert torch.equal(valid, valid_ref) and torch.allclose(cano, cano_ref, atol=1e-6)
+    assert valid[:400].float().mean() > 0.9 and not valid.all()
+
+    def model(x, _):
+        return torch.sigmoid(x), x.sum(-1) * 10
+
+    rgb_t, sig_t = d(pts, model, eval_mode=False)
+    rgb_e, sig_e = d(pts, model, eval_mode=True)
+    assert torch.all(sig_t[~valid] == -1e5) and torch.all(sig_e[~valid] == 0) and torch.all(rgb_t[~valid] == 0)
+    assert torch.allclose(sig_t[valid], cano_ref[valid].sum(-1) * 10, atol=1e-5) and torch.allclose(rgb_e[valid], torch.sigmoid(cano_ref[valid]), atol=1e-6)
+    # non-finite network outputs count as empty space in training mode only
+    def bad_model(x, _):
+        s = x.sum(-1)
+        s = torch.where(torch.arange(len(s)) == 0, torch.full_like(s, float("nan")), s)
+        return torch.sigmoid(x), s
+    _, sig_bad = d(pts, bad_model, eval_mode=False)
+    first = valid.nonzero()[0, 0]
+    assert sig_bad[first] == -1e5
+    sig_t[valid].sum().backward()
+    assert pose["body_pose"].grad is not None and pose["body_pose"].grad.abs().sum() > 0
