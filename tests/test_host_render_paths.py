@@ -98,3 +98,57 @@ def test_training_march_and_compositing_match_the_oracle(cpu_ops):
     np.testing.assert_allclose(_np(out["rgb_coarse"]).reshape(-1, 3), ref["rgb"], atol=5e-6)
     np.testing.assert_allclose(_np(out["alpha_coarse"]).reshape(-1), ref["alpha"], atol=5e-6)
     np.testing.assert_allclose(_np(out["depth_coarse"]).reshape(-1), ref["depth"], atol=5e-5)
+
+
+def test_density_grid_update_and_initialize_host_logic(monkeypatch):
+    """DensityGrid.update (EMA of the cached density, 1 - exp(-0.01 d) regulariser input, `valid` selection) and the generic
+    DensityGrid.initialize loop against oracle.render.density_grid_update / density_grid_initialize, with the CUDA grid
+    post-processing replaced by the oracle's (density_grid.py:46-125)"""
+    from instantavatar_b200.models.structures.density_grid import DensityGrid
+
+    def occupancy_build(density, bits=None, want_field=True, workspace=None, field=None):
+        f = torch.from_numpy(orender._field_from_density(_np(density).astype(f32)))
+        if field is not None:
+            field.copy_(f)
+        else:
+            field = f
+        return field, torch.zeros(64 ** 3 // 32 + 8, dtype=torch.int32)
+
+    monkeypatch.setattr(ops, "occupancy_build", occupancy_build)
+    rng = np.random.default_rng(5)
+    centres = rng.uniform(-0.6, 0.6, (3, 3)).astype(f32)
+
+    def blob_np(p, scale=40.0):    # a smooth density with three blobs; train mode: may be negative
+        d2 = ((p[:, None, :] - centres[None]) ** 2).sum(-1)
+        sig = (scale * np.exp(-d2 / 0.02).sum(-1) - 2.0).astype(f32)
+        return np.zeros((len(p), 3), f32), sig
+
+    def deformer(pts, net, eval_mode=True):
+        rgb, sig = blob_np(_np(pts))
+        return torch.from_numpy(rgb), torch.from_numpy(sig)
+
+    aabb_np = [np.array([-1.25, -1.55, -1.25], f32), np.array([1.25, 0.95, 1.25], f32)]
+    grid = DensityGrid(64, [torch.from_numpy(a) for a in aabb_np], device="cpu")
+    cached = np.zeros((64, 64, 64), f32); old = np.zeros((64, 64, 64), bool)
+    for step in (0, 600):   # `valid` is the new field before step 500 and the previous one afterwards
+        jit = rng.random((64, 64, 64, 3), dtype=f32)
+        dens, valid = grid.update(deformer, None, step, torch.from_numpy(jit))
+        ref_reg, ref_valid, cached, field = orender.density_grid_update(lambda p: blob_np(p), aabb_np, jit, cached, old, step)
+        np.testing.assert_allclose(_np(dens), ref_reg, atol=1e-6)
+        np.testing.assert_array_equal(_np(valid), ref_valid)
+        np.testing.assert_array_equal(_np(grid.density_field), field)
+        np.testing.assert_allclose(_np(grid.density_cached), cached, atol=1e-6)
+        old = field
+        assert field.sum() > 50
+    # generic initialize (foreign deformer): max over the jitter passes, then the same post-processing
+    class Foreign:
+        def get_bbox_deformed(self):
+            return [torch.from_numpy(a) for a in aabb_np]
+        def __call__(self, pts, net, eval_mode=True):
+            rgb, sig = blob_np(_np(pts))
+            return torch.from_numpy(rgb), torch.from_numpy(np.maximum(sig, 0))   # eval mode: invalid -> 0
+    g2 = DensityGrid(64, device="cpu")
+    jits = rng.random((5, 64, 64, 64, 3), dtype=f32)
+    g2.initialize(Foreign(), None, jitters=torch.from_numpy(jits))
+    ref_field, _ = orender.density_grid_initialize(lambda p: (blob_np(p)[0], np.maximum(blob_np(p)[1], 0)), aabb_np, jits, 64)
+    np.testing.assert_array_equal(_np(g2.density_field), ref_field)
