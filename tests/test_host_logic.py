@@ -143,3 +143,38 @@ def test_smpl_deformer_host_logic_against_literal_restatement(monkeypatch):
     assert sig_bad[first] == -1e5
     sig_t[valid].sum().backward()
     assert pose["body_pose"].grad is not None and pose["body_pose"].grad.abs().sum() > 0
+
+
+def test_snarf_deformer_frame_state_matches_oracle(monkeypatch):
+    """SNARFDeformer.initialize / prepare_deformer (torch SMPL path) against the numpy oracle's SubjectOracle /
+    prepare_frame (snarf_deformer.py:41-107): canonical bbox, voxel-grid normalisation, bone transforms, root transform,
+    posed vertices; the CUDA field kernel is replaced by the oracle's C restatement."""
+    from instantavatar_b200 import ops, synthetic
+    from instantavatar_b200.deformers.snarf_deformer import SNARFDeformer
+    from oracle import capi
+    from oracle import testing as scene_util
+
+    sc = scene_util.oracle_scene(0)
+    subj, fr = sc["subj"], sc["frame"]
+
+    def precompute(voxel_w, tfs, offset_k, scale_k, want_voxel_d=True):
+        w = voxel_w.reshape(24, *voxel_w.shape[-3:]).numpy()
+        vd, vJ = capi.precompute(w, tfs.detach().reshape(24, 4, 4).numpy(), offset_k.reshape(3).numpy(), scale_k.reshape(3).numpy(), *w.shape[1:])
+        v = vd.reshape(3, -1)
+        return torch.from_numpy(vJ), torch.from_numpy(vd), torch.from_numpy(np.concatenate([v.min(1), v.max(1)]))
+
+    monkeypatch.setattr(ops, "precompute", precompute)
+    d = SNARFDeformer(None, "male", {"cano_pose": "A_pose", "resolution": 128}, smpl_data=synthetic.smpl_dict_cached(0))
+    d.fast_prepare = False   # torch SMPL forward (the one-launch kernel needs a GPU)
+    pose = {k: torch.from_numpy(v) for k, v in sc["pose"].items()}
+    d.initialize(pose["betas"], torch.device("cpu"), lbs_voxel=torch.from_numpy(subj.lbs_voxel))
+    d.initialized = True
+    d.prepare_deformer(pose)
+    np.testing.assert_allclose(d.bbox.numpy(), subj.bbox, atol=1e-6)
+    np.testing.assert_allclose(d.deformer.offset_kernel.reshape(3).numpy(), subj.offset_kernel, atol=1e-7)
+    np.testing.assert_allclose(d.deformer.scale_kernel.reshape(3).numpy(), subj.scale_kernel, rtol=1e-6)
+    np.testing.assert_allclose(d.tfs[0].numpy(), fr["tfs"], atol=5e-6)
+    np.testing.assert_allclose(d.w2s[0].numpy(), fr["w2s"], atol=5e-6)
+    np.testing.assert_allclose(d.vertices[0].numpy(), fr["vertices"], atol=1e-5)
+    lo, hi = d.get_bbox_deformed()
+    np.testing.assert_allclose(torch.stack([lo, hi]).numpy(), fr["bbox_deformed"], atol=1e-5)
