@@ -1,0 +1,1 @@
+"""alias of instantavatar_b200.models.networks"""

@@ -93,6 +93,7 @@ class _DeformQueryTrain(torch.autograd.Function):
         ctx.pose = (pts.reshape(-1, 3).float().contiguous(), lbs_voxel, tfs.shape) if tfs is not None and tfs.requires_grad else None
         ctx.shapes = (enc_params.shape, col_params.shape)
         ctx.accum = accum
+        ctx.frozen = not (enc_params.requires_grad or col_params.requires_grad)  # pose refinement with a fixed network
         return rgb, sigma
 
     @staticmethod
@@ -105,7 +106,11 @@ class _DeformQueryTrain(torch.autograd.Function):
         count = torch.full((1,), xc.shape[0], device=dev, dtype=torch.int32)
         pose = ctx.pose
         denc = torch.empty((xc.shape[0], 32), device=dev, dtype=torch.float32) if pose is not None else None
-        if ctx.accum is not None:
+        if ctx.frozen:
+            if pose is None:
+                return (None,) * 7
+            g_enc = g_col = None  # ia_ngp_backward then only exports d loss / d (hash features) for the pose gradient
+        elif ctx.accum is not None:
             g_enc, g_col = ctx.accum
         else:
             g_enc = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32)
@@ -116,7 +121,7 @@ class _DeformQueryTrain(torch.autograd.Function):
             g_tfs = torch.zeros((24, 4, 4), device=dev, dtype=torch.float32)
             ops.pose_grad(ctx.scene, pose[1], pose[0], best.to(torch.int8).contiguous(), denc, count, g_tfs)
             g_tfs = g_tfs.reshape(pose[2])
-        if ctx.accum is not None:
+        if ctx.accum is not None or ctx.frozen:
             return (None,) * 5 + (g_tfs, None)
         return g_enc, g_col, None, None, None, g_tfs, None
 

@@ -814,15 +814,15 @@ int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d
     int* ws_cost = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + 256);
     int* ws_order = ws_cost + (n_rays + 1);
     const size_t smem = sizeof(RenderSmem<kRenderWarps>);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
         IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set.set();
     }
     const int rpw = g_render_rays;
     const int n_tiles = (n_rays + rpw - 1) / rpw;
@@ -861,10 +861,10 @@ int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode
 static int launch_query(QueryArgs& a, cudaStream_t stream) {
     const int n = a.n;
     const size_t smem = sizeof(QuerySmem<kQueryWarps>);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
         IA_CHECK_CUDA(cudaFuncSetAttribute(deform_query_kernel<kQueryWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set.set();
     }
     const int n_batches = a.grid_aabb ? (a.G * a.G * a.G + (32 / a.passes) - 1) / (32 / a.passes) : (n + 31) / 32;
     int grid = sm_count();

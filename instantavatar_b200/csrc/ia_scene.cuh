@@ -29,16 +29,6 @@ static float filter_threshold() {
     return cf;
 }
 
-inline int sm_count() {
-    static int g_sm_count = 0;
-    if (!g_sm_count) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return g_sm_count;
-}
-
 // ================================================================================================
 // per-CTA prologue shared by the fused kernels: stage per-frame constants in shared memory
 // ================================================================================================

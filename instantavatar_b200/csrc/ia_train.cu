@@ -968,12 +968,12 @@ int ia_train_fwd(const IaScene* scene, const float* rays_o, const float* rays_d,
     IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
     constexpr int kW = 10;
     const size_t smem = sizeof(TrainSmem<kW>);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
         IA_CHECK_CUDA(cudaFuncSetAttribute(train_fwd_kernel<kW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IA_CHECK_CUDA(cudaFuncSetAttribute(train_fwd_kernel<kW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IA_CHECK_CUDA(cudaFuncSetAttribute(train_fwd_kernel<kW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set.set();
     }
     const int kR = ia_train_rays_per_warp();
     const int n_tiles = (n_rays + kR - 1) / kR;
@@ -1026,10 +1026,10 @@ int ia_ngp_backward(const IaScene* scene, const float* xc, const float* dsigma, 
     a.grad_enc = grad_enc; a.scratch = reinterpret_cast<__half*>(scratch); a.denc_out = denc_out;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = sizeof(BwdSmem);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
         IA_CHECK_CUDA(cudaFuncSetAttribute(ngp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set.set();
     }
     const int sms = sm_count();
     if (sms <= 0) return set_err(IA_ECUDA, "no CUDA device%s");

@@ -240,12 +240,21 @@ class SNARFDeformer:
         pts = pts.reshape(-1, 3).type(self.dtype).contiguous()
         if isinstance(model, NeRFNGPNet):
             model.initialize(self.bbox)
-            if eval_mode or not torch.is_grad_enabled() or not model.encoder.params.requires_grad:
+            # differentiable path (deform_train, snarf_deformer.py:143-159) whenever something upstream can receive a
+            # gradient: either parameter tensor of the network, or the bone transforms (pose refinement with a frozen net)
+            wants_grad = (model.encoder.params.requires_grad or model.color_net.params.requires_grad
+                          or (torch.is_tensor(self.tfs) and self.tfs.requires_grad))
+            if eval_mode or not torch.is_grad_enabled() or not wants_grad:
                 rgb, sigma = ops.deform_query(self.scene(model), pts, eval_mode)
                 return rgb, sigma
             from ..autograd import deform_query_train
             return deform_query_train(self, model, pts)
-        # legacy contract: any callable model(x, d) -> (rgb, sigma)
+        # legacy contract: any callable model(x, d) -> (rgb, sigma).  The roots come from the fine-grained Broyden operator
+        # and carry no autograd history: a foreign model gets parameter gradients through `model(xc)` but NO pose gradient
+        # (the implicit-differentiation correction of deformer_torch.py:50-67 exists only on the fused NeRFNGPNet path).
+        if not eval_mode and torch.is_grad_enabled() and torch.is_tensor(self.tfs) and self.tfs.requires_grad:
+            raise NotImplementedError("pose gradients (tfs.requires_grad) are only implemented for NeRFNGPNet models; "
+                                      "detach the SMPL parameters or use NeRFNGPNet")
         xc, valid = self.deform(pts, eval_mode)
         rgb_c = torch.zeros_like(xc)
         sig_c = torch.zeros_like(xc[..., 0]) if eval_mode else -torch.ones_like(xc[..., 0]) * 1e5

@@ -23,27 +23,60 @@ class Rays:  # models/structures/utils.py:5-11
 
 
 class DNeRFModel(torch.nn.Module):
-    def __init__(self, smpl_data=None, model_path=None, gender="male", n_train_frames=1, device="cuda", net_seed=1337,
-                 deformer_opt=None):
+    def __init__(self, opt=None, datamodule=None, smpl_data=None, model_path=None, gender="male", n_train_frames=1, device="cuda",
+                 net_seed=1337, deformer_opt=None):
+        """Two forms.  The reference's (DNeRF.py:18-30): `DNeRFModel(opt, datamodule)` with `opt` the `model.opt` node of
+        confs/SNARF_NGP*.yaml (network / deformer / renderer / loss given as `_target_` configs, optimizer, scheduler,
+        optimize_SMPL) and `datamodule.trainset` supplying `len()` and `get_SMPL_params()`.  Or keyword arguments only
+        (tests, bench): the SNARF_NGP.yaml defaults with a synthetic SMPL dictionary."""
         super().__init__()
-        self.net_coarse = NeRFNGPNet(None, seed=net_seed).to(device)
-        self.deformer = SNARFDeformer(model_path, gender, deformer_opt or {"cano_pose": "A_pose", "resolution": 128},
-                                      smpl_data=smpl_data)
+        from ..optim import FusedAdam, GradScaler
+        from ..utils_loss import NeRFLoss
+        lr, betas, eps, max_epochs = 1e-2, (0.9, 0.99), 1e-15, 30
+        pose_cfg = None
+        if opt is not None:
+            from ..config import Cfg, instantiate
+            opt = Cfg.wrap(dict(opt))
+            self.net_coarse = instantiate(opt["network"]).to(device)
+            self.deformer = instantiate(opt["deformer"], **({"smpl_data": smpl_data} if smpl_data is not None else {}))
+            self.loss_fn = instantiate(opt["loss"]) if "loss" in opt else NeRFLoss()
+            self.renderer = instantiate(opt["renderer"], smpl_init=opt.get("smpl_init", False), device=device)
+            n_train_frames = len(datamodule.trainset) if datamodule is not None else n_train_frames
+            o = opt.get("optimizer", {})
+            lr, betas, eps = float(o.get("lr", lr)), tuple(o.get("betas", betas)), float(o.get("eps", eps))
+            max_epochs = int(opt.get("scheduler", {}).get("max_epochs", max_epochs))
+            pose_cfg = opt.get("optimize_SMPL", None)
+        else:
+            self.net_coarse = NeRFNGPNet(None, seed=net_seed).to(device)
+            self.deformer = SNARFDeformer(model_path, gender, deformer_opt or {"cano_pose": "A_pose", "resolution": 128},
+                                          smpl_data=smpl_data)
+            self.loss_fn = NeRFLoss()
+            self.renderer = Raymarcher(256, 291600, device=device)
+        self.opt, self.datamodule = opt, datamodule
         self.deformer.body_model = self.deformer.body_model.to(device)
-        self.renderer = Raymarcher(256, 291600, device=device)
         self.renderer.initialize(n_train_frames)
         self.global_step = 0
         self.image_width = 0
-        from ..optim import FusedAdam, GradScaler
-        from ..utils_loss import NeRFLoss
-        self.loss_fn = NeRFLoss()
-        self.optimizer = FusedAdam(self.net_coarse, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, max_epochs=30)
+        self.optimizer = FusedAdam(self.net_coarse, lr=lr, betas=betas, eps=eps, max_epochs=max_epochs)
+        self._pose_cfg = pose_cfg
         self.scaler = GradScaler(device)
         self.world_size = 1
         self.fused_loss = True  # NeRFLoss forward/backward in one kernel (False: torch autograd through utils_loss.NeRFLoss)
         self.SMPL_param = None
         self.pose_optimizer = None
         self.is_refine = False
+        if self._pose_cfg is not None and self._pose_cfg.get("enable", False):  # DNeRF.py:23-24
+            if datamodule is None:
+                raise ValueError("optimize_SMPL.enable needs a datamodule whose trainset provides get_SMPL_params()")
+            self.enable_pose_optimisation(datamodule.trainset.get_SMPL_params(), lr=float(self._pose_cfg.get("lr", 5e-4)),
+                                          is_refine=bool(self._pose_cfg.get("is_refine", False)))
+
+    def scheduler_step(self):
+        """LambdaLR (1 - epoch / max_epochs)^1.5 of DNeRF.py:52-55: ONE schedule for every parameter group, the SMPL
+        pose group (base lr 5e-4) included; the reference steps it in on_validation_epoch_end (DNeRF.py:163-166)."""
+        self.optimizer.scheduler_step()
+        if self.pose_optimizer is not None:
+            self.pose_optimizer.set_lr_factor(self.optimizer.lr_factor)
 
     def enable_pose_optimisation(self, smpl_params: dict, lr: float = 5e-4, is_refine: bool = False):
         """DNeRF.py:23-24,40-51 (`opt.optimize_SMPL.enable`): per-frame SMPL parameters become learnable embeddings with
@@ -54,7 +87,8 @@ class DNeRFModel(torch.nn.Module):
         self.SMPL_param = SMPLParamEmbedding(**{k: torch.as_tensor(v) for k, v in smpl_params.items()}).to(dev)
         group = [p for n, p in self.SMPL_param.named_parameters() if not n.startswith("betas")]
         from ..optim import DeviceAdam
-        self.pose_optimizer = DeviceAdam(group, lr=lr, betas=(0.9, 0.99), eps=1e-15)
+        self.pose_optimizer = DeviceAdam(group, lr=lr, betas=self.optimizer.betas, eps=self.optimizer.eps)
+        self.pose_optimizer.set_lr_factor(self.optimizer.lr_factor)
         self.is_refine = is_refine
 
     def freeze_network(self, frozen: bool = True):

@@ -381,3 +381,43 @@ def knn1(pts, verts):
     _lib.count(1); check(lib().ia_knn1(ptr(pts, f32), C.c_int(n), ptr(verts, f32), C.c_int(verts.shape[0]), ptr(idx, torch.int32), ptr(d2),
                                        stream()))
     return d2, idx.long()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# device guard: every operator launches on the current stream OF THE DEVICE ITS TENSORS LIVE ON (one process may hold
+# tensors on several GPUs; function attributes and SM counts are cached per device inside the library)
+# ------------------------------------------------------------------------------------------------------------------
+def _device_of(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if torch.is_tensor(a):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, Scene):
+            for t in (a.field, a.table_h, a.tfs, a.occ_bits):
+                if t is not None and t.is_cuda:
+                    return t.device
+        elif isinstance(a, dict):
+            for v in a.values():
+                if torch.is_tensor(v) and v.is_cuda:
+                    return v.device
+    return None
+
+
+def _on_device(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _device_of(args, kwargs)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and getattr(_fn, "__module__", None) == __name__ and not _name.startswith("_") \
+            and _name not in ("Scene", "set_option", "new_stats", "stats_dict") and isinstance(_fn, type(_on_device)):
+        globals()[_name] = _on_device(_fn)
+del _name, _fn

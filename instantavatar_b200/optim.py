@@ -44,8 +44,12 @@ class FusedAdam:
         self.state_t = torch.tensor([lr, betas[0], betas[1], eps, 0.0, 1.0, 1.0, 1.0], dtype=torch.float32).to(dev)
 
     @property
-    def lr(self):  # LambdaLR of DNeRF.py:52-55, stepped in on_validation_epoch_end only
-        return self.base_lr * (1 - self.epoch / self.max_epochs) ** 1.5
+    def lr_factor(self):  # LambdaLR of DNeRF.py:52-55, stepped in on_validation_epoch_end only
+        return (1 - self.epoch / self.max_epochs) ** 1.5
+
+    @property
+    def lr(self):
+        return self.base_lr * self.lr_factor
 
     @property
     def step_count(self):
@@ -85,7 +89,21 @@ class DeviceAdam:
         self.state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in self.params]
         dev = self.params[0].device
         self.state_t = torch.tensor([lr, betas[0], betas[1], eps, 0.0, 1.0, 1.0, 1.0], dtype=torch.float32).to(dev)
-        self.param_groups = [{"params": self.params, "lr": lr}]
+        self.base_lr = lr
+
+    @property
+    def lr(self):
+        """current learning rate (host copy of the device-resident value the kernels read)"""
+        return self._lr if hasattr(self, "_lr") else self.base_lr
+
+    def set_lr(self, lr: float):
+        """the learning rate lives in the device state the kernels read (state_t[0]); written without a host sync"""
+        self._lr = float(lr)
+        self.state_t[0:1].fill_(self._lr)
+
+    def set_lr_factor(self, factor: float):
+        """LambdaLR semantics: lr = base_lr * factor (DNeRF.py:52-55 applies one lambda to all groups)"""
+        self.set_lr(self.base_lr * float(factor))
 
     def zero_grad(self, set_to_none=False):
         for p in self.params:

@@ -46,6 +46,11 @@ class Raymarcher(torch.nn.Module):
         super().__init__()
         if MAX_SAMPLES != 256:
             raise ValueError("the fused kernels are built for MAX_SAMPLES = 256 (confs/renderer/raymarcher_acc.yaml)")
+        if smpl_init:
+            # demo.yaml: one DensityGrid(smpl_init=True) per training frame, voxelised from the SMPL mesh with kaolin
+            # (raymarcher_acc.py:57-66, density_grid.py:52-68) -- kaolin is absent; fail instead of silently training
+            # with the plain single-grid semantics
+            raise NotImplementedError("Raymarcher(smpl_init=True) needs kaolin (reference demo.yaml only); out of scope, DESIGN.md §8")
         self.MAX_SAMPLES = MAX_SAMPLES
         self.MAX_BATCH_SIZE = MAX_BATCH_SIZE
         self.aabb = torch.tensor([[-1.25, -1.55, -1.25], [1.25, 0.95, 1.25]]).float().to(device)
