@@ -152,6 +152,12 @@ def load_pose(frame: int = 0, track: str = "male-3-casual") -> dict:
     }
 
 
+def track_frames(track: str = "male-3-casual") -> list:
+    """frame numbers of `track` held by tests/golden/poses.npz"""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "poses.npz")
+    return [int(f) for f in np.load(path)[f"{track}/frames"]]
+
+
 def demo_camera_rays(H: int = 512, W: int = 512):
     """Rays of the reference demo camera (novel_view.py:27-44: f=2000 px at 1080^2, c2w = I)
     rescaled to HxW, generated as datasets/peoplesnapshot.py:12-25 does."""

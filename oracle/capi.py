@@ -80,12 +80,13 @@ def hashgrid_layout():
 
 
 def ngp_forward(x, center, scale, enc_params, col_params, emulate=True, want_feat=False):
+    """emulate: 0/False fp32, 1/True fp16 values + fp32 accumulation (the product's model), 2 tiny-cuda-nn-like fp16 accumulation"""
     x = _c(x).reshape(-1, 3); P = len(x)
     center, scale, enc_params, col_params = _c(center), _c(scale), _c(enc_params), _c(col_params)
     sigma = np.empty(P, f32); rgb = np.empty((P, 3), f32)
     feat = np.empty((P, 16), f32) if want_feat else None
     lib().orc_ngp_forward(_p(x), C.c_long(P), _p(center), _p(scale), _p(enc_params), _p(col_params),
-                          C.c_int(1 if emulate else 0), _p(sigma), _p(rgb), _p(feat) if want_feat else None)
+                          C.c_int(int(emulate)), _p(sigma), _p(rgb), _p(feat) if want_feat else None)
     return (sigma, rgb, feat) if want_feat else (sigma, rgb)
 
 

@@ -85,13 +85,20 @@ class SubjectOracle:
             lbs_voxel = query_weights_smpl(g, out["vertices"], self.smpl.lbs_weights, resolution)
         self.lbs_voxel = np.ascontiguousarray(lbs_voxel, f32)  # [24,d,h,w]
 
-    def prepare_frame(self, pose: dict):
-        """snarf_deformer.py:71-93 -> dict(tfs, w2s, voxel_d, voxel_J, vertices, bbox_deformed)."""
+    def prepare_frame(self, pose: dict, tfs: np.ndarray | None = None, w2s: np.ndarray | None = None):
+        """snarf_deformer.py:71-93 -> dict(tfs, w2s, voxel_d, voxel_J, vertices, bbox_deformed).
+        `tfs` / `w2s` given: continue from those bone transforms instead of this file's SMPL algebra -- the public-API
+        parity tests hand over the product's transforms (equal to the ones computed here to ~1e-6: another summation
+        order of the same kinematic chain) so that everything downstream is compared on identical inputs."""
         out = self.smpl.forward(self.betas, pose["body_pose"], pose["global_orient"], pose["transl"])
         A = out["A"].astype(f32)
         s2w = A[0]
-        w2s = np.linalg.inv(s2w).astype(f32)
-        tfs = (w2s[None] @ A @ self.tfs_inv_t).astype(f32)  # :86
+        if w2s is None:
+            w2s = np.linalg.inv(s2w).astype(f32)
+        w2s = np.asarray(w2s, f32).reshape(4, 4)
+        if tfs is None:
+            tfs = (w2s[None] @ A @ self.tfs_inv_t).astype(f32)  # :86
+        tfs = np.ascontiguousarray(np.asarray(tfs, f32).reshape(24, 4, 4))
         d, h, w = self.dhw
         voxel_d, voxel_J = capi.precompute(self.lbs_voxel, tfs, self.offset_kernel, self.scale_kernel, d, h, w)
         verts = out["vertices"] @ w2s[:3, :3].T + w2s[:3, 3]

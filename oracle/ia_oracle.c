@@ -280,8 +280,13 @@ ORC_API void orc_filter(const float *xc, const uint8_t *valid, long M, int I, ui
 /* no biases, row-major [out,in] weights, ReLU hidden).  Numerics model      */
 /* (documented in DESIGN.md §3): tables/weights/activations are fp16 values, */
 /* every dot product and the 8-corner interpolation accumulate in fp32 and   */
-/* are rounded to fp16 at layer boundaries ("emulate" = 1).  emulate = 0     */
-/* keeps everything fp32 (for reporting the fp16 model's deviation).         */
+/* are rounded to fp16 at layer boundaries ("emulate" = 1, the model the CUDA */
+/* product implements).  emulate = 0 keeps everything fp32.  emulate = 2      */
+/* restates tiny-cuda-nn's own rounding as far as it is known [TCNN-MEM]:     */
+/* fp16 corner terms + fp16 running sum in the hash interpolation, fp16       */
+/* accumulator fragments (rounded per 16-wide k-block) in every MLP layer.    */
+/* It exists to BOUND how far real tcnn can be from mode 1; the deltas are   */
+/* committed in tests/golden/ngp_kat_golden.npz and profiles/parity_r2.json. */
 /* ------------------------------------------------------------------------ */
 #define ORC_NLEVELS 16
 
@@ -334,8 +339,15 @@ static void hash_encode_one(const float *x, const float *table, int emulate, con
             const float *e = table + ((size_t)off[l] + idx) * 2;
             float f0 = e[0], f1 = e[1];
             if (emulate) { f0 = h2f_round(f0); f1 = h2f_round(f1); }
-            a0 = fmaf(wt, f0, a0);
-            a1 = fmaf(wt, f1, a1);
+            if (emulate == 2) {
+                /* tiny-cuda-nn v1.6 kernel_grid [TCNN-MEM]: `result[f] += (T)(weight * (float)val[f])` with T = __half:
+                 * every corner term is rounded to fp16 and the running sum is an fp16 addition */
+                a0 = h2f_round(a0 + h2f_round(wt * f0));
+                a1 = h2f_round(a1 + h2f_round(wt * f1));
+            } else {
+                a0 = fmaf(wt, f0, a0);
+                a1 = fmaf(wt, f1, a1);
+            }
         }
         if (emulate) { a0 = h2f_round(a0); a1 = h2f_round(a1); }
         enc[2 * l + 0] = a0;
@@ -344,16 +356,27 @@ static void hash_encode_one(const float *x, const float *table, int emulate, con
 }
 
 static inline void dense_layer(const float *Wt, int nout, int nin, const float *in, float *out, int relu,
-                               int emulate) {
+                               int emulate, int round_out) {
     for (int j = 0; j < nout; j++) {
         float acc = 0.f;
-        for (int k = 0; k < nin; k++) {
-            float wv = Wt[j * nin + k];
-            if (emulate) wv = h2f_round(wv);
-            acc = fmaf(wv, in[k], acc);
+        if (emulate == 2) {
+            /* tiny-cuda-nn FullyFusedMLP [TCNN-MEM]: wmma m16n16k16 with __half accumulator fragments -- the running sum
+             * is rounded to fp16 after every 16-wide k-block (what happens inside one block is the tensor core's
+             * business; modelled as an fp32 sum of the 16 products) */
+            for (int kb = 0; kb < nin; kb += 16) {
+                float part = 0.f;
+                for (int k = kb; k < kb + 16 && k < nin; k++) part = fmaf(h2f_round(Wt[j * nin + k]), in[k], part);
+                acc = h2f_round(acc + part);
+            }
+        } else {
+            for (int k = 0; k < nin; k++) {
+                float wv = Wt[j * nin + k];
+                if (emulate) wv = h2f_round(wv);
+                acc = fmaf(wv, in[k], acc);
+            }
         }
         if (relu) acc = acc > 0.f ? acc : 0.f;
-        out[j] = emulate ? h2f_round(acc) : acc;
+        out[j] = round_out ? h2f_round(acc) : acc;
     }
 }
 
@@ -379,15 +402,17 @@ ORC_API void orc_ngp_forward(const float *x, long P, const float *center, const 
         }
         float enc[32], h1[64], o16[16], cin[16], h2[64], h3[64], o3[16];
         hash_encode_one(xn, grid, emulate, res, lscale, size, off, enc);
-        dense_layer(W1, 64, 32, enc, h1, 1, emulate);
-        dense_layer(W2, 16, 64, h1, o16, 0, emulate);
+        dense_layer(W1, 64, 32, enc, h1, 1, emulate, emulate != 0);
+        dense_layer(W2, 16, 64, h1, o16, 0, emulate, emulate != 0);
         sigma[p] = o16[0]; /* ngp.py:80 raw, no activation */
         if (feat16) memcpy(feat16 + p * 16, o16, sizeof(o16));
         for (int k = 0; k < 15; k++) cin[k] = o16[k + 1];
         cin[15] = 1.0f; /* tcnn pads the 15-d input to 16 with ones */
-        dense_layer(W3, 64, 16, cin, h2, 1, emulate);
-        dense_layer(W4, 64, 64, h2, h3, 1, emulate);
-        dense_layer(W5, 16, 64, h3, o3, 0, 0);
+        dense_layer(W3, 64, 16, cin, h2, 1, emulate, emulate != 0);
+        dense_layer(W4, 64, 64, h2, h3, 1, emulate, emulate != 0);
+        /* fp16 weights in modes 1 and 2; the pre-sigmoid output stays fp32 in mode 1 (the product applies the sigmoid to its
+         * fp32 accumulators) and is an fp16 fragment in mode 2 (tcnn) */
+        dense_layer(W5, 16, 64, h3, o3, 0, emulate, emulate == 2);
         for (int c = 0; c < 3; c++) {
             float s = 1.0f / (1.0f + expf(-o3[c]));
             rgb[p * 3 + c] = emulate ? h2f_round(s) : s;

@@ -15,7 +15,9 @@ _CACHE_DIR = os.environ.get("IA_ORACLE_CACHE", "/tmp/ia_oracle_cache")
 
 
 def build_subject(resolution=128, track="male-3-casual", cache=True):
-    pose0 = synthetic.load_pose(0, track)
+    if track == "aist_demo":  # animate.py:100: the animation is rendered with the training subject's shape
+        track = "male-3-casual"
+    pose0 = synthetic.load_pose(synthetic.track_frames(track)[0], track)
     data = synthetic.smpl_dict_cached(0)
     lbs = None
     path = os.path.join(_CACHE_DIR, f"lbs_voxel_{track}_{resolution}.npy")

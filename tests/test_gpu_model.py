@@ -12,48 +12,72 @@ pytestmark = pytest.mark.gpu
 H = W = 128  # subsampled demo camera (every 4th pixel of the 512x512 frame)
 
 
-def make_model(frame=0):
+def make_model(frame=0, track="male-3-casual", step=4):
+    """DNeRFModel + one host batch: every `step`-th pixel of the 512x512 demo camera"""
     import torch
     from instantavatar_b200 import synthetic
     from instantavatar_b200.models.dnerf import DNeRFModel
     model = DNeRFModel(smpl_data=synthetic.smpl_dict_cached(0), device="cuda")
-    pose = synthetic.load_pose(frame)
+    pose = synthetic.load_pose(frame, track)
     o, d = synthetic.demo_camera_rays(512, 512)
-    idx = (np.arange(0, 512, 4)[:, None] * 512 + np.arange(0, 512, 4)[None]).ravel()
+    idx = (np.arange(0, 512, step)[:, None] * 512 + np.arange(0, 512, step)[None]).ravel()
     batch = {"rays_o": torch.from_numpy(o[idx][None]).cuda(), "rays_d": torch.from_numpy(d[idx][None]).cuda(),
              "near": torch.zeros((1, len(idx)), device="cuda"), "far": torch.ones((1, len(idx)), device="cuda")}
     batch.update({k: torch.from_numpy(v).cuda() for k, v in pose.items()})
     return model, batch, idx
 
 
-def test_prepare_and_render_image_matches_oracle_pipeline():
+def public_api_frame_vs_oracle(track, frame, step, min_hit):
+    """`DNeRFModel.render_image_fast` (the call a user of the reference makes, DNeRF.py:72-97) against the oracle's
+    pipeline on the same pose, subject, network and jitter.  The bone transforms are compared first (the product's
+    one-launch kernel and the oracle's numpy SMPL forward sum the same kinematic chain in different orders: ~1e-6);
+    the oracle then continues FROM THE PRODUCT'S transforms, so that field, occupancy grid, rays and image are compared
+    on identical inputs -- and the image must meet the 1e-3 contract with no ray exempted."""
     import torch
-    from instantavatar_b200 import synthetic
-    sc = scene_util.oracle_scene(0)
-    model, batch, idx = make_model(0)
+    sc0 = scene_util.oracle_scene(frame, track)
+    model, batch, idx = make_model(frame, track, step)
     model.eval()
+    side = 512 // step
     # feed the oracle's skinning-weight voxelisation so both sides start from the same subject state
-    model.deformer.initialize(batch["betas"], batch["betas"].device, lbs_voxel=torch.from_numpy(sc["subj"].lbs_voxel).cuda())
+    model.deformer.initialize(batch["betas"], batch["betas"].device, lbs_voxel=torch.from_numpy(sc0["subj"].lbs_voxel).cuda())
     model.deformer.initialized = True
     model.net_coarse.initialize(model.deformer.bbox)
-    model.net_coarse.load_flat_params(torch.from_numpy(sc["net"].enc).cuda(), torch.from_numpy(sc["net"].col).cuda())
-    jit = torch.from_numpy(sc["occ_jitter"]).cuda()
-    rgb, depth, alpha, counter = model.render_image_fast(dict(batch), (H, W), jitters=jit)
+    model.net_coarse.load_flat_params(torch.from_numpy(sc0["net"].enc).cuda(), torch.from_numpy(sc0["net"].col).cuda())
+    jit = torch.from_numpy(sc0["occ_jitter"]).cuda()
+    rgb, depth, alpha, counter = model.render_image_fast(dict(batch), (side, side), jitters=jit)
     torch.cuda.synchronize()
-    # per-frame state vs the oracle (different BLAS / op order in the SMPL forward: ~1e-6)
-    np.testing.assert_allclose(model.deformer.tfs[0].cpu().numpy(), sc["frame"]["tfs"], atol=5e-6)
-    np.testing.assert_allclose(model.deformer.bbox.cpu().numpy(), sc["subj"].bbox, atol=1e-5)
-    np.testing.assert_allclose(torch.stack(model.deformer.get_bbox_deformed()).cpu().numpy(), sc["frame"]["bbox_deformed"], atol=1e-5)
-    occ = model.renderer.density_grid_test.density_field.cpu().numpy()
-    assert (occ != sc["occ"]).mean() < 2e-3  # a few boundary cells may flip under the 1e-6 input perturbation
+    tfs, w2s = model.deformer.tfs[0].cpu().numpy(), model.deformer.w2s[0].cpu().numpy()
+    np.testing.assert_allclose(tfs, sc0["frame"]["tfs"], atol=5e-6)
+    np.testing.assert_allclose(w2s, sc0["frame"]["w2s"], atol=5e-6)
+    np.testing.assert_allclose(model.deformer.bbox.cpu().numpy(), sc0["subj"].bbox, atol=1e-5)
+    sc = scene_util.oracle_scene(frame, track, tfs=tfs, w2s=w2s)   # the oracle from the product's bone transforms on
     fr = sc["frame"]
+    np.testing.assert_array_equal(torch.stack(model.deformer.get_bbox_deformed()).cpu().numpy(), fr["bbox_deformed"])
+    occ = model.renderer.density_grid_test.density_field.cpu().numpy()
+    # identical geometry; the densities differ by an fp16 ulp in ~3 % of the network evaluations, which can move a cell
+    # whose density sits on the threshold (such a cell holds alpha < 0.01 samples, skipped by compositing)
+    assert (occ != sc["occ"]).sum() <= 4, int((occ != sc["occ"]).sum())
     o, d, near, far = oscene.camera_rays(fr, 512, 512)
     ref = orender.render_test(o[idx], d[idx], near[idx], far[idx], sc["occ"], fr["bbox_deformed"][0], fr["bbox_deformed"][1],
                               scene_util.oracle_model(sc, True))
-    a, r = alpha.reshape(-1).cpu().numpy(), rgb.reshape(-1, 3).cpu().numpy()
-    assert np.mean(np.abs(a - ref["alpha"]) > 2e-2) < 5e-3
-    assert np.mean(np.abs(r - ref["rgb"]).max(-1) > 2e-2) < 5e-3
-    assert np.abs(a - ref["alpha"]).mean() < 1e-3
+    got = {"rgb": rgb.reshape(-1, 3).cpu().numpy(), "alpha": alpha.reshape(-1).cpu().numpy()}
+    return scene_util.assert_render_contract(ref, got, allowed_threshold_flips=0, min_hit=min_hit, label=f"{track}/{frame} step {step}")
+
+
+def test_prepare_and_render_image_matches_oracle_pipeline():
+    public_api_frame_vs_oracle("male-3-casual", 0, 4, 600)
+
+
+def test_full_512x512_frame_meets_the_contract():
+    """BASELINE.json's headline configuration: every one of the 262 144 rays of the 512x512 frame"""
+    public_api_frame_vs_oracle("male-3-casual", 20, 1, 10000)
+
+
+@pytest.mark.parametrize("track,frame", [("seattle", 0), ("seattle", 20), ("aist_demo", 40), ("aist_demo", 200)])
+def test_other_tracks_meet_the_contract(track, frame):
+    """BASELINE.json config 5 (NeuMan seattle poses, data/custom/seattle/poses/train.npz) and config 3 (AIST animation
+    poses, data/animation/aist_demo.npz prepared as animate.py:45-54)"""
+    public_api_frame_vs_oracle(track, frame, 4, 300)
 
 
 def test_short_training_run_reduces_loss():

@@ -94,6 +94,27 @@ def test_ngp_forward_close(sc, dev):
     assert (s_o > 10).sum() > 1000
 
 
+def test_ngp_kat_matches_oracle_mode1(sc, dev):
+    """hash-grid + MLP known-answer test (tests/golden/ngp_kat_golden.npz, SURVEY.md 8c golden vector 3): the product
+    against the committed mode-1 outputs (fp16 values, fp32 accumulation) on the committed points."""
+    import torch
+    from instantavatar_b200 import ops
+    GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ngp_kat_golden.npz")
+    scene, _ = dev
+    z = np.load(GOLD)
+    c, s = ops.ngp_forward(scene, torch.from_numpy(z["x"]).cuda())
+    c, s = c.cpu().numpy(), s.cpu().numpy()
+    s_o, c_o = z["sigma_mode1"], z["rgb_mode1"]
+    # same rounding model; tensor-core accumulation order may flip the last fp16 bit of an output
+    ulp = np.maximum(np.abs(s_o), 2.0 ** -14) * 2.0 ** -10
+    assert np.all(np.abs(s - s_o) <= 2.001 * ulp), np.abs(s - s_o).max()
+    assert np.mean(s == s_o) > 0.97
+    assert np.abs(c - c_o).max() <= 2.0 ** -10, np.abs(c - c_o).max()   # one fp16 ulp of a value in [0.5, 1)
+    assert np.mean(c == c_o) > 0.97
+    # and how far the tcnn-like mode 2 sits from what the product computes (reported, bounded)
+    assert np.abs(c - z["rgb_mode2"]).max() < 6e-3
+
+
 def test_deform_query_matches_oracle(sc, dev):
     import torch
     from instantavatar_b200 import ops
@@ -132,19 +153,25 @@ def _render_compare(sc, dev, idx, image_width):
     return ref, got, ops.stats_dict(stats)
 
 
-def check_render(ref, got, n_hit_min):
+# The contract (BASELINE.json north_star): rendered RGB / alpha within 1e-3 L-inf of the reference on identical rays.
+# A ray may only exceed it when a discrete decision of the reference algorithm (alpha < 0.01 skip, T <= 1e-4 stop,
+# arg-max over candidates) sits within rounding distance of its threshold; such rays are COUNTED against this
+# explicit allow-list (0: none is tolerated in the committed test frames) and bounded by the size of one skipped term.
+ALLOWED_THRESHOLD_FLIPS = 0
+TOL = 1e-3
+
+
+def check_render(ref, got, n_hit_min, allowed=ALLOWED_THRESHOLD_FLIPS):
     err_rgb = np.abs(got["rgb"] - ref["rgb"]).max(-1)
     err_a = np.abs(got["alpha"] - ref["alpha"])
-    bad = (err_rgb > 1e-3) | (err_a > 1e-3)
+    bad = (err_rgb > TOL) | (err_a > TOL)
     hit = ref["alpha"] > 0.5
     assert hit.sum() >= n_hit_min
-    # The 1e-3 bound (BASELINE.json north_star) holds for all rays except those where a discrete decision of the
-    # reference algorithm (alpha < 0.01 skip, T <= 1e-4 stop, arg-max over candidates) sits within rounding
-    # distance of its threshold; those are bounded by the size of the skipped term.
-    assert bad.mean() <= 2e-4, (bad.sum(), bad.mean(), err_rgb.max(), err_a.max())
+    assert bad.sum() <= allowed, (int(bad.sum()), float(err_rgb.max()), float(err_a.max()))
     assert err_rgb.max() <= 3e-2 and err_a.max() <= 3e-2
     dep = np.abs(got["depth"] - ref["depth"])
     assert np.mean(dep > 5e-3) <= 2e-4
+    return int(bad.sum()), float(err_rgb.max()), float(err_a.max())
 
 
 def test_render_fwd_subsampled_image(sc, dev):
