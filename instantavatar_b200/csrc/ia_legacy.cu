@@ -381,6 +381,42 @@ __global__ void __launch_bounds__(32) smpl_tfs_bwd_kernel(const float* __restric
 
 }  // namespace
 
+// snarf_deformer.py:95-103: rays into the SMPL-root frame + the [|o| - 1, |o| + 1] marching interval.  The dot products are
+// the k = 0, 1, 2 fused-multiply-add chain a 3-wide SGEMM evaluates (what the reference's `rays.o @ R^T` runs), the
+// translation is a separate add, the norm is sqrt(x*x + y*y + z*z) accumulated in that order.
+__global__ void __launch_bounds__(256) transform_rays_kernel(const float* __restrict__ w2s, const float* __restrict__ rays_o,
+                                                             const float* __restrict__ rays_d, int n, float* __restrict__ o_out,
+                                                             float* __restrict__ d_out, float* __restrict__ near_out,
+                                                             float* __restrict__ far_out) {
+    __shared__ float M[12];
+    if (threadIdx.x < 12) M[threadIdx.x] = w2s[threadIdx.x];  // rows 0..2 of the 4x4
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float ox = rays_o[i * 3], oy = rays_o[i * 3 + 1], oz = rays_o[i * 3 + 2];
+    const float dx = rays_d[i * 3], dy = rays_d[i * 3 + 1], dz = rays_d[i * 3 + 2];
+    const float px = __fmaf_rn(oz, M[2], __fmaf_rn(oy, M[1], ox * M[0])) + M[3];
+    const float py = __fmaf_rn(oz, M[6], __fmaf_rn(oy, M[5], ox * M[4])) + M[7];
+    const float pz = __fmaf_rn(oz, M[10], __fmaf_rn(oy, M[9], ox * M[8])) + M[11];
+    o_out[i * 3] = px; o_out[i * 3 + 1] = py; o_out[i * 3 + 2] = pz;
+    d_out[i * 3] = __fmaf_rn(dz, M[2], __fmaf_rn(dy, M[1], dx * M[0]));
+    d_out[i * 3 + 1] = __fmaf_rn(dz, M[6], __fmaf_rn(dy, M[5], dx * M[4]));
+    d_out[i * 3 + 2] = __fmaf_rn(dz, M[10], __fmaf_rn(dy, M[9], dx * M[8]));
+    const float dist = sqrtf(__fmaf_rn(pz, pz, __fmaf_rn(py, py, px * px)));
+    near_out[i] = dist - 1.0f;
+    far_out[i] = dist + 1.0f;
+}
+
+extern "C" int ia_transform_rays(const float* w2s, const float* rays_o, const float* rays_d, int n, float* o_out, float* d_out,
+                      float* near_out, float* far_out, ia_stream_t stream) {
+    IA_REQUIRE(n >= 0);
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(w2s && rays_o && rays_d && o_out && d_out && near_out && far_out);
+    transform_rays_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w2s, rays_o, rays_d, n, o_out, d_out, near_out, far_out);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
 extern "C" int ia_smpl_tfs(const float* global_orient, const float* body_pose, const float* transl, const float* joints,
                            const int* parents, const float* tfs_inv_t, float* tfs, float* w2s, float* A_out,
                            ia_stream_t stream) {

@@ -213,8 +213,17 @@ class SNARFDeformer:
         return self._vertices
 
     def transform_rays_w2s(self, rays):
-        """snarf_deformer.py:95-103"""
-        rays_to_root_frame(rays, self.w2s)
+        """snarf_deformer.py:95-103 -- one launch of ia_transform_rays for a single frame of CUDA rays without autograd
+        history (the renderer's case); the torch expression otherwise (batched frames, gradients, CPU tests)"""
+        w2s = self.w2s
+        plain = (w2s.shape[0] == 1 and rays.o.is_cuda and rays.o.dtype == torch.float32
+                 and not (torch.is_grad_enabled() and (w2s.requires_grad or rays.o.requires_grad or rays.d.requires_grad)))
+        if plain:
+            o, d, near, far = ops.transform_rays(w2s.detach(), rays.o, rays.d)
+            rays.o, rays.d = o.reshape(rays.o.shape), d.reshape(rays.d.shape)
+            rays.near, rays.far = near.reshape(rays.o.shape[:-1]), far.reshape(rays.o.shape[:-1])
+            return
+        rays_to_root_frame(rays, w2s)
 
     def get_bbox_deformed(self):
         """snarf_deformer.py:105-107 (computed by the precompute kernel)"""

@@ -313,6 +313,17 @@ def smpl_tfs(global_orient, body_pose, transl, joints, parents_i32, tfs_inv_t, w
     return tfs, w2s, A
 
 
+def transform_rays(w2s, rays_o, rays_d):
+    """SNARFDeformer.transform_rays_w2s (snarf_deformer.py:95-103) in one launch -> (o', d', near, far)"""
+    o = rays_o.reshape(-1, 3).float().contiguous(); d = rays_d.reshape(-1, 3).float().contiguous()
+    n = o.shape[0]
+    o2 = torch.empty_like(o); d2 = torch.empty_like(d)
+    near = torch.empty(n, device=o.device, dtype=f32); far = torch.empty(n, device=o.device, dtype=f32)
+    _lib.count(1); check(lib().ia_transform_rays(ptr(w2s.reshape(-1, 4, 4)[0].float().contiguous(), f32), ptr(o, f32), ptr(d, f32), C.c_int(n),
+                                                 ptr(o2), ptr(d2), ptr(near), ptr(far), stream()))
+    return o2, d2, near, far
+
+
 def nerf_loss(out: dict, target_rgb, target_alpha, w_rgb=1.0, w_alpha=0.1, w_reg=0.1, scale_dev=None):
     """NeRFLoss (utils/loss.py:53-79) forward + gradients w.r.t. (rgb, alpha, weights) in one launch.
     Returns (losses dict of device scalars, g_rgb, g_alpha, g_weights)."""

@@ -192,3 +192,36 @@ def test_smpl_tfs_kernel_and_fused_loss_match_torch_paths():
     assert torch.allclose(g_rgb, pr["rgb_coarse"].grad, rtol=1e-4, atol=1e-7)
     assert torch.allclose(g_alpha, pr["alpha_coarse"].grad, rtol=1e-4, atol=1e-7)
     assert torch.allclose(g_w, pr["weight_coarse"].grad, rtol=1e-4, atol=1e-8)
+
+
+def test_transform_rays_kernel_matches_torch_expression():
+    """ia_transform_rays (one launch) against the reference's expression (snarf_deformer.py:95-103) in torch and against the
+    oracle's numpy restatement; PatchSampler-shaped rays keep their shape"""
+    import torch
+    from instantavatar_b200 import ops
+    from instantavatar_b200.deformers.snarf_deformer import rays_to_root_frame
+    from instantavatar_b200.models.dnerf import Rays
+    from oracle import frame as oframe
+    model, batch, idx = make_model(57)
+    model.deformer.prepare_deformer(batch)
+    w2s = model.deformer.w2s
+    r1 = Rays(o=batch["rays_o"].clone(), d=batch["rays_d"].clone(), near=batch["near"].clone(), far=batch["far"].clone())
+    r2 = Rays(o=batch["rays_o"].clone(), d=batch["rays_d"].clone(), near=batch["near"].clone(), far=batch["far"].clone())
+    rays_to_root_frame(r1, w2s)
+    model.deformer.transform_rays_w2s(r2)
+    torch.cuda.synchronize()
+    for k in ("o", "d", "near", "far"):
+        a, b = getattr(r1, k), getattr(r2, k)
+        assert a.shape == b.shape, k
+        assert (a - b).abs().max().item() <= 2e-6, (k, (a - b).abs().max().item())
+    o_np, d_np, near_np, far_np = oframe.transform_rays_w2s(batch["rays_o"][0].cpu().numpy(), batch["rays_d"][0].cpu().numpy(), w2s[0].cpu().numpy())
+    assert np.abs(r2.o[0].cpu().numpy() - o_np).max() <= 2e-6 and np.abs(r2.near[0].cpu().numpy() - near_np).max() <= 2e-6
+    # patch-shaped rays [1, 4, 32, 32, 3] (utils/sampler.py PatchSampler)
+    o4 = batch["rays_o"][:, :4096].reshape(1, 4, 32, 32, 3).contiguous(); d4 = batch["rays_d"][:, :4096].reshape(1, 4, 32, 32, 3).contiguous()
+    r3 = Rays(o=o4, d=d4, near=None, far=None)
+    model.deformer.transform_rays_w2s(r3)
+    assert r3.o.shape == (1, 4, 32, 32, 3) and r3.near.shape == (1, 4, 32, 32)
+    assert torch.equal(r3.o.reshape(1, -1, 3), r2.o[:, :4096]) and torch.equal(r3.far.reshape(1, -1), r2.far[:, :4096])
+    # empty input
+    e = ops.transform_rays(w2s, torch.empty((0, 3), device="cuda"), torch.empty((0, 3), device="cuda"))
+    assert e[0].shape == (0, 3) and e[2].shape == (0,)
