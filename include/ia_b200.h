@@ -264,6 +264,15 @@ int ia_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg
                      const float* found_inf, void* half_out, long half_skip, ia_stream_t stream);
 /* fp16 refresh of the padded MLP weight block only (the hash table is refreshed by ia_adam_step_dev) */
 int ia_mlp_to_half(const float* enc_params, const float* col_params, void* mlp_h, ia_stream_t stream);
+/* the same block built from the flat fp16 image of the parameters (enc_mlp_h: the first 3072 halfs of the image of
+ * `encoder.params`, col_h: the 6144 halfs of `color_net.params`): with the sharded optimiser every rank holds the
+ * all-gathered fp16 image while only a shard's owner holds current fp32 values. */
+int ia_mlp_to_half_from_half(const void* enc_mlp_h, const void* col_h, void* mlp_h, ia_stream_t stream);
+/* Sharded optimiser (reduce-scatter -> Adam on 1/G of the parameters -> all-gather of the fp16 image; the reference has
+ * one replicated torch.optim.Adam, DNeRF.py:46-59,152-159): if *found_inf != 0 (this rank's LOCAL gradient overflowed,
+ * ia_grad_check_finite) write a NaN into element k*shard_elems of `grads` for k < n_shards, so that after the
+ * sum-reduce-scatter EVERY rank's shard fails ia_grad_check_finite and all ranks skip the step together. */
+int ia_grad_poison_shards(float* grads, long shard_elems, int n_shards, const float* found_inf, ia_stream_t stream);
 
 #ifdef __cplusplus
 }

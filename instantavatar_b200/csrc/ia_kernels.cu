@@ -631,12 +631,17 @@ __global__ void aabb_init_kernel(float* aabb) {
     if (threadIdx.x < 6) aabb[threadIdx.x] = threadIdx.x < 3 ? INFINITY : -INFINITY;
 }
 
-__global__ void params_to_half_kernel(const float* __restrict__ enc, const float* __restrict__ col,
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+
+// T = float: fp32 master parameters; T = __half: the flat fp16 image of the masters (sharded optimiser: every rank holds
+// the all-gathered fp16 copy, only the shard owner holds current fp32 values -- half(float) is taken once either way)
+template <typename T>
+__global__ void params_to_half_kernel(const T* __restrict__ enc, const T* __restrict__ col,
                                       __half2* __restrict__ table, __half* __restrict__ mlp, uint32_t total_entries) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (table && i < total_entries) {
-        const float2 v = *reinterpret_cast<const float2*>(enc + IA_ENC_MLP_PARAMS + 2 * i);
-        table[i] = __floats2half2_rn(v.x, v.y);
+        table[i] = __floats2half2_rn(to_f32(enc[IA_ENC_MLP_PARAMS + 2 * i]), to_f32(enc[IA_ENC_MLP_PARAMS + 2 * i + 1]));
     }
     if (i < kMlpAllHalfs) {
         // padded [out][in+8] blocks (forward) followed by padded transposed [in][out+8] blocks (backward);
@@ -644,17 +649,17 @@ __global__ void params_to_half_kernel(const float* __restrict__ enc, const float
         // columns 1..15 the 15 geometry features.
         float v = 0.f;
         int o = (int)i;
-        auto W3r = [&](int r, int c) { return col[r * 16 + (c == 0 ? 15 : c - 1)]; };
-        if (o < kW2Off) { const int r = o / kW1Stride, c = o % kW1Stride; if (c < 32) v = enc[r * 32 + c]; }
-        else if (o < kW3Off) { o -= kW2Off; const int r = o / kW2Stride, c = o % kW2Stride; if (c < 64) v = enc[2048 + r * 64 + c]; }
+        auto W3r = [&](int r, int c) { return to_f32(col[r * 16 + (c == 0 ? 15 : c - 1)]); };
+        if (o < kW2Off) { const int r = o / kW1Stride, c = o % kW1Stride; if (c < 32) v = to_f32(enc[r * 32 + c]); }
+        else if (o < kW3Off) { o -= kW2Off; const int r = o / kW2Stride, c = o % kW2Stride; if (c < 64) v = to_f32(enc[2048 + r * 64 + c]); }
         else if (o < kW4Off) { o -= kW3Off; const int r = o / kW3Stride, c = o % kW3Stride; if (c < 16) v = W3r(r, c); }
-        else if (o < kW5Off) { o -= kW4Off; const int r = o / kW4Stride, c = o % kW4Stride; if (c < 64) v = col[1024 + r * 64 + c]; }
-        else if (o < kW5TOff) { o -= kW5Off; const int r = o / kW5Stride, c = o % kW5Stride; if (c < 64) v = col[1024 + 4096 + r * 64 + c]; }
-        else if (o < kW4TOff) { o -= kW5TOff; const int r = o / kW5TStride, c = o % kW5TStride; if (c < 16) v = col[1024 + 4096 + c * 64 + r]; }
-        else if (o < kW3TOff) { o -= kW4TOff; const int r = o / kW4TStride, c = o % kW4TStride; if (c < 64) v = col[1024 + c * 64 + r]; }
+        else if (o < kW5Off) { o -= kW4Off; const int r = o / kW4Stride, c = o % kW4Stride; if (c < 64) v = to_f32(col[1024 + r * 64 + c]); }
+        else if (o < kW5TOff) { o -= kW5Off; const int r = o / kW5Stride, c = o % kW5Stride; if (c < 64) v = to_f32(col[1024 + 4096 + r * 64 + c]); }
+        else if (o < kW4TOff) { o -= kW5TOff; const int r = o / kW5TStride, c = o % kW5TStride; if (c < 16) v = to_f32(col[1024 + 4096 + c * 64 + r]); }
+        else if (o < kW3TOff) { o -= kW4TOff; const int r = o / kW4TStride, c = o % kW4TStride; if (c < 64) v = to_f32(col[1024 + c * 64 + r]); }
         else if (o < kW2TOff) { o -= kW3TOff; const int r = o / kW3TStride, c = o % kW3TStride; if (c < 64) v = W3r(c, r); }
-        else if (o < kW1TOff) { o -= kW2TOff; const int r = o / kW2TStride, c = o % kW2TStride; if (c < 16) v = enc[2048 + c * 64 + r]; }
-        else { o -= kW1TOff; const int r = o / kW1TStride, c = o % kW1TStride; if (c < 64) v = enc[c * 32 + r]; }
+        else if (o < kW1TOff) { o -= kW2TOff; const int r = o / kW2TStride, c = o % kW2TStride; if (c < 16) v = to_f32(enc[2048 + c * 64 + r]); }
+        else { o -= kW1TOff; const int r = o / kW1TStride, c = o % kW1TStride; if (c < 64) v = to_f32(enc[c * 32 + r]); }
         mlp[i] = __float2half_rn(v);
     }
 }
@@ -745,7 +750,7 @@ int ia_params_to_half(const float* enc_params, const float* col_params, void* ta
     HashLevels hl;
     uint32_t tot;
     host_hash_levels(hl, &tot);
-    params_to_half_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+    params_to_half_kernel<float><<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         enc_params, col_params, reinterpret_cast<__half2*>(table_h), reinterpret_cast<__half*>(mlp_h), tot);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
@@ -753,8 +758,16 @@ int ia_params_to_half(const float* enc_params, const float* col_params, void* ta
 
 int ia_mlp_to_half(const float* enc_params, const float* col_params, void* mlp_h, ia_stream_t stream) {
     IA_REQUIRE(enc_params && col_params && mlp_h);
-    params_to_half_kernel<<<(kMlpAllHalfs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(enc_params, col_params, nullptr,
-                                                                                      reinterpret_cast<__half*>(mlp_h), 0);
+    params_to_half_kernel<float><<<(kMlpAllHalfs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(enc_params, col_params, nullptr,
+                                                                                             reinterpret_cast<__half*>(mlp_h), 0);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_mlp_to_half_from_half(const void* enc_mlp_h, const void* col_h, void* mlp_h, ia_stream_t stream) {
+    IA_REQUIRE(enc_mlp_h && col_h && mlp_h);
+    params_to_half_kernel<__half><<<(kMlpAllHalfs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(enc_mlp_h), reinterpret_cast<const __half*>(col_h), nullptr, reinterpret_cast<__half*>(mlp_h), 0);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

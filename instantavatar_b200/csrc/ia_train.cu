@@ -761,6 +761,14 @@ __global__ void grad_finite_kernel(const float* __restrict__ g, long n, float* _
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *found_inf = 1.f;
 }
 
+// sharded optimiser: a rank whose LOCAL gradient holds a non-finite value writes a NaN into one element of every rank's
+// shard, so that after the reduce-scatter (sum) every rank's shard fails its own finite check and all ranks skip the
+// step together -- the overflow flag travels inside the one gradient collective
+__global__ void grad_poison_kernel(float* __restrict__ g, long shard_elems, int n_shards, const float* __restrict__ found_inf) {
+    if (*found_inf == 0.f) return;
+    for (int k = threadIdx.x; k < n_shards; k += blockDim.x) g[(long)k * shard_elems] = __int_as_float(0x7fc00000);
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1060,6 +1068,13 @@ int ia_grad_check_finite(const float* grads, long n, float* found_inf, ia_stream
     if (n == 0) return IA_OK;
     IA_REQUIRE(grads != nullptr);
     grad_finite_kernel<<<sm_count() > 0 ? sm_count() * 8 : 1024, 256, 0, (cudaStream_t)stream>>>(grads, n, found_inf);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_grad_poison_shards(float* grads, long shard_elems, int n_shards, const float* found_inf, ia_stream_t stream) {
+    IA_REQUIRE(grads && found_inf && shard_elems > 0 && n_shards >= 1);
+    grad_poison_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(grads, shard_elems, n_shards, found_inf);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

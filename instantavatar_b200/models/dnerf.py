@@ -236,9 +236,8 @@ class DNeRFModel(torch.nn.Module):
             self.scaler.scale(loss).backward()
         if self.world_size > 1:
             import torch.distributed as dist
-            if not self.network_frozen:
-                for g in self.net_coarse.grad_buffers():
-                    dist.all_reduce(g)
+        # the network's ONE collective per step (reduce-scatter of the flat gradient, followed by the all-gather of the
+        # updated fp16 image) happens inside FusedAdam.step
         pose_grads = self.pose_optimizer.grads() if self.pose_optimizer is not None else []
         if pose_grads:
             if self.world_size > 1:

@@ -69,6 +69,12 @@ class NeRFNGPNet(nn.Module):
         self.scale = s
         self.bbox = bbox
 
+    def adopt_half_table(self, table_h):
+        """use `table_h` ([total, 2] fp16, e.g. a view into the optimiser's flat fp16 image) as the working copy of the
+        hash table from now on; refreshed from the fp32 masters on the next half_params() call"""
+        self._table_h = table_h
+        self._dirty = True
+
     def mark_dirty(self):
         self._dirty = True
 
@@ -78,7 +84,7 @@ class NeRFNGPNet(nn.Module):
 
     def half_buffers(self):
         """persistent fp16 working copies (allocated on first use), without refreshing them"""
-        if self._table_h is None or self._table_h.device != self.encoder.params.device:
+        if self._table_h is None or self._mlp_h is None or self._table_h.device != self.encoder.params.device:
             self.half_params()
         return self._table_h, self._mlp_h
 

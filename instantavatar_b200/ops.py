@@ -260,6 +260,14 @@ def adam_step_dev(params, grads, exp_avg, exp_avg_sq, state, found_inf=None, hal
                                                 C.c_long(half_skip), stream()))
 
 
+def mlp_to_half_from_half(enc_mlp_h, col_h, mlp_h):
+    _lib.count(1); check(lib().ia_mlp_to_half_from_half(ptr(enc_mlp_h, torch.float16), ptr(col_h, torch.float16), ptr(mlp_h), stream()))
+
+
+def grad_poison_shards(grads, shard_elems: int, n_shards: int, found_inf):
+    _lib.count(1); check(lib().ia_grad_poison_shards(ptr(grads, f32), C.c_long(shard_elems), C.c_int(n_shards), ptr(found_inf, f32), stream()))
+
+
 def mlp_to_half(enc_params, col_params, mlp_h):
     _lib.count(1); check(lib().ia_mlp_to_half(ptr(enc_params, f32), ptr(col_params, f32), ptr(mlp_h), stream()))
 

@@ -2,9 +2,10 @@
 
 The reference has no distributed code.  The path shards by rays:
   * render: whole frames (or 8192-ray tiles dealt round-robin) per rank, no data-path collective;
-  * training: each rank marches its shard of the step's rays, then ONE all-reduce (sum) of the flat fp32 gradient
-    [encoder.params | color_net.params] (13 036 208 elements, 52.1 MB) precedes the (replicated) Adam step, which
-    divides by the world size.  The density-grid refresh is replicated bit-identically (same jitter on every rank).
+  * training: each rank marches its shard of the step's rays, then ONE gradient collective: reduce-scatter (sum) of the
+    flat fp32 gradient [encoder.params | color_net.params | pad] (13 036 208 elements, 52.1 MB), Adam on this rank's 1/G
+    of the parameters (dividing by the world size), all-gather of the updated fp16 image (26 MB) -- optim.FusedAdam.
+    The density-grid refresh is replicated bit-identically (same jitter on every rank).
 """
 from __future__ import annotations
 
@@ -78,3 +79,34 @@ def gather_image(local: torch.Tensor, idx: torch.Tensor, n_rays: int, group=None
     for i, b in zip(idxs, bufs):
         out[i] = b
     return out
+
+
+def _has_native_scatter(group=None) -> bool:
+    return dist.get_backend(group) == "nccl"
+
+
+def reduce_scatter_sum(out: torch.Tensor, flat: torch.Tensor, group=None):
+    """out = this rank's equal slice of sum_over_ranks(flat).  NCCL: one reduce-scatter over NVLink; gloo (CPU tests):
+    all-reduce + slice."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    assert flat.numel() == out.numel() * world
+    if _has_native_scatter(group):
+        dist.reduce_scatter_tensor(out, flat, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        out.copy_(flat[rank * out.numel():(rank + 1) * out.numel()])
+    return out
+
+
+def all_gather_inplace(flat: torch.Tensor, group=None):
+    """every rank contributes its own equal slice of `flat` (already in place) and receives the others'"""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per = flat.numel() // world
+    assert per * world == flat.numel()
+    if _has_native_scatter(group):
+        dist.all_gather_into_tensor(flat, flat[rank * per:(rank + 1) * per], group=group)
+    else:
+        parts = [torch.empty(per, dtype=flat.dtype) for _ in range(world)]
+        dist.all_gather(parts, flat[rank * per:(rank + 1) * per].clone(), group=group)
+        flat.copy_(torch.cat(parts))
+    return flat
