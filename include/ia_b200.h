@@ -54,6 +54,9 @@ typedef struct IaStats {
     unsigned long long gathers;   /* trilinear field samples taken by Broyden (M*13*kbar) */
     unsigned long long net_evals; /* hash-grid + MLP evaluations (P) */
     unsigned long long rays_hit;  /* rays with at least one occupied sample */
+    unsigned long long field_loads; /* of `gathers`, those that issued loads (12 sectors of 32 B each): footprints outside the
+                                     * skinning volume and early-out solves are exact zeros computed without memory traffic */
+    unsigned long long reserved;
 } IaStats;
 
 int ia_abi_version(void);
@@ -164,6 +167,14 @@ int ia_deform_query(const IaScene* scene /*[host]*/, const float* pts, int n, in
  * n_shards-th batch of cells starting at `shard` (multi-GPU: the caller max-all-reduces density_max; 0 / 1 = all). */
 int ia_occupancy_query(const IaScene* scene /*[host]*/, const float* jitter, const float* aabb, int G, int passes,
                        float* density_max, void* workspace, int shard, int n_shards, IaStats* stats, ia_stream_t stream);
+
+/* Measurement aid (bench.py `roofline.peak`): the fused kernels' memory access shape in isolation -- every lane gathers
+ * trilinear footprints (4 x-pair records = 12 x 32-byte sectors, 12 LDG.E.256) from the L2-resident field `field`
+ * [D][H][W][24], the next footprint depending on the loaded data -- at one persistent CTA of `warps` (12 / 16 / 24 / 32)
+ * warps per SM.  coherent != 0: the lanes of a warp stay within a 10 x 3 x 3 voxel neighbourhood (a batch of the
+ * occupancy query).  *sectors_out (device) += sectors requested; the caller times the launch with CUDA events. */
+int ia_gather_ceiling(const float* field, int D, int H, int W, int iters, int warps, int coherent,
+                      unsigned long long* sectors_out, float* sink /*nullable*/, ia_stream_t stream);
 
 /* Fine-grained entry points (serve the legacy `model(pts)` callback path and the tinycudann-named shim):
  * ia_broyden replaces fuse_kernel.fuse_broyden + filter_cuda.filter

@@ -23,7 +23,7 @@ SYMBOLS = [
     "ia_abi_version", "ia_last_error", "ia_sm_count", "ia_set_option", "ia_hashgrid_layout", "ia_precompute", "ia_params_to_half",
     "ia_pack_occupancy", "ia_occupancy_build", "ia_render_workspace_bytes", "ia_occupancy_query", "ia_train_fwd", "ia_composite_bwd", "ia_ngp_backward",
     "ia_ngp_backward_scratch_bytes", "ia_adam_step", "ia_grad_check_finite", "ia_adam_prepare", "ia_adam_step_dev",
-    "ia_mlp_to_half", "ia_raymarch_train", "ia_raymarch_test", "ia_composite_test", "ia_smpl_tfs", "ia_nerf_loss", "ia_pose_grad", "ia_knn1", "ia_smpl_tfs_backward", "ia_ngp_input_grad", "ia_voxelize_weights", "ia_render_fwd", "ia_deform_query", "ia_broyden", "ia_ngp_forward", "ia_transform_rays", "ia_mlp_to_half_from_half", "ia_grad_poison_shards",
+    "ia_mlp_to_half", "ia_raymarch_train", "ia_raymarch_test", "ia_composite_test", "ia_smpl_tfs", "ia_nerf_loss", "ia_pose_grad", "ia_knn1", "ia_smpl_tfs_backward", "ia_ngp_input_grad", "ia_voxelize_weights", "ia_render_fwd", "ia_deform_query", "ia_broyden", "ia_ngp_forward", "ia_transform_rays", "ia_mlp_to_half_from_half", "ia_grad_poison_shards", "ia_gather_ceiling",
 ]
 
 
@@ -38,7 +38,7 @@ class IaScene(C.Structure):
 
 class IaStats(C.Structure):
     _fields_ = [("samples", C.c_ulonglong), ("gathers", C.c_ulonglong), ("net_evals", C.c_ulonglong),
-                ("rays_hit", C.c_ulonglong)]
+                ("rays_hit", C.c_ulonglong), ("field_loads", C.c_ulonglong), ("reserved", C.c_ulonglong)]
 
 
 _lib = None

@@ -57,7 +57,7 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
 template <bool kKeepXc>
 __device__ __forceinline__ void warp_eval_samples(const EvalCtx& ctx, WarpScratch<kKeepXc>& ws, bool active, float xd0,
                                                   float xd1, float xd2, bool eval_mode, int lane, SampleOut& out,
-                                                  unsigned& ngather, unsigned& nroots) {
+                                                  unsigned& ngather, unsigned& nroots, unsigned& nload) {
     const FrameConst& fc = *ctx.fc;
     // ---- 1. Broyden from the 13 bone initialisations ------------------------------------------------
     unsigned vmask = 0;
@@ -67,7 +67,8 @@ __device__ __forceinline__ void warp_eval_samples(const EvalCtx& ctx, WarpScratc
             float x[3];
             int ng = 0;
             const bool ok = broyden_solve(ctx.field, fc.bp, fc.Tb[b], xd0, xd1, xd2, x, nullptr, ng);
-            ngather += ng;
+            ngather += ng & 0xffff;
+            nload += (unsigned)ng >> 16;
             ws.cand[0][b][lane] = x[0];
             ws.cand[1][b][lane] = x[1];
             ws.cand[2][b][lane] = x[2];

@@ -84,15 +84,45 @@ class GraphedTrainStep:
         step = self.model.global_step
         return (step % 20 == 0, step < 500, step < 1000)
 
+    def _training_state(self):
+        """every tensor a training step mutates: parameters, Adam moments and device step state, fp16 images, GradScaler,
+        the train occupancy grid (EMA densities, field, bits) and the pose tables / their optimiser"""
+        m = self.model
+        opt = m.optimizer
+        ts = [opt.flat_p, opt.flat_m, opt.flat_v, opt.flat_h, opt.flat_g, opt.state_t, m.scaler.scale_t, m.scaler.growth_tracker,
+              m.scaler.found_inf]
+        _, mlp_h = m.net_coarse.half_buffers()
+        ts.append(mlp_h)
+        grid = m.renderer.density_grid_train
+        ts += [grid.density_cached, grid.density_field] + ([grid._bits] if grid._bits is not None else [])
+        if m.pose_optimizer is not None:
+            ts += [p.data for p in m.pose_optimizer.params] + [t for mv in m.pose_optimizer.state for t in mv] + [m.pose_optimizer.state_t]
+        return ts
+
     def _capture(self, key):
+        """Warm-up runs `warmup` real steps of this control-flow variant (lazy allocations, NCCL channel setup, cuBLAS-free
+        but allocator-warming) and is then UNDONE: parameters, moments, the device step counter, GradScaler state and the
+        occupancy grid are restored, so that a graphed run performs exactly the optimisation steps an ungraphed run does."""
         model = self.model
         step0 = model.global_step
+        if "idx" not in self.static_in and model.SMPL_param is not None:
+            raise ValueError("GraphedTrainStep with pose optimisation needs a static `idx` tensor in the batch "
+                             "(a host scalar would become a pageable H2D copy inside the capture)")
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(self.warmup):  # warm-up steps are real optimisation steps of the same variant
+            model.net_coarse.half_params()
+            grid = model.renderer.density_grid_train
+            if grid.aabb is not None:
+                grid.occupancy_bits()  # allocate + pack now so that the bit field is part of the snapshot
+            state = self._training_state()
+            saved = [t.clone() for t in state]
+            for _ in range(self.warmup):
                 model.global_step = step0
                 model.training_step(dict(self.static_in))
+            for t, c in zip(state, saved):
+                t.copy_(c)
+            del saved
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         model.global_step = step0

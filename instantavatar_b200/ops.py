@@ -111,17 +111,38 @@ class Scene:
         return s
 
 
+def gather_ceiling(field: torch.Tensor, iters: int = 200, warps: int = 12, coherent: bool = True, reps: int = 3) -> dict:
+    """measured ceiling of the fused kernels' gather shape on this GPU (ia_gather_ceiling), best of `reps` timed launches
+    -> {"sectors_per_s", "GBps", "ms"}"""
+    D, H, W, _ = field.shape
+    cnt = torch.zeros(1, device=field.device, dtype=torch.int64)
+    best = None
+    for i in range(reps + 1):  # first launch warms L2 / instruction cache
+        cnt.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.count(1); check(lib().ia_gather_ceiling(ptr(field, f32), C.c_int(D), C.c_int(H), C.c_int(W), C.c_int(iters), C.c_int(warps),
+                                                     C.c_int(1 if coherent else 0), ptr(cnt), None, stream()))
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        if i > 0 and (best is None or ms < best):
+            best = ms
+    sect = int(cnt.item())
+    return {"sectors_per_s": sect / (best * 1e-3), "GBps": sect * 32 / (best * 1e-3) / 1e9, "ms": best, "warps": warps, "coherent": bool(coherent)}
+
+
 def set_option(name: str, value: int):
     check(lib().ia_set_option(name.encode(), C.c_int(value)))
 
 
 def new_stats(device) -> torch.Tensor:
-    return torch.zeros(4, device=device, dtype=torch.int64)
+    return torch.zeros(6, device=device, dtype=torch.int64)
 
 
 def stats_dict(t: torch.Tensor) -> dict:
     v = t.tolist()
-    return {"samples": v[0], "gathers": v[1], "net_evals": v[2], "rays_hit": v[3]}
+    return {"samples": v[0], "gathers": v[1], "net_evals": v[2], "rays_hit": v[3], "field_loads": v[4]}
 
 
 def render_fwd(scene: Scene, rays_o, rays_d, near, far, bg=None, image_width: int = 0, stats: torch.Tensor | None = None,
@@ -437,6 +458,6 @@ def _on_device(fn):
 
 for _name, _fn in list(globals().items()):
     if callable(_fn) and getattr(_fn, "__module__", None) == __name__ and not _name.startswith("_") \
-            and _name not in ("Scene", "set_option", "new_stats", "stats_dict") and isinstance(_fn, type(_on_device)):
+            and _name not in ("Scene", "set_option", "new_stats", "stats_dict", "gather_ceiling") and isinstance(_fn, type(_on_device)):
         globals()[_name] = _on_device(_fn)
 del _name, _fn
