@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--rays-per-warp", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--train-rays-per-warp", type=int, default=0)
+    ap.add_argument("--render-warps", type=int, default=0, help="warps per CTA of the fused renderer (12 / 16)")
+    ap.add_argument("--query-warps", type=int, default=0, help="warps per CTA of the point-query kernel (12 / 16 / 20)")
     return ap.parse_args()
 
 
@@ -478,6 +480,10 @@ def run_ours(args):
         ops.set_option("render_rays_per_warp", args.rays_per_warp)
     if args.train_rays_per_warp:
         ops.set_option("train_rays_per_warp", args.train_rays_per_warp)
+    if args.render_warps:
+        ops.set_option("render_warps", args.render_warps)
+    if args.query_warps:
+        ops.set_option("query_warps", args.query_warps)
 
     frame = FRAMES[rank % len(FRAMES)]
     model, hb, batch = build_model(device, frame)

@@ -10,6 +10,8 @@ using namespace ia;
 
 static int g_render_rays = 4;  // rays per warp (32 / 16 / 8 / 4), tunable through ia_set_option
 static int g_render_plan = 1;  // longest-first tile scheduling (needs the large workspace)
+static int g_render_warps = 12;  // warps per persistent CTA of the fused renderer (12: 168 registers / thread, 16: 128)
+static int g_query_warps = 12;   // same for the point-query kernel (12 / 16 / 20; 16 and 20 only without xc output)
 static int g_train_rays = 2;   // rays per warp of the training forward (4 / 2 / 1)
 int ia_train_rays_per_warp() { return g_train_rays; }
 
@@ -374,18 +376,20 @@ struct QueryArgs {
     int batch_first, batch_stride;  // grid mode: this launch handles batches first, first+stride, ... (multi-GPU sharding)
 };
 
-template <int kWarps>
+template <int kWarps, bool kKeepXc>
 struct QuerySmem {
     __align__(16) __half W[kMlpHalfs];
     FrameConst fc;
     __align__(8) uint64_t mbar;
-    WarpScratch<true> ws[kWarps];
+    WarpScratch<kKeepXc> ws[kWarps];
 };
 
-template <int kWarps>
+// kKeepXc: the canonical point of the winning candidate is an output (xc_best; training-time queries); the occupancy
+// passes do not need it, which frees 5 KB of shared memory per warp => more resident warps per SM
+template <int kWarps, bool kKeepXc>
 __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __grid_constant__ QueryArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    QuerySmem<kWarps>& sm = *reinterpret_cast<QuerySmem<kWarps>*>(smem_raw);
+    QuerySmem<kWarps, kKeepXc>& sm = *reinterpret_cast<QuerySmem<kWarps, kKeepXc>*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         mbar_init(&sm.mbar, 1);
@@ -439,14 +443,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
             }
         }
         SampleOut so;
-        warp_eval_samples<true>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots, st_load);
+        warp_eval_samples<kKeepXc>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots, st_load);
         st_samples += act ? 1u : 0u;
         if (act && a.grid_aabb) {
             if (so.sigma > 0.f) atomicMax(reinterpret_cast<int*>(a.density_max) + cell, __float_as_int(so.sigma));
         } else if (act) {
             a.sigma[p] = so.sigma;
             a.rgb[p * 3] = so.r; a.rgb[p * 3 + 1] = so.g; a.rgb[p * 3 + 2] = so.b;
-            if (a.xc_best) { a.xc_best[p * 3] = so.xc[0]; a.xc_best[p * 3 + 1] = so.xc[1]; a.xc_best[p * 3 + 2] = so.xc[2]; }
+            if constexpr (kKeepXc) {
+                if (a.xc_best) { a.xc_best[p * 3] = so.xc[0]; a.xc_best[p * 3 + 1] = so.xc[1]; a.xc_best[p * 3 + 2] = so.xc[2]; }
+            }
             if (a.best_init) a.best_init[p] = (int8_t)so.best;
         }
     }
@@ -714,6 +720,16 @@ int ia_set_option(const char* name, int value) {
         g_render_plan = value != 0;
         return IA_OK;
     }
+    if (!strcmp(name, "render_warps")) {
+        IA_REQUIRE(value == 12 || value == 16);
+        g_render_warps = value;
+        return IA_OK;
+    }
+    if (!strcmp(name, "query_warps")) {
+        IA_REQUIRE(value == 12 || value == 16 || value == 20);
+        g_query_warps = value;
+        return IA_OK;
+    }
     if (!strcmp(name, "train_rays_per_warp")) {
         IA_REQUIRE(value == 4 || value == 2 || value == 1);
         g_train_rays = value;
@@ -785,25 +801,57 @@ int ia_pack_occupancy(const uint8_t* field_bool, uint32_t* bits, int G, ia_strea
     return IA_OK;
 }
 
-constexpr int kRenderWarps = 12;
-constexpr int kQueryWarps = 12;
-
 size_t ia_render_workspace_bytes(int n_rays) { return 256 + 2 * sizeof(int) * (size_t)(n_rays + 1); }
 
 }  // extern "C"
 
-template <int kRays>
-static int launch_render(RenderArgs& a, bool plan, int* ws_cost, int* ws_order, int grid, size_t smem, cudaStream_t st) {
+template <int kWarps, int kRays>
+static int launch_render(RenderArgs& a, bool plan, int* ws_cost, int* ws_order, cudaStream_t st) {
+    const size_t smem = sizeof(RenderSmem<kWarps>);
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kWarps, kRays>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set.set();
+    }
+    const int n_tiles = (a.n_rays + kRays - 1) / kRays;
+    int grid = sm_count();
+    if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    grid = min(grid, (n_tiles + kWarps - 1) / kWarps);
     if (plan) {
-        const int n_tiles = (a.n_rays + kRays - 1) / kRays;
         const long threads = (long)n_tiles * kRays;
         render_plan_kernel<kRays><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a, ws_cost);
         order_tiles_kernel<<<1, 1024, 0, st>>>(ws_cost, n_tiles, ws_order, a.tile_counter + 1);
         a.tile_order = ws_order;
         a.n_active = a.tile_counter + 1;
     }
-    render_fwd_kernel<kRenderWarps, kRays><<<grid, kRenderWarps * 32, smem, st>>>(a);
-    return 0;
+    render_fwd_kernel<kWarps, kRays><<<grid, kWarps * 32, smem, st>>>(a);
+    return IA_OK;
+}
+
+template <int kWarps, bool kKeepXc>
+static int launch_query_t(QueryArgs& a, cudaStream_t stream) {
+    const size_t smem = sizeof(QuerySmem<kWarps, kKeepXc>);
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(deform_query_kernel<kWarps, kKeepXc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set.set();
+    }
+    const int n_batches = a.grid_aabb ? (a.G * a.G * a.G + (32 / a.passes) - 1) / (32 / a.passes) : (a.n + 31) / 32;
+    int grid = sm_count();
+    if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    grid = min(grid, (n_batches + kWarps - 1) / kWarps);
+    deform_query_kernel<kWarps, kKeepXc><<<grid, kWarps * 32, smem, stream>>>(a);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+static int launch_query(QueryArgs& a, cudaStream_t stream) {
+    if (a.xc_best) return launch_query_t<12, true>(a, stream);
+    switch (g_query_warps) {
+        case 20: return launch_query_t<20, false>(a, stream);
+        case 16: return launch_query_t<16, false>(a, stream);
+        default: return launch_query_t<12, false>(a, stream);
+    }
 }
 
 extern "C" {
@@ -830,35 +878,20 @@ int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d
     const bool plan = g_render_plan && workspace_bytes >= ia_render_workspace_bytes(n_rays);
     int* ws_cost = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + 256);
     int* ws_order = ws_cost + (n_rays + 1);
-    const size_t smem = sizeof(RenderSmem<kRenderWarps>);
-    static PerDeviceFlag attr_set;
-    if (!attr_set.get()) {
-        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        IA_CHECK_CUDA(cudaFuncSetAttribute(render_fwd_kernel<kRenderWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set.set();
-    }
     const int rpw = g_render_rays;
-    const int n_tiles = (n_rays + rpw - 1) / rpw;
-    int grid = sm_count();
-    if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
-    grid = min(grid, (n_tiles + kRenderWarps - 1) / kRenderWarps);
+    const bool w16 = g_render_warps == 16 && (rpw == 4 || rpw == 8);  // the 16-warp build exists for the two useful tile shapes
     switch (rpw) {
-        case 32: launch_render<32>(a, plan, ws_cost, ws_order, grid, smem, st); break;
-        case 16: launch_render<16>(a, plan, ws_cost, ws_order, grid, smem, st); break;
-        case 4: launch_render<4>(a, plan, ws_cost, ws_order, grid, smem, st); break;
-        case 2: launch_render<2>(a, plan, ws_cost, ws_order, grid, smem, st); break;
-        case 1: launch_render<1>(a, plan, ws_cost, ws_order, grid, smem, st); break;
-        default: launch_render<8>(a, plan, ws_cost, ws_order, grid, smem, st); break;
+        case 32: rc = launch_render<12, 32>(a, plan, ws_cost, ws_order, st); break;
+        case 16: rc = launch_render<12, 16>(a, plan, ws_cost, ws_order, st); break;
+        case 4: rc = w16 ? launch_render<16, 4>(a, plan, ws_cost, ws_order, st) : launch_render<12, 4>(a, plan, ws_cost, ws_order, st); break;
+        case 2: rc = launch_render<12, 2>(a, plan, ws_cost, ws_order, st); break;
+        case 1: rc = launch_render<12, 1>(a, plan, ws_cost, ws_order, st); break;
+        default: rc = w16 ? launch_render<16, 8>(a, plan, ws_cost, ws_order, st) : launch_render<12, 8>(a, plan, ws_cost, ws_order, st); break;
     }
+    if (rc) return rc;
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }
-
-static int launch_query(QueryArgs& a, cudaStream_t stream);
 
 int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode, float* rgb, float* sigma,
                     float* xc_best, int8_t* best_init, IaStats* stats, ia_stream_t stream) {
@@ -873,23 +906,6 @@ int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode
     a.grid_jitter = nullptr; a.grid_aabb = nullptr; a.G = 0; a.density_max = nullptr; a.passes = 1;
     a.batch_counter = nullptr; a.batch_first = 0; a.batch_stride = 1;
     return launch_query(a, (cudaStream_t)stream);
-}
-
-static int launch_query(QueryArgs& a, cudaStream_t stream) {
-    const int n = a.n;
-    const size_t smem = sizeof(QuerySmem<kQueryWarps>);
-    static PerDeviceFlag attr_set;
-    if (!attr_set.get()) {
-        IA_CHECK_CUDA(cudaFuncSetAttribute(deform_query_kernel<kQueryWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set.set();
-    }
-    const int n_batches = a.grid_aabb ? (a.G * a.G * a.G + (32 / a.passes) - 1) / (32 / a.passes) : (n + 31) / 32;
-    int grid = sm_count();
-    if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
-    grid = min(grid, (n_batches + kQueryWarps - 1) / kQueryWarps);
-    deform_query_kernel<kQueryWarps><<<grid, kQueryWarps * 32, smem, stream>>>(a);
-    IA_CHECK_CUDA(cudaPeekAtLastError());
-    return IA_OK;
 }
 
 extern "C" int ia_occupancy_query(const IaScene* scene, const float* jitter, const float* aabb, int G, int passes,
