@@ -106,10 +106,11 @@ int ia_smpl_tfs(const float* global_orient, const float* body_pose, const float*
 /* Rays world -> SMPL-root frame, one launch.  Replaces SNARFDeformer.transform_rays_w2s
  * (deformers/snarf_deformer.py:95-103: two small GEMMs, a norm and two element-wise ops):
  *   o' = o R^T + t,  d' = d R^T   with [R | t] = w2s[:3, :4],   near = |o'| - 1,   far = |o'| + 1.
- * rays_o / rays_d [n][3] (inputs), w2s [4][4] row-major (device); outputs o_out / d_out [n][3], near_out / far_out [n]
- * (in-place use with o_out == rays_o, d_out == rays_d is allowed: every thread reads its ray before it writes it). */
-int ia_transform_rays(const float* w2s, const float* rays_o, const float* rays_d, int n, float* o_out, float* d_out,
-                      float* near_out, float* far_out, ia_stream_t stream);
+ * rays_o / rays_d [.][3] (inputs), w2s [4][4] row-major (device); outputs o_out / d_out [n][3], near_out / far_out [n].
+ * index (int32 [n], nullable): output ray i is input ray index[i] -- a rank of a ray-sharded frame picks its tiles in the
+ * same launch.  Without index, in-place use (o_out == rays_o, d_out == rays_d) is allowed. */
+int ia_transform_rays(const float* w2s, const float* rays_o, const float* rays_d, const int* index /*nullable*/, int n,
+                      float* o_out, float* d_out, float* near_out, float* far_out, ia_stream_t stream);
 
 /* Reverse mode of ia_smpl_tfs for pose optimisation (what autograd computes through smplx/lbs.py:295-329,345-401 and
  * snarf_deformer.py:84-86): grad_tfs [24][4][4] -> grad_orient [3] (nullable), grad_pose [69], grad_transl [3]

@@ -385,16 +385,17 @@ __global__ void __launch_bounds__(32) smpl_tfs_bwd_kernel(const float* __restric
 // the k = 0, 1, 2 fused-multiply-add chain a 3-wide SGEMM evaluates (what the reference's `rays.o @ R^T` runs), the
 // translation is a separate add, the norm is sqrt(x*x + y*y + z*z) accumulated in that order.
 __global__ void __launch_bounds__(256) transform_rays_kernel(const float* __restrict__ w2s, const float* __restrict__ rays_o,
-                                                             const float* __restrict__ rays_d, int n, float* __restrict__ o_out,
-                                                             float* __restrict__ d_out, float* __restrict__ near_out,
-                                                             float* __restrict__ far_out) {
+                                                             const float* __restrict__ rays_d, const int* __restrict__ index, int n,
+                                                             float* __restrict__ o_out, float* __restrict__ d_out,
+                                                             float* __restrict__ near_out, float* __restrict__ far_out) {
     __shared__ float M[12];
     if (threadIdx.x < 12) M[threadIdx.x] = w2s[threadIdx.x];  // rows 0..2 of the 4x4
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float ox = rays_o[i * 3], oy = rays_o[i * 3 + 1], oz = rays_o[i * 3 + 2];
-    const float dx = rays_d[i * 3], dy = rays_d[i * 3 + 1], dz = rays_d[i * 3 + 2];
+    const long s = index ? index[i] : i;  // optional gather: output ray i is input ray index[i] (ray-sharded frames)
+    const float ox = rays_o[s * 3], oy = rays_o[s * 3 + 1], oz = rays_o[s * 3 + 2];
+    const float dx = rays_d[s * 3], dy = rays_d[s * 3 + 1], dz = rays_d[s * 3 + 2];
     const float px = __fmaf_rn(oz, M[2], __fmaf_rn(oy, M[1], ox * M[0])) + M[3];
     const float py = __fmaf_rn(oz, M[6], __fmaf_rn(oy, M[5], ox * M[4])) + M[7];
     const float pz = __fmaf_rn(oz, M[10], __fmaf_rn(oy, M[9], ox * M[8])) + M[11];
@@ -407,12 +408,13 @@ __global__ void __launch_bounds__(256) transform_rays_kernel(const float* __rest
     far_out[i] = dist + 1.0f;
 }
 
-extern "C" int ia_transform_rays(const float* w2s, const float* rays_o, const float* rays_d, int n, float* o_out, float* d_out,
-                      float* near_out, float* far_out, ia_stream_t stream) {
+extern "C" int ia_transform_rays(const float* w2s, const float* rays_o, const float* rays_d, const int* index, int n, float* o_out,
+                                 float* d_out, float* near_out, float* far_out, ia_stream_t stream) {
     IA_REQUIRE(n >= 0);
     if (n == 0) return IA_OK;
     IA_REQUIRE(w2s && rays_o && rays_d && o_out && d_out && near_out && far_out);
-    transform_rays_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w2s, rays_o, rays_d, n, o_out, d_out, near_out, far_out);
+    IA_REQUIRE(!index || (o_out != rays_o && d_out != rays_d));  // the gather form cannot run in place
+    transform_rays_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w2s, rays_o, rays_d, index, n, o_out, d_out, near_out, far_out);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

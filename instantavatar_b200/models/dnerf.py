@@ -258,17 +258,23 @@ class DNeRFModel(torch.nn.Module):
         """One frame rendered cooperatively by `world` GPUs (BASELINE.json config 3): per-frame preparation is replicated
         (0.1 ms), the occupancy-grid queries are sharded with one 1 MB max-all-reduce, rays are dealt round-robin in tiles
         of `tile` rays (whole image rows) and the RGBA rows are gathered on rank 0.  `jitters` must be identical on all
-        ranks.  Returns [H*W, 4] on rank 0, None elsewhere."""
+        ranks.  Returns [H*W, 4] (RGBA) on every rank (on rank 0 only when the tiles do not divide evenly)."""
         from .. import parallel
         H, W = img_size
         self.deformer.prepare_deformer(batch)
         self.net_coarse.initialize(self.deformer.bbox)
         self.renderer.density_grid_test.initialize(self.deformer, self.net_coarse, jitters=jitters, shard=(rank, world))
-        idx = parallel.shard_tiles_cached(H * W, rank, world, tile, batch["rays_o"].device)
-        b = dict(batch)
-        for k in ("rays_o", "rays_d", "near", "far"):
-            b[k] = batch[k][:, idx].contiguous()
-        self.image_width = W if tile % (2 * W) == 0 else 0
-        d = self.forward(b, eval_mode=True)
-        local = torch.cat([d["rgb_coarse"].reshape(-1, 3), d["alpha_coarse"].reshape(-1, 1)], dim=1)
+        dev = batch["rays_o"].device
+        idx = parallel.shard_tiles_cached(H * W, rank, world, tile, dev)
+        # this rank's tiles are picked and moved to the root frame in ONE launch (index form of ia_transform_rays)
+        o, d, near, far = ops.transform_rays(self.deformer.w2s, batch["rays_o"], batch["rays_d"],
+                                             parallel.shard_tiles_cached(H * W, rank, world, tile, dev, torch.int32))
+        rays = Rays(o=o[None], d=d[None], near=near[None], far=far[None])
+        self.renderer.image_width = W if tile % (2 * W) == 0 else 0
+        bg = batch["bg_color"].reshape(-1, 3)[idx] if batch.get("bg_color", None) is not None else None
+        out = self.renderer.render_test(rays, BoundModel(self.deformer, self.net_coarse, True), bg)
+        local = torch.cat([out["rgb_coarse"].reshape(-1, 3), out["alpha_coarse"].reshape(-1, 1)], dim=1)
+        img = parallel.all_gather_image(local, H * W, tile)   # every rank ends up with the frame (one all-gather)
+        if img is not None:
+            return img
         return parallel.gather_image(local, idx, H * W, tile=tile)

@@ -342,13 +342,15 @@ def smpl_tfs(global_orient, body_pose, transl, joints, parents_i32, tfs_inv_t, w
     return tfs, w2s, A
 
 
-def transform_rays(w2s, rays_o, rays_d):
-    """SNARFDeformer.transform_rays_w2s (snarf_deformer.py:95-103) in one launch -> (o', d', near, far)"""
+def transform_rays(w2s, rays_o, rays_d, index=None):
+    """SNARFDeformer.transform_rays_w2s (snarf_deformer.py:95-103) in one launch -> (o', d', near, far).
+    index (int32 [n]): transform only rays index[i] of the input (compact output) -- ray-sharded frames."""
     o = rays_o.reshape(-1, 3).float().contiguous(); d = rays_d.reshape(-1, 3).float().contiguous()
-    n = o.shape[0]
-    o2 = torch.empty_like(o); d2 = torch.empty_like(d)
+    n = o.shape[0] if index is None else index.numel()
+    o2 = torch.empty((n, 3), device=o.device, dtype=f32); d2 = torch.empty((n, 3), device=o.device, dtype=f32)
     near = torch.empty(n, device=o.device, dtype=f32); far = torch.empty(n, device=o.device, dtype=f32)
-    _lib.count(1); check(lib().ia_transform_rays(ptr(w2s.reshape(-1, 4, 4)[0].float().contiguous(), f32), ptr(o, f32), ptr(d, f32), C.c_int(n),
+    _lib.count(1); check(lib().ia_transform_rays(ptr(w2s.reshape(-1, 4, 4)[0].float().contiguous(), f32), ptr(o, f32), ptr(d, f32),
+                                                 ptr(index, torch.int32) if index is not None else None, C.c_int(n),
                                                  ptr(o2), ptr(d2), ptr(near), ptr(far), stream()))
     return o2, d2, near, far
 

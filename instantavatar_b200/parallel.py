@@ -30,11 +30,11 @@ def init_from_env(backend: str | None = None, device: torch.device | None = None
 _TILE_CACHE = {}
 
 
-def shard_tiles_cached(n_rays: int, rank: int, world: int, tile: int, device) -> torch.Tensor:
+def shard_tiles_cached(n_rays: int, rank: int, world: int, tile: int, device, dtype=torch.int64) -> torch.Tensor:
     """device-resident copy of shard_tiles (built once: no per-frame host->device index upload)"""
-    key = (n_rays, rank, world, tile, str(device))
+    key = (n_rays, rank, world, tile, str(device), dtype)
     if key not in _TILE_CACHE:
-        _TILE_CACHE[key] = shard_tiles(n_rays, rank, world, tile).to(device)
+        _TILE_CACHE[key] = shard_tiles(n_rays, rank, world, tile).to(device=device, dtype=dtype)
     return _TILE_CACHE[key]
 
 
@@ -110,3 +110,23 @@ def all_gather_inplace(flat: torch.Tensor, group=None):
         dist.all_gather(parts, flat[rank * per:(rank + 1) * per].clone(), group=group)
         flat.copy_(torch.cat(parts))
     return flat
+
+
+def all_gather_image(local: torch.Tensor, n_rays: int, tile: int, group=None) -> torch.Tensor | None:
+    """Assemble a ray-sharded render on EVERY rank with one collective: ranks hold the rows of their round-robin tiles
+    (shard_tiles) in tile order; all-gather -> [world, tiles_per_rank, tile, C] -> one permuting copy into image order.
+    Needs n_rays % (tile * world) == 0 (else None: the caller falls back to gather_image)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1 or n_rays % (tile * world) != 0:
+        return None
+    per = n_rays // (tile * world)
+    assert local.shape[0] == per * tile
+    C = local.shape[1]
+    buf = local.new_empty((world, per, tile, C))
+    if _has_native_scatter(group):
+        dist.all_gather_into_tensor(buf.view(-1), local.contiguous().view(-1), group=group)
+    else:
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local.contiguous(), group=group)
+        buf.copy_(torch.stack(parts).view(world, per, tile, C))
+    return buf.permute(1, 0, 2, 3).reshape(n_rays, C)  # tile (t, r) is global tile t * world + r

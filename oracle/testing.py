@@ -24,19 +24,24 @@ def load_golden_frame(frame_idx):
     return ref
 
 
-def oracle_scene(frame_idx=0, track="male-3-casual", sigma_in=100.0, tfs=None, w2s=None):
-    """tfs / w2s: bone transforms to continue from (see SubjectOracle.prepare_frame); not cached"""
+def oracle_scene(frame_idx=0, track="male-3-casual", sigma_in=100.0, tfs=None, w2s=None, subject_overrides=None):
+    """tfs / w2s: bone transforms to continue from (see SubjectOracle.prepare_frame); subject_overrides: per-subject constants
+    (offset_kernel, scale_kernel, bbox) to take over instead of this oracle's own (the product derives them from ITS SMPL
+    forward: equal to ~1e-7; handing them over keeps everything downstream on identical inputs).  Neither is cached."""
     key = (frame_idx, track, sigma_in)
-    if key in _CACHE and tfs is None:
+    if key in _CACHE and tfs is None and subject_overrides is None:
         return _CACHE[key]
     from instantavatar_b200 import synthetic
     subj = oscene.build_subject(track=track)
+    for k, v in (subject_overrides or {}).items():
+        assert hasattr(subj, k), k
+        setattr(subj, k, np.ascontiguousarray(np.asarray(v, np.float32).reshape(np.shape(getattr(subj, k)))))
     pose = synthetic.load_pose(frame_idx, track)
     fr = subj.prepare_frame(pose, tfs, w2s)
     net = oscene.build_net(subj, sigma_in=sigma_in)
     field, density, jit = oscene.build_occupancy(subj, fr, net)
     sc = {"subj": subj, "pose": pose, "frame": fr, "net": net, "occ": field, "occ_density": density, "occ_jitter": jit}
-    if tfs is None:
+    if tfs is None and subject_overrides is None:
         _CACHE[key] = sc
     return sc
 

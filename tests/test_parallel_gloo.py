@@ -47,6 +47,12 @@ def _worker(rank, world, port, ret):
     idx = parallel.shard_tiles(n_img, rank, world)
     full = torch.arange(n_img, dtype=torch.float32)[:, None].repeat(1, 4)
     img = parallel.gather_image(full[idx], idx, n_img)
+    # one-collective variant: every rank ends up with the image (all-gather + tile un-permutation)
+    for tile in (parallel.TILE, 2048):
+        idx_t = parallel.shard_tiles(n_img, rank, world, tile)
+        img2 = parallel.all_gather_image(full[idx_t], n_img, tile)
+        assert img2 is not None and torch.equal(img2, full)
+    assert parallel.all_gather_image(full[parallel.shard_tiles(1000, rank, world, 300)], 1000, 300) is None  # ragged: caller falls back
     if rank == 0:
         assert torch.equal(img, full)
         ret["ok"] = True
