@@ -75,9 +75,11 @@ def _worker(rank, world, port, ret):
         losses, g_rgb, g_alpha, g_w = ops.nerf_loss(out, b["rgb"], b["alpha"])
         l = ops.composite_bwd(ne, fa, bg, noi_, saved, g_rgb, None, g_alpha, g_w)
         ops.ngp_backward(scene, l[0], l[1], l[2], l[3], g_enc, g_col, GRAD_SCALE)
+        ge, gc = g_enc.clone(), g_col.clone()
+        g_enc.zero_(); g_col.zero_()
         if world_size > 1:
-            parallel.allreduce_sum_([g_enc, g_col])
-        return g_enc.clone() / world_size, g_col.clone() / world_size
+            parallel.allreduce_sum_([ge, gc])
+        return ge / world_size, gc / world_size
 
     full_enc, full_col = grads(tb, jitter, noise, 1)
     sl = parallel.shard_train_rays(n, rank, world)
@@ -89,6 +91,37 @@ def _worker(rank, world, port, ret):
         rel = lambda a, b: float((a - b).norm() / b.norm())
         ret["rel_enc"] = rel(sh_enc, full_enc); ret["rel_col"] = rel(sh_col, full_col)
         ret["gnorm"] = float(full_enc.norm())
+    # ---- sharded optimiser: 3 training steps on ray shards (reduce-scatter, Adam on 1/G, all-gather of the fp16 image)
+    #      against 3 single-process steps on the full batch from the same initial state ----
+    def fresh_model():
+        m = DNeRFModel(smpl_data=synthetic.smpl_dict_cached(0), device=dev)
+        m.deformer.prepare_deformer(batch)
+        m.net_coarse.initialize(m.deformer.bbox)
+        m.net_coarse.load_flat_params(torch.from_numpy(enc).to(dev), torch.from_numpy(col).to(dev))
+        m.global_step = 2001
+        m.renderer.density_grid_train.set_field(torch.ones((64, 64, 64), dtype=torch.bool, device=dev))  # march everything
+        return m
+
+    def steps(m, b, jit_, noi_, k=3):
+        for _ in range(k):
+            m.training_step(dict(b), jitter=jit_, noise_tensor=noi_)
+        return m
+
+    single = steps(fresh_model(), tb, jitter, noise)
+    sharded_m = fresh_model(); sharded_m.world_size = world
+    steps(sharded_m, sb, jitter[sl].contiguous(), noise[sl].contiguous())
+    torch.cuda.synchronize()
+    h_single, h_shard = single.optimizer.flat_h[: single.optimizer.n].float(), sharded_m.optimizer.flat_h[: single.optimizer.n].float()
+    gathered = [torch.empty_like(h_shard) for _ in range(world)]
+    dist.all_gather(gathered, h_shard)
+    sharded_m.optimizer.gather_master_params(world)
+    p_single, p_shard = single.optimizer.flat_p[: single.optimizer.n], sharded_m.optimizer.flat_p[: single.optimizer.n]
+    if rank == 0:
+        ret["fp16_image_same_on_ranks"] = bool(all(torch.equal(gathered[0], g) for g in gathered))
+        ret["adam_steps"] = (single.optimizer.step_count, sharded_m.optimizer.step_count)
+        ret["param_max_diff"] = float((p_single - p_shard).abs().max()); ret["param_mean_diff"] = float((p_single - p_shard).abs().mean())
+        ret["param_moved"] = float((p_single - torch.cat([torch.from_numpy(enc), torch.from_numpy(col)]).to(dev)).abs().max())
+        ret["fp16_frac_diff"] = float((h_single != h_shard).float().mean())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -103,3 +136,8 @@ def test_two_gpu_frame_and_gradient():
     assert ret["hit"] > 1000
     assert ret["frame_equal"], "cooperative frame differs from the single-GPU frame"
     assert ret["gnorm"] > 0 and ret["rel_enc"] < 1e-3 and ret["rel_col"] < 1e-3, dict(ret)
+    # sharded optimiser == replicated optimiser up to the summation order of the gradient (Adam normalises the update, so
+    # an entry whose gradient is pure rounding noise can move by a full lr step in either run: bounded by 3 steps x lr)
+    assert ret["fp16_image_same_on_ranks"] and ret["adam_steps"] == (3, 3), dict(ret)
+    assert ret["param_moved"] > 1e-3 and ret["param_max_diff"] <= 3.5e-2 and ret["param_mean_diff"] < 1e-5, dict(ret)
+    assert ret["fp16_frac_diff"] < 1e-3, dict(ret)
