@@ -187,6 +187,25 @@ int ia_broyden(const IaScene* scene /*[host]*/, const float* xd, int n, float* x
 int ia_ngp_forward(const IaScene* scene /*[host]*/, const float* x, int n, float* sigma, float* rgb,
                    ia_stream_t stream);
 
+/* The two tiny-cuda-nn modules of models/networks/ngp.py:27-57 as separate operators -- what the in-repo `tinycudann`
+ * module (tcnn.NetworkWithInputEncoding / tcnn.Network with flat fp32 `params`, fp16 outputs, internal loss scale) binds, so
+ * that the reference's ngp.py runs verbatim on these kernels:
+ *   ia_tcnn_encoder_forward : x01 [n][3] in [0,1] -> out16 [n][16] fp16 (HashGrid 16 x 2, 2^19, base 16, scale 1.5 +
+ *                             FullyFusedMLP 32 -> 64 ReLU -> 16); scene needs table_h and mlp_h
+ *   ia_tcnn_encoder_backward: d loss / d out16 [n][16] fp32 -> grad_enc [3072 + 2*total] (+=; nullable) and/or denc_out
+ *                             [n][32] (d loss / d hash features, for the input gradient via ia_ngp_input_grad)
+ *   ia_tcnn_mlp_forward     : in15 [n][15] fp32 -> out3 [n][3] fp16 (15 (+1.0 pad) -> 64 -> 64 -> 3, ReLU, sigmoid output)
+ *   ia_tcnn_mlp_backward    : d loss / d out3 [n][3] fp32 -> grad_col [6144] (+=; nullable) and/or din15 [n][15]
+ * scratch >= ia_tcnn_backward_scratch_bytes(n); grad_*_dummy: 6144 / 3072 floats the shared weight-gradient pass may touch
+ * (the other module's all-zero contribution).  mlp_h as produced by ia_mlp_to_half. */
+size_t ia_tcnn_backward_scratch_bytes(int n);
+int ia_tcnn_encoder_forward(const IaScene* scene /*[host]*/, const float* x01, int n, void* out16_h, ia_stream_t stream);
+int ia_tcnn_encoder_backward(const IaScene* scene /*[host]*/, const float* x01, const float* dout16, int n, float grad_scale,
+                             float* grad_enc, float* grad_col_dummy, void* scratch, float* denc_out, ia_stream_t stream);
+int ia_tcnn_mlp_forward(const void* mlp_h, const float* in15, int n, void* out3_h, ia_stream_t stream);
+int ia_tcnn_mlp_backward(const void* mlp_h, const float* in15, const float* dout3, int n, float grad_scale, float* grad_col,
+                         float* grad_enc_dummy, void* scratch, float* din15, ia_stream_t stream);
+
 /* Kernel-for-kernel replacements of the reference's raymarcher extension (renderers/cuda/raymarcher.cpp:16-81), for
  * the legacy `model(pts)` callback path.  Layouts are the reference's: density_grid bool [G][G][G], alive int64,
  * outputs zero-initialised by the caller (the reference allocates them with at::zeros), `nears` / `color` / `depth` /

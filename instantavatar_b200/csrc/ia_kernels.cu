@@ -555,6 +555,92 @@ __global__ void __launch_bounds__(kWarps * 32) ngp_forward_kernel(const __grid_c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// the two tiny-cuda-nn modules of ngp.py:27-57 as separate operators (the `tinycudann`-named shim): the hash-grid
+// encoder + density MLP (x in [0,1]^3 -> 16 fp16 outputs) and the colour MLP (15 inputs -> 3 fp16 outputs)
+// ------------------------------------------------------------------------------------------------
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) tcnn_encoder_forward_kernel(const __grid_constant__ SceneDev sd,
+                                                                           const float* __restrict__ x, int n,
+                                                                           __half* __restrict__ out16) {
+    __shared__ __align__(16) __half W[kMlpHalfs];
+    __shared__ __align__(16) __half At[kWarps][32][kW1Stride];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kMlpHalfs / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(W)[i] = reinterpret_cast<const uint32_t*>(sd.s.mlp_h)[i];
+    __syncthreads();
+    const __half2* table = reinterpret_cast<const __half2*>(sd.s.table_h);
+    const int n_batches = (n + 31) / 32;
+    const int g = lane >> 2, t = lane & 3;
+    for (int bidx = blockIdx.x * kWarps + warp; bidx < n_batches; bidx += gridDim.x * kWarps) {
+        const int p = bidx * 32 + lane;
+        __half2* arow = reinterpret_cast<__half2*>(&At[warp][lane][0]);
+        if (p < n) {
+            const float n0 = fminf(fmaxf(x[p * 3], 0.f), 1.f), n1 = fminf(fmaxf(x[p * 3 + 1], 0.f), 1.f), n2 = fminf(fmaxf(x[p * 3 + 2], 0.f), 1.f);
+#pragma unroll 4
+            for (int l = 0; l < kLevels; l++) arow[l] = hash_encode_level(table, sd.hl, l, n0, n1, n2);
+        } else {
+            for (int l = 0; l < kLevels; l++) arow[l] = __floats2half2_rn(0.f, 0.f);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            float o[2][4];
+            mlp_density_tile16(&At[warp][16 * mt][0], W, lane, o);
+            const int rA = bidx * 32 + 16 * mt + g, rB = rA + 8;
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+                if (rA < n) *reinterpret_cast<__half2*>(out16 + (long)rA * 16 + nt * 8 + 2 * t) = __floats2half2_rn(o[nt][0], o[nt][1]);
+                if (rB < n) *reinterpret_cast<__half2*>(out16 + (long)rB * 16 + nt * 8 + 2 * t) = __floats2half2_rn(o[nt][2], o[nt][3]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// fp16 A fragment of the colour net from 15 fp32 inputs per row (column 0 = tcnn's 1.0 pad, column c = input c - 1)
+__device__ __forceinline__ void colour_input_fragment(const float* __restrict__ in15, int n, int rA, int rB, int t, uint32_t c3[1][4]) {
+    auto v = [&](int r, int c) { return r < n ? (c == 0 ? 1.0f : in15[(long)r * 15 + c - 1]) : 0.f; };
+    c3[0][0] = pack_h2(v(rA, 2 * t), v(rA, 2 * t + 1));
+    c3[0][1] = pack_h2(v(rB, 2 * t), v(rB, 2 * t + 1));
+    c3[0][2] = pack_h2(v(rA, 8 + 2 * t), v(rA, 9 + 2 * t));
+    c3[0][3] = pack_h2(v(rB, 8 + 2 * t), v(rB, 9 + 2 * t));
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) tcnn_mlp_forward_kernel(const __half* __restrict__ mlp_h, const float* __restrict__ in15,
+                                                                       int n, __half* __restrict__ out3) {
+    __shared__ __align__(16) __half W[kMlpHalfs];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kMlpHalfs / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(W)[i] = reinterpret_cast<const uint32_t*>(mlp_h)[i];
+    __syncthreads();
+    const int g = lane >> 2, t = lane & 3;
+    const int n_tiles = (n + 15) / 16;
+    for (int tile = blockIdx.x * kWarps + warp; tile < n_tiles; tile += gridDim.x * kWarps) {
+        const int rA = tile * 16 + g, rB = rA + 8;
+        uint32_t c3[1][4];
+        colour_input_fragment(in15, n, rA, rB, t, c3);
+        float c5[4];
+        mlp_colour_tile16(c3, W, lane, c5);
+        // sigmoid output activation, fp16 result (tcnn)
+        if (t < 2) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int row = h ? rB : rA;
+                if (row >= n) continue;
+                const __half s0 = __float2half_rn(1.0f / (1.0f + expf(-c5[2 * h])));
+                if (t == 0) {
+                    out3[(long)row * 3] = s0;
+                    out3[(long)row * 3 + 1] = __float2half_rn(1.0f / (1.0f + expf(-c5[2 * h + 1])));
+                } else {
+                    out3[(long)row * 3 + 2] = s0;
+                }
+            }
+        }
+    }
+}
+
 // ================================================================================================
 // per-frame preparation
 // ================================================================================================
@@ -934,6 +1020,37 @@ int ia_broyden(const IaScene* scene, const float* xd, int n, float* xc, uint8_t*
     int rc = make_scene_dev(scene, sd, false, false);
     if (rc) return rc;
     broyden_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sd, xd, n, xc, valid, j_inv);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_tcnn_encoder_forward(const IaScene* scene, const float* x01, int n, void* out16_h, ia_stream_t stream) {
+    IA_REQUIRE(n >= 0);
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(x01 && out16_h && scene && scene->table_h && scene->mlp_h);
+    SceneDev sd;
+    sd.s = *scene;
+    host_hash_levels(sd.hl, nullptr);
+    sd.filter_thr = 0.f;
+    constexpr int kW = 8;
+    const int n_batches = (n + 31) / 32;
+    const int grid = min(sm_count() * 4, (n_batches + kW - 1) / kW);
+    if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    tcnn_encoder_forward_kernel<kW><<<grid, kW * 32, 0, (cudaStream_t)stream>>>(sd, x01, n, reinterpret_cast<__half*>(out16_h));
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_tcnn_mlp_forward(const void* mlp_h, const float* in15, int n, void* out3_h, ia_stream_t stream) {
+    IA_REQUIRE(n >= 0);
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(mlp_h && in15 && out3_h);
+    constexpr int kW = 8;
+    const int n_tiles = (n + 15) / 16;
+    const int grid = min(sm_count() * 4, (n_tiles + kW - 1) / kW);
+    if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    tcnn_mlp_forward_kernel<kW><<<grid, kW * 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(mlp_h), in15, n,
+                                                                            reinterpret_cast<__half*>(out3_h));
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

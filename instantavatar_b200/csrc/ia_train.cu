@@ -677,6 +677,232 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const __half* __restrict__ s
 }
 
 // ================================================================================================
+// backward of the two tiny-cuda-nn modules as separate operators (`tinycudann`-named shim): the same tensor-core dgrad
+// chain and scratch-row layout as ngp_backward_kernel, cut at the module boundary.  The scratch rows of the layers a
+// module does not own stay zero (the host clears the scratch), so wgrad_kernel adds nothing for them.
+// ================================================================================================
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+struct TcnnEncBwdArgs {
+    SceneDev sd;
+    const float* x; const float* dout16; int n; float grad_scale;
+    float* grad_enc; __half* scratch; float* denc_out;
+};
+
+// density net of one 16-row tile: forward recompute of the hidden layer, upstream d(out16) from global memory
+__device__ __forceinline__ void enc_bwd_tile16(const __half* __restrict__ At, const __half* __restrict__ Wsm, int lane, int mt,
+                                               const float* __restrict__ dout16, int n, float gscale, __half* __restrict__ scratch,
+                                               long row0, float (*dEnc)[33]) {
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t a1[2][4];
+#pragma unroll
+    for (int kt = 0; kt < 2; kt++) {
+        const __half* p0 = At + g * kW1Stride + kt * 16 + 2 * t;
+        const __half* p1 = At + (g + 8) * kW1Stride + kt * 16 + 2 * t;
+        a1[kt][0] = *reinterpret_cast<const uint32_t*>(p0);
+        a1[kt][1] = *reinterpret_cast<const uint32_t*>(p1);
+        a1[kt][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+        a1[kt][3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
+    }
+    float acc[8][4];
+    uint32_t aH1[4][4], aD[4][4];
+    layer_n64<2>(Wsm + kW1Off, kW1Stride, a1, g, t, acc);
+    chain_relu(acc, aH1);
+    const long rA = row0 + 16 * mt + g, rB = rA + 8;
+    const bool okA = rA < n, okB = rB < n;
+    auto d = [&](long r, int c) { return r < n ? dout16[r * 16 + c] * gscale : 0.f; };
+    uint32_t a2[1][4] = {{pack_h2(d(rA, 2 * t), d(rA, 2 * t + 1)), pack_h2(d(rB, 2 * t), d(rB, 2 * t + 1)),
+                          pack_h2(d(rA, 8 + 2 * t), d(rA, 9 + 2 * t)), pack_h2(d(rB, 8 + 2 * t), d(rB, 9 + 2 * t))}};
+    __half* rowA = scratch + rA * kRowHalfs;
+    __half* rowB = scratch + rB * kRowHalfs;
+    if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffD2 + 2 * t) = a2[0][0]; *reinterpret_cast<uint32_t*>(rowA + kOffD2 + 8 + 2 * t) = a2[0][2]; }
+    if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffD2 + 2 * t) = a2[0][1]; *reinterpret_cast<uint32_t*>(rowB + kOffD2 + 8 + 2 * t) = a2[0][3]; }
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+        if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffH1 + kt * 16 + 2 * t) = aH1[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffH1 + kt * 16 + 8 + 2 * t) = aH1[kt][2]; }
+        if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffH1 + kt * 16 + 2 * t) = aH1[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffH1 + kt * 16 + 8 + 2 * t) = aH1[kt][3]; }
+    }
+    layer_n64<1>(Wsm + kW2TOff, kW2TStride, a2, g, t, acc);   // dH1 = d(out16) . W2
+    mask_chain(acc, aH1, aD);                                 // dZ1
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+        if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffD1 + kt * 16 + 2 * t) = aD[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffD1 + kt * 16 + 8 + 2 * t) = aD[kt][2]; }
+        if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffD1 + kt * 16 + 2 * t) = aD[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffD1 + kt * 16 + 8 + 2 * t) = aD[kt][3]; }
+    }
+#pragma unroll
+    for (int kt = 0; kt < 2; kt++) {
+        if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffEnc + kt * 16 + 2 * t) = a1[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffEnc + kt * 16 + 8 + 2 * t) = a1[kt][2]; }
+        if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffEnc + kt * 16 + 2 * t) = a1[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffEnc + kt * 16 + 8 + 2 * t) = a1[kt][3]; }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {                          // dEnc = dZ1 . W1 (N = 32)
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kt = 0; kt < 4; kt++) {
+            uint32_t b0, b1;
+            load_b(Wsm + kW1TOff, kW1TStride, nt, kt, g, t, b0, b1);
+            mma16816(e, aD[kt], b0, b1);
+        }
+        dEnc[16 * mt + g][nt * 8 + 2 * t] = e[0]; dEnc[16 * mt + g][nt * 8 + 2 * t + 1] = e[1];
+        dEnc[16 * mt + g + 8][nt * 8 + 2 * t] = e[2]; dEnc[16 * mt + g + 8][nt * 8 + 2 * t + 1] = e[3];
+    }
+}
+
+__global__ void __launch_bounds__(kBwdWarps * 32, 1) tcnn_encoder_backward_kernel(const __grid_constant__ TcnnEncBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kMlpAllHalfs / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(sm.W)[i] = reinterpret_cast<const uint32_t*>(a.sd.s.mlp_h)[i];
+    __syncthreads();
+    const __half2* table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
+    BwdWarpSmem& ws = sm.w[warp];
+    const float inv_scale = 1.0f / a.grad_scale;
+    float* ggrid = a.grad_enc ? a.grad_enc + IA_ENC_MLP_PARAMS : nullptr;
+    const int n_tiles = (a.n + 31) / 32;
+    for (int tile = blockIdx.x * kBwdWarps + warp; tile < n_tiles; tile += gridDim.x * kBwdWarps) {
+        const int p = tile * 32 + lane;
+        const bool has = p < a.n;
+        float n0 = 0, n1 = 0, n2 = 0;
+        __half2* arow = reinterpret_cast<__half2*>(&ws.At[lane][0]);
+        if (has) {
+            n0 = fminf(fmaxf(a.x[p * 3], 0.f), 1.f); n1 = fminf(fmaxf(a.x[p * 3 + 1], 0.f), 1.f); n2 = fminf(fmaxf(a.x[p * 3 + 2], 0.f), 1.f);
+#pragma unroll 4
+            for (int l = 0; l < kLevels; l++) arow[l] = hash_encode_level(table, a.sd.hl, l, n0, n1, n2);
+        } else {
+#pragma unroll
+            for (int l = 0; l < kLevels; l++) arow[l] = __floats2half2_rn(0.f, 0.f);
+        }
+        __syncwarp();
+        enc_bwd_tile16(&ws.At[0][0], sm.W, lane, 0, a.dout16, a.n, a.grad_scale, a.scratch, (long)tile * 32, ws.dEnc);
+        enc_bwd_tile16(&ws.At[16][0], sm.W, lane, 1, a.dout16, a.n, a.grad_scale, a.scratch, (long)tile * 32, ws.dEnc);
+        __syncwarp();
+        if (has && a.denc_out) {
+#pragma unroll
+            for (int c = 0; c < 32; c++) a.denc_out[(long)p * 32 + c] = ws.dEnc[lane][c] * inv_scale;
+        }
+        if (ggrid && has) {
+#pragma unroll 1
+            for (int l = 0; l < kLevels; l++) {
+                const float s = a.sd.hl.scale[l];
+                const float px = __fmaf_rn(n0, s, 0.5f), py = __fmaf_rn(n1, s, 0.5f), pz = __fmaf_rn(n2, s, 0.5f);
+                const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
+                const uint32_t cx = (uint32_t)flx, cy = (uint32_t)fly, cz = (uint32_t)flz;
+                const float wx = px - flx, wy = py - fly, wz = pz - flz;
+                const uint32_t res = a.sd.hl.res[l], hs = a.sd.hl.size[l];
+                const float g0 = ws.dEnc[lane][2 * l] * inv_scale, g1 = ws.dEnc[lane][2 * l + 1] * inv_scale;
+                float2* tb = reinterpret_cast<float2*>(ggrid) + a.sd.hl.offset[l];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float wt = (((k & 1) ? wx : 1.f - wx) * ((k & 2) ? wy : 1.f - wy)) * ((k & 4) ? wz : 1.f - wz);
+                    const uint32_t idx = grid_index(cx + (k & 1), cy + ((k >> 1) & 1), cz + (k >> 2), res, hs);
+                    atomicAdd(tb + idx, make_float2(wt * g0, wt * g1));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+struct TcnnMlpBwdArgs {
+    const __half* mlp_h; const float* in15; const float* dout3; int n; float grad_scale;
+    __half* scratch; float* din15;
+};
+
+__global__ void __launch_bounds__(kBwdWarps * 32, 1) tcnn_mlp_backward_kernel(const __grid_constant__ TcnnMlpBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __half* W = reinterpret_cast<__half*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kMlpAllHalfs / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(W)[i] = reinterpret_cast<const uint32_t*>(a.mlp_h)[i];
+    __syncthreads();
+    const int g = lane >> 2, t = lane & 3;
+    const float gscale = a.grad_scale, inv_scale = 1.0f / a.grad_scale;
+    const int n = a.n;
+    const int n_tiles = (n + 15) / 16;
+    for (int tile = blockIdx.x * kBwdWarps + warp; tile < n_tiles; tile += gridDim.x * kBwdWarps) {
+        const long rA = (long)tile * 16 + g, rB = rA + 8;
+        const bool okA = rA < n, okB = rB < n;
+        // ---- forward recompute (same fragments as tcnn_mlp_forward_kernel) ----
+        auto v = [&](long r, int c) { return r < n ? (c == 0 ? 1.0f : a.in15[r * 15 + c - 1]) : 0.f; };
+        uint32_t c3[1][4] = {{pack_h2(v(rA, 2 * t), v(rA, 2 * t + 1)), pack_h2(v(rB, 2 * t), v(rB, 2 * t + 1)),
+                              pack_h2(v(rA, 8 + 2 * t), v(rA, 9 + 2 * t)), pack_h2(v(rB, 8 + 2 * t), v(rB, 9 + 2 * t))}};
+        float acc[8][4];
+        uint32_t aH2[4][4], aH3[4][4], aD[4][4];
+        layer_n64<1>(W + kW3Off, kW3Stride, c3, g, t, acc);
+        chain_relu(acc, aH2);
+        layer_n64<4>(W + kW4Off, kW4Stride, aH2, g, t, acc);
+        chain_relu(acc, aH3);
+        float c5[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kt = 0; kt < 4; kt++) {
+            uint32_t b0, b1;
+            load_b(W + kW5Off, kW5Stride, 0, kt, g, t, b0, b1);
+            mma16816(c5, aH3[kt], b0, b1);
+        }
+        // ---- upstream gradient through the sigmoid ----
+        auto dsgm = [](float x) { const float s = 1.0f / (1.0f + expf(-x)); return s * (1.0f - s); };
+        auto du = [&](long r, int c) { return r < n ? a.dout3[r * 3 + c] : 0.f; };
+        float d5[4] = {0.f, 0.f, 0.f, 0.f};
+        if (t == 0) {
+            d5[0] = du(rA, 0) * dsgm(c5[0]) * gscale; d5[1] = du(rA, 1) * dsgm(c5[1]) * gscale;
+            d5[2] = du(rB, 0) * dsgm(c5[2]) * gscale; d5[3] = du(rB, 1) * dsgm(c5[3]) * gscale;
+        } else if (t == 1) {
+            d5[0] = du(rA, 2) * dsgm(c5[0]) * gscale; d5[2] = du(rB, 2) * dsgm(c5[2]) * gscale;
+        }
+        __half* rowA = a.scratch + rA * kRowHalfs;
+        __half* rowB = a.scratch + rB * kRowHalfs;
+        uint32_t a5[1][4] = {{pack_h2(d5[0], d5[1]), pack_h2(d5[2], d5[3]), 0u, 0u}};
+        if (okA) *reinterpret_cast<uint32_t*>(rowA + kOffD5 + 2 * t) = a5[0][0];
+        if (okB) *reinterpret_cast<uint32_t*>(rowB + kOffD5 + 2 * t) = a5[0][1];
+#pragma unroll
+        for (int kt = 0; kt < 4; kt++) {
+            if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffH3 + kt * 16 + 2 * t) = aH3[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffH3 + kt * 16 + 8 + 2 * t) = aH3[kt][2]; }
+            if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffH3 + kt * 16 + 2 * t) = aH3[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffH3 + kt * 16 + 8 + 2 * t) = aH3[kt][3]; }
+        }
+        layer_n64<1>(W + kW5TOff, kW5TStride, a5, g, t, acc);    // dH3 = dO5 . W5
+        mask_chain(acc, aH3, aD);                                // dZ3
+#pragma unroll
+        for (int kt = 0; kt < 4; kt++) {
+            if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffD4 + kt * 16 + 2 * t) = aD[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffD4 + kt * 16 + 8 + 2 * t) = aD[kt][2]; }
+            if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffD4 + kt * 16 + 2 * t) = aD[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffD4 + kt * 16 + 8 + 2 * t) = aD[kt][3]; }
+            if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffH2 + kt * 16 + 2 * t) = aH2[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffH2 + kt * 16 + 8 + 2 * t) = aH2[kt][2]; }
+            if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffH2 + kt * 16 + 2 * t) = aH2[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffH2 + kt * 16 + 8 + 2 * t) = aH2[kt][3]; }
+        }
+        layer_n64<4>(W + kW4TOff, kW4TStride, aD, g, t, acc);    // dH2 = dZ3 . W4
+        mask_chain(acc, aH2, aD);                                // dZ2'
+#pragma unroll
+        for (int kt = 0; kt < 4; kt++) {
+            if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffD3 + kt * 16 + 2 * t) = aD[kt][0]; *reinterpret_cast<uint32_t*>(rowA + kOffD3 + kt * 16 + 8 + 2 * t) = aD[kt][2]; }
+            if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffD3 + kt * 16 + 2 * t) = aD[kt][1]; *reinterpret_cast<uint32_t*>(rowB + kOffD3 + kt * 16 + 8 + 2 * t) = aD[kt][3]; }
+        }
+        if (okA) { *reinterpret_cast<uint32_t*>(rowA + kOffC3 + 2 * t) = c3[0][0]; *reinterpret_cast<uint32_t*>(rowA + kOffC3 + 8 + 2 * t) = c3[0][2]; }
+        if (okB) { *reinterpret_cast<uint32_t*>(rowB + kOffC3 + 2 * t) = c3[0][1]; *reinterpret_cast<uint32_t*>(rowB + kOffC3 + 8 + 2 * t) = c3[0][3]; }
+        if (a.din15) {                                           // d(in16) = dZ2' . W3'  (N = 16), column c -> input c - 1
+            float d2[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+                d2[nt][0] = d2[nt][1] = d2[nt][2] = d2[nt][3] = 0.f;
+#pragma unroll
+                for (int kt = 0; kt < 4; kt++) {
+                    uint32_t b0, b1;
+                    load_b(W + kW3TOff, kW3TStride, nt, kt, g, t, b0, b1);
+                    mma16816(d2[nt], aD[kt], b0, b1);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int c = nt * 8 + 2 * t + j;
+                    if (c >= 1) {
+                        if (okA) a.din15[rA * 15 + c - 1] = d2[nt][j] * inv_scale;
+                        if (okB) a.din15[rB * 15 + c - 1] = d2[nt][2 + j] * inv_scale;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ================================================================================================
 // fused dense Adam (torch.optim.Adam semantics, DNeRF.py:46-50) + fp16 working-copy refresh
 // ================================================================================================
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -1018,6 +1244,7 @@ int ia_composite_bwd(int n_rays, const float* near, const float* far, const floa
 }
 
 size_t ia_ngp_backward_scratch_bytes(int capacity) { return (size_t)capacity * kRowHalfs * sizeof(__half); }
+size_t ia_tcnn_backward_scratch_bytes(int n) { return (size_t)((n + 31) / 32 * 32) * kRowHalfs * sizeof(__half) + 16; }
 
 int ia_ngp_backward(const IaScene* scene, const float* xc, const float* dsigma, const float* drgb, const int* count,
                     int capacity, float grad_scale, float* grad_enc, float* grad_col, void* scratch, float* denc_out,
@@ -1047,6 +1274,69 @@ int ia_ngp_backward(const IaScene* scene, const float* xc, const float* dsigma, 
     ngp_backward_kernel<<<min(sms, (n_tiles + kBwdWarps - 1) / kBwdWarps), kBwdWarps * 32, smem, st>>>(a);
     if (grad_enc)
         wgrad_kernel<<<min(sms * 2, (capacity + 31) / 32), 256, 0, st>>>(a.scratch, count, capacity, 1.0f / grad_scale, grad_enc, grad_col);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_tcnn_encoder_backward(const IaScene* scene, const float* x01, const float* dout16, int n, float grad_scale, float* grad_enc,
+                             float* grad_col_dummy, void* scratch, float* denc_out, ia_stream_t stream) {
+    IA_REQUIRE(n >= 0);
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(x01 && dout16 && scratch && grad_scale > 0.f && (grad_enc || denc_out) && (!grad_enc || grad_col_dummy));
+    IA_REQUIRE(scene && scene->table_h && scene->mlp_h);
+    TcnnEncBwdArgs a;
+    a.sd.s = *scene;
+    host_hash_levels(a.sd.hl, nullptr);
+    a.sd.filter_thr = 0.f;
+    a.x = x01; a.dout16 = dout16; a.n = n; a.grad_scale = grad_scale; a.grad_enc = grad_enc;
+    a.scratch = reinterpret_cast<__half*>(scratch); a.denc_out = denc_out;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sizeof(BwdSmem);
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(tcnn_encoder_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set.set();
+    }
+    const int sms = sm_count();
+    if (sms <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    IA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)((n + 31) / 32 * 32) * kRowHalfs * sizeof(__half), st));
+    const int n_tiles = (n + 31) / 32;
+    tcnn_encoder_backward_kernel<<<min(sms, (n_tiles + kBwdWarps - 1) / kBwdWarps), kBwdWarps * 32, smem, st>>>(a);
+    if (grad_enc) {
+        // the row count lives in device memory for wgrad_kernel: the first 4 bytes past the rows
+        int* count_dev = reinterpret_cast<int*>(reinterpret_cast<char*>(scratch) + (size_t)((n + 31) / 32 * 32) * kRowHalfs * sizeof(__half));
+        set_int_kernel<<<1, 1, 0, st>>>(count_dev, n);
+        wgrad_kernel<<<min(sms * 2, (n + 31) / 32), 256, 0, st>>>(a.scratch, count_dev, n, 1.0f / grad_scale, grad_enc, grad_col_dummy);
+    }
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_tcnn_mlp_backward(const void* mlp_h, const float* in15, const float* dout3, int n, float grad_scale, float* grad_col,
+                         float* grad_enc_dummy, void* scratch, float* din15, ia_stream_t stream) {
+    IA_REQUIRE(n >= 0);
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(mlp_h && in15 && dout3 && scratch && grad_scale > 0.f && (grad_col || din15) && (!grad_col || grad_enc_dummy));
+    TcnnMlpBwdArgs a;
+    a.mlp_h = reinterpret_cast<const __half*>(mlp_h); a.in15 = in15; a.dout3 = dout3; a.n = n; a.grad_scale = grad_scale;
+    a.scratch = reinterpret_cast<__half*>(scratch); a.din15 = din15;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)kMlpAllHalfs * sizeof(__half);
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(tcnn_mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set.set();
+    }
+    const int sms = sm_count();
+    if (sms <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    IA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)((n + 31) / 32 * 32) * kRowHalfs * sizeof(__half), st));
+    const int n_tiles = (n + 15) / 16;
+    tcnn_mlp_backward_kernel<<<min(sms, (n_tiles + kBwdWarps - 1) / kBwdWarps), kBwdWarps * 32, smem, st>>>(a);
+    if (grad_col) {
+        int* count_dev = reinterpret_cast<int*>(reinterpret_cast<char*>(scratch) + (size_t)((n + 31) / 32 * 32) * kRowHalfs * sizeof(__half));
+        set_int_kernel<<<1, 1, 0, st>>>(count_dev, n);
+        wgrad_kernel<<<min(sms * 2, (n + 31) / 32), 256, 0, st>>>(a.scratch, count_dev, n, 1.0f / grad_scale, grad_enc_dummy, grad_col);
+    }
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

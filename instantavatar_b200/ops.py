@@ -426,6 +426,51 @@ def knn1(pts, verts):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# the two tiny-cuda-nn modules as separate operators (bound by the in-repo `tinycudann` module)
+# ------------------------------------------------------------------------------------------------------------------
+def _tcnn_scratch(n, dev):
+    nbytes = int(lib().ia_tcnn_backward_scratch_bytes(C.c_int(n)))
+    key = ("tcnn", dev.index)
+    if key not in _SCRATCH or _SCRATCH[key].numel() < nbytes:
+        _SCRATCH[key] = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    return _SCRATCH[key]
+
+
+def tcnn_encoder_forward(scene: Scene, x01):
+    x01 = x01.reshape(-1, 3).float().contiguous()
+    out = torch.empty((x01.shape[0], 16), device=x01.device, dtype=torch.float16)
+    _lib.count(1); check(lib().ia_tcnn_encoder_forward(C.byref(scene.c_struct()), ptr(x01, f32), C.c_int(x01.shape[0]), ptr(out), stream()))
+    return out
+
+
+def tcnn_encoder_backward(scene: Scene, x01, dout16, grad_enc=None, want_denc=False, grad_scale=128.0):
+    x01 = x01.reshape(-1, 3).float().contiguous(); dout16 = dout16.reshape(-1, 16).float().contiguous()
+    n, dev = x01.shape[0], x01.device
+    denc = torch.empty((n, 32), device=dev, dtype=f32) if want_denc else None
+    dummy = torch.zeros(_lib.IA_COL_MLP_PARAMS, device=dev, dtype=f32) if grad_enc is not None else None
+    _lib.count(3); check(lib().ia_tcnn_encoder_backward(C.byref(scene.c_struct()), ptr(x01, f32), ptr(dout16, f32), C.c_int(n), C.c_float(grad_scale),
+                                                        ptr(grad_enc, f32), ptr(dummy), ptr(_tcnn_scratch(n, dev)), ptr(denc), stream()))
+    return denc
+
+
+def tcnn_mlp_forward(mlp_h, in15):
+    in15 = in15.reshape(-1, 15).float().contiguous()
+    out = torch.empty((in15.shape[0], 3), device=in15.device, dtype=torch.float16)
+    _lib.count(1); check(lib().ia_tcnn_mlp_forward(ptr(mlp_h, torch.float16), ptr(in15, f32), C.c_int(in15.shape[0]), ptr(out), stream()))
+    return out
+
+
+def tcnn_mlp_backward(mlp_h, in15, dout3, grad_col=None, want_din=False, grad_scale=128.0):
+    in15 = in15.reshape(-1, 15).float().contiguous(); dout3 = dout3.reshape(-1, 3).float().contiguous()
+    n, dev = in15.shape[0], in15.device
+    din = torch.zeros((n, 15), device=dev, dtype=f32) if want_din else None
+    dummy = torch.zeros(_lib.IA_ENC_MLP_PARAMS, device=dev, dtype=f32) if grad_col is not None else None
+    _lib.count(3); check(lib().ia_tcnn_mlp_backward(ptr(mlp_h, torch.float16), ptr(in15, f32), ptr(dout3, f32), C.c_int(n), C.c_float(grad_scale),
+                                                    ptr(grad_col, f32), ptr(dummy), ptr(_tcnn_scratch(n, dev)), ptr(din), stream()))
+    return din
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # device guard: every operator launches on the current stream OF THE DEVICE ITS TENSORS LIVE ON (one process may hold
 # tensors on several GPUs; function attributes and SM counts are cached per device inside the library)
 # ------------------------------------------------------------------------------------------------------------------

@@ -137,7 +137,8 @@ def test_two_gpu_frame_and_gradient():
     assert ret["frame_equal"], "cooperative frame differs from the single-GPU frame"
     assert ret["gnorm"] > 0 and ret["rel_enc"] < 1e-3 and ret["rel_col"] < 1e-3, dict(ret)
     # sharded optimiser == replicated optimiser up to the summation order of the gradient (Adam normalises the update, so
-    # an entry whose gradient is pure rounding noise can move by a full lr step in either run: bounded by 3 steps x lr)
+    # an entry whose gradient is pure rounding noise can move by a full lr step in OPPOSITE directions in the two runs:
+    # the worst case is 2 x 3 steps x lr = 6e-2; the mean difference must be tiny)
     assert ret["fp16_image_same_on_ranks"] and ret["adam_steps"] == (3, 3), dict(ret)
-    assert ret["param_moved"] > 1e-3 and ret["param_max_diff"] <= 3.5e-2 and ret["param_mean_diff"] < 1e-5, dict(ret)
+    assert ret["param_moved"] > 1e-3 and ret["param_max_diff"] <= 6.1e-2 and ret["param_mean_diff"] < 1e-5, dict(ret)
     assert ret["fp16_frac_diff"] < 1e-3, dict(ret)
