@@ -94,3 +94,24 @@ def test_reference_import_statements():
     import instantavatar_b200.models.dnerf as m
     assert Rays is m.Rays and ForwardDeformer.__module__.startswith("instantavatar_b200")
     assert DensityGrid.__module__.startswith("instantavatar_b200") and SMPLParamEmbedding.__module__.startswith("instantavatar_b200")
+
+
+def test_reference_ngp_file_runs_on_the_tinycudann_shim():
+    """the reference's OWN models/networks/ngp.py, loaded from /root/reference by path, builds on the in-repo `tinycudann`
+    module: same sub-module names and flat parameter sizes (CPU: construction only; the forward is a GPU test)"""
+    import importlib.util
+    import sys
+    ref = "/root/reference/instant_avatar/models/networks/ngp.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not mounted (GPU box)")
+    import tinycudann  # the shim must win the import inside the reference file
+    assert "ia_b200" in tinycudann.__version__
+    spec = importlib.util.spec_from_file_location("_ref_ngp_under_shim", ref)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from instantavatar_b200.config import Cfg
+    net = mod.NeRFNGPNet(Cfg({"center": [0, -0.3, 0], "scale": [2.5, 2.5, 2.5]}))
+    sizes = {k: v.numel() for k, v in net.named_parameters()}
+    assert sizes == {"encoder.params": 3072 + 2 * 6513496, "color_net.params": 6144}
+    assert set(dict(net.named_buffers())) == {"center", "scale"}
+    sys.modules.pop("_ref_ngp_under_shim", None)
