@@ -175,9 +175,13 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 def bench_frame_sharded(model, batch, device, rank, world, flush, steps=20, warmup=5):
     """BASELINE.json config 3 (one frame, rays sharded over the GPUs): latency of ONE 512x512 frame rendered cooperatively
-    -- occupancy queries sharded + 1 MB max-all-reduce, ray tiles round-robin, RGBA gathered on rank 0 (strong scaling)."""
+    (strong scaling).  Two exchange paths, both measured, both checked bit-equal to the single-GPU frame:
+      nccl : occupancy queries sharded + 1 MB max-all-reduce, ray tiles round-robin, RGBA all-gather (+ un-permute);
+      peer : the same exchanges INSIDE the kernels over NVLink peer memory (parallel.PeerFrame: atomics into every rank's
+             density grid, RGBA stores into every rank's image) -- two barriers, no collective."""
     import torch
     import torch.distributed as dist
+    from instantavatar_b200 import parallel
     model.eval()
     torch.manual_seed(99)  # identical jitter on every rank
     jit = torch.rand((5, 64, 64, 64, 3), device=device)
@@ -185,26 +189,49 @@ def bench_frame_sharded(model, batch, device, rank, world, flush, steps=20, warm
     b = {k: v.clone() for k, v in batch.items()}
     for k in ("betas", "body_pose", "global_orient", "transl"):
         dist.broadcast(b[k], 0)
-    graphed = None
+    rgb, _, alpha, _ = model.render_image_fast(dict(b), (H, W), jit)
+    single = torch.cat([rgb.reshape(-1, 3), alpha.reshape(-1, 1)], dim=1).clone()
+    peer, peer_err = None, None
     try:
-        from instantavatar_b200.graphs import GraphedShardedFrame
-        graphed = GraphedShardedFrame(model, b, (H, W), rank, world, jit)
-    except Exception as exc:  # NCCL capture unavailable: fall back to eager launches
-        if rank == 0:
-            print(f"[bench] sharded-frame graph capture failed ({type(exc).__name__}), running eagerly", file=sys.stderr)
-    run = (lambda: graphed()) if graphed is not None else (lambda: model.render_image_sharded(b, (H, W), rank, world, jit))
-    for _ in range(warmup):
-        run()
-    dist.barrier(); torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for a, e in ev:
-        flush.zero_()
-        a.record(); run(); e.record()
-    dist.barrier(); torch.cuda.synchronize()
-    ms = torch.tensor([sum(a.elapsed_time(e) for a, e in ev) / steps], device=device, dtype=torch.float64)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return {"ms_per_frame": float(ms.item()), "rays_per_s": N_RAYS / (float(ms.item()) * 1e-3), "scaling": "strong",
-            "tile_rays": 2048, "collectives": "all_reduce(max) of the 1 MB density grid + gather of RGBA rows", "cuda_graph": graphed is not None}
+        peer = parallel.PeerFrame(H * W, device)
+    except Exception as exc:  # platform without peer mapping: NCCL path only
+        peer_err = f"{type(exc).__name__}: {exc}"[:200]
+    ok = torch.tensor([1.0 if peer is not None else 0.0], device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() == 0:
+        peer = None
+    res = {"scaling": "strong", "tile_rays": 2048}
+    for name, pf in (("nccl", None), ("peer", peer)):
+        if name == "peer" and pf is None:
+            res["peer_unavailable"] = peer_err or "another rank could not map peer memory"
+            continue
+        graphed = None
+        try:
+            from instantavatar_b200.graphs import GraphedShardedFrame
+            graphed = GraphedShardedFrame(model, b, (H, W), rank, world, jit, peer=pf)
+        except Exception as exc:  # capture unavailable: eager launches
+            if rank == 0:
+                print(f"[bench] sharded-frame graph capture failed for {name} ({type(exc).__name__}: {exc}), running eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
+        run = (lambda: graphed()) if graphed is not None else (lambda: model.render_image_sharded(b, (H, W), rank, world, jit, peer=pf))
+        for _ in range(warmup):
+            img = run()
+        dist.barrier(); torch.cuda.synchronize()
+        equal = torch.tensor([1.0 if (img is not None and torch.equal(img, single)) else 0.0], device=device)
+        dist.all_reduce(equal, op=dist.ReduceOp.MIN)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, e in ev:
+            flush.zero_()
+            a.record(); run(); e.record()
+        dist.barrier(); torch.cuda.synchronize()
+        ms = torch.tensor([sum(a.elapsed_time(e) for a, e in ev) / steps], device=device, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        res[name] = {"ms_per_frame": float(ms.item()), "rays_per_s": N_RAYS / (float(ms.item()) * 1e-3), "bit_equal_all_ranks": bool(equal.item() == 1.0),
+                     "cuda_graph": graphed is not None}
+    best = min((k for k in ("nccl", "peer") if k in res), key=lambda k: res[k]["ms_per_frame"])
+    res.update({"ms_per_frame": res[best]["ms_per_frame"], "rays_per_s": res[best]["rays_per_s"], "path": best,
+                "bit_equal": all(res[k]["bit_equal_all_ranks"] for k in ("nccl", "peer") if k in res)})
+    return res
 
 
 def bench_ref_structure(model, batch, device, iters=5):
@@ -632,7 +659,10 @@ def run_ours(args):
            "train_ms_per_step": train["ms_per_step"], "train_rays_per_step": train["rays_per_step"], "train_scaling": "strong"}
     if sharded is not None:
         cfg.update({"frame_sharded_ms": sharded["ms_per_frame"], "frame_sharded_rays_per_s": sharded["rays_per_s"],
-                    "frame_sharded_bit_equal": checks["frame_bit_equal"], "train_grad_rel_err": checks["train_grad_rel_err"]})
+                    "frame_sharded_path": sharded["path"], "frame_sharded_nccl_ms": sharded["nccl"]["ms_per_frame"],
+                    "frame_sharded_peer_ms": sharded["peer"]["ms_per_frame"] if "peer" in sharded else None,
+                    "frame_sharded_bit_equal": bool(sharded["bit_equal"] and checks["frame_bit_equal"]),
+                    "train_grad_rel_err": checks["train_grad_rel_err"]})
     if comm is not None:
         cfg.update({"grad_collective_ms": comm["ms"], "grad_collective_bus_GBps": comm["bus_GBps"], "grad_collective_bytes": comm["bytes"]})
     line = {

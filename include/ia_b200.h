@@ -152,6 +152,16 @@ int ia_render_fwd(const IaScene* scene /*[host]*/, const float* rays_o, const fl
                   float* alpha, float* counter, void* workspace, size_t workspace_bytes, IaStats* stats,
                   ia_stream_t stream);
 
+/* Ray-sharded frame over peer memory (one process per GPU, NVLink): as ia_render_fwd, and additionally the RGBA of ray i
+ * is stored straight into the [n_pixels][4] fp32 image of every peer at pixel pixel_index[i] (int32 [n_rays]; NULL: i).
+ * peer_rgba: DEVICE array of n_peers image pointers (symmetric-memory mappings of the peers' buffers).  The caller
+ * separates frames with a cross-GPU barrier; no gather collective is needed.  (No counterpart in the reference, which is
+ * single-GPU: BASELINE.json config 3.) */
+int ia_render_fwd_peer(const IaScene* scene /*[host]*/, const float* rays_o, const float* rays_d, const float* near,
+                       const float* far, int n_rays, const float* bg, int image_width, float* rgb, float* depth,
+                       float* alpha, float* counter, void* workspace, size_t workspace_bytes, IaStats* stats,
+                       const int* pixel_index, float* const* peer_rgba, int n_peers, ia_stream_t stream);
+
 /* Point query: per point, max density over the valid canonical correspondences.  Replaces
  * SNARFDeformer.__call__(pts, model, eval_mode) (deformers/snarf_deformer.py:126-165), used by
  * DensityGrid.update / initialize (models/structures/density_grid.py:46-110).
@@ -168,6 +178,13 @@ int ia_deform_query(const IaScene* scene /*[host]*/, const float* pts, int n, in
  * n_shards-th batch of cells starting at `shard` (multi-GPU: the caller max-all-reduces density_max; 0 / 1 = all). */
 int ia_occupancy_query(const IaScene* scene /*[host]*/, const float* jitter, const float* aabb, int G, int passes,
                        float* density_max, void* workspace, int shard, int n_shards, IaStats* stats, ia_stream_t stream);
+
+/* ia_occupancy_query over peer memory: this rank's shard of the cells is max-reduced into the density grid of EVERY rank
+ * with NVLink atomics (positive densities only: ~2 % of the cells), replacing the 1 MB max-all-reduce.  peer_density: DEVICE
+ * array of n_peers pointers to [G][G][G] fp32 buffers, zeroed by their owners before the barrier that precedes the launch. */
+int ia_occupancy_query_peer(const IaScene* scene /*[host]*/, const float* jitter, const float* aabb, int G, int passes,
+                            float* const* peer_density, int n_peers, void* workspace, int shard, int n_shards,
+                            IaStats* stats, ia_stream_t stream);
 
 /* Measurement aid (bench.py `roofline.peak`): the fused kernels' memory access shape in isolation -- every lane gathers
  * trilinear footprints (4 x-pair records = 12 x 32-byte sectors, 12 LDG.E.256) from the L2-resident field `field`

@@ -33,7 +33,17 @@ struct RenderArgs {
     IaStats* stats;
     const int* tile_order;   // optional: tiles sorted by decreasing estimated cost (render_plan kernels)
     const int* n_active;     // number of entries of tile_order
+    // ray-sharded frame over peer memory (NVLink): ray i of this launch is pixel gidx[i] of the frame; its RGBA goes straight
+    // into the [n_pixels][4] image of every peer (symmetric-memory pointers) -- no gather collective afterwards
+    const int* gidx; float* const* peer_rgba; int n_peers;
 };
+
+__device__ __forceinline__ void peer_store_rgba(const RenderArgs& a, int ray, float r, float g, float b, float al) {
+    if (!a.peer_rgba) return;
+    const long px = a.gidx ? a.gidx[ray] : ray;
+    const float4 v = make_float4(r, g, b, al);
+    for (int p = 0; p < a.n_peers; p++) reinterpret_cast<float4*>(a.peer_rgba[p])[px] = v;
+}
 
 struct RenderWarpExtra {
     float qx[64], qy[64], qz[64], qt[64];
@@ -144,6 +154,7 @@ __global__ void __launch_bounds__(256) render_plan_kernel(const __grid_constant_
             if (a.bg) { b0 = a.bg[ray * 3]; b1 = a.bg[ray * 3 + 1]; b2 = a.bg[ray * 3 + 2]; }
             a.rgb[ray * 3 + 0] = 0.f + 1.f * b0; a.rgb[ray * 3 + 1] = 0.f + 1.f * b1; a.rgb[ray * 3 + 2] = 0.f + 1.f * b2;
             a.depth[ray] = 0.f; a.alpha[ray] = 0.f; a.counter[ray] = 0.f;
+            peer_store_rgba(a, ray, 0.f + 1.f * b0, 0.f + 1.f * b1, 0.f + 1.f * b2, 0.f);
         }
     }
 }
@@ -339,6 +350,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
             a.depth[ray] = Dp;
             a.alpha[ray] = 1.0f - T;
             a.counter[ray] = (float)nocc;
+            peer_store_rgba(a, ray, Cr + T * b0, Cg + T * b1, Cb + T * b2, 1.0f - T);
             st_hit += nocc > 0 ? 1u : 0u;
         }
     }
@@ -374,6 +386,7 @@ struct QueryArgs {
     const float* grid_jitter; const float* grid_aabb; int G; float* density_max; int passes;
     int* batch_counter;  // optional: dynamic batch scheduling (zeroed by the launcher)
     int batch_first, batch_stride;  // grid mode: this launch handles batches first, first+stride, ... (multi-GPU sharding)
+    float* const* peer_density; int n_peers;  // grid mode over peer memory: max-reduce into EVERY rank's density (NVLink atomics)
 };
 
 template <int kWarps, bool kKeepXc>
@@ -446,7 +459,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
         warp_eval_samples<kKeepXc>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots, st_load);
         st_samples += act ? 1u : 0u;
         if (act && a.grid_aabb) {
-            if (so.sigma > 0.f) atomicMax(reinterpret_cast<int*>(a.density_max) + cell, __float_as_int(so.sigma));
+            if (so.sigma > 0.f) {
+                // positive densities are ~2 % of the cells: with peer pointers the cross-GPU max-reduction is these few
+                // atomics over NVLink instead of a 1 MB all-reduce after the kernel
+                if (a.peer_density) {
+                    for (int pr = 0; pr < a.n_peers; pr++) atomicMax(reinterpret_cast<int*>(a.peer_density[pr]) + cell, __float_as_int(so.sigma));
+                } else {
+                    atomicMax(reinterpret_cast<int*>(a.density_max) + cell, __float_as_int(so.sigma));
+                }
+            }
         } else if (act) {
             a.sigma[p] = so.sigma;
             a.rgb[p * 3] = so.r; a.rgb[p * 3 + 1] = so.g; a.rgb[p * 3 + 2] = so.b;
@@ -942,9 +963,10 @@ static int launch_query(QueryArgs& a, cudaStream_t stream) {
 
 extern "C" {
 
-int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d, const float* near, const float* far,
-                  int n_rays, const float* bg, int image_width, float* rgb, float* depth, float* alpha, float* counter,
-                  void* workspace, size_t workspace_bytes, IaStats* stats, ia_stream_t stream) {
+static int render_fwd_impl(const IaScene* scene, const float* rays_o, const float* rays_d, const float* near, const float* far,
+                           int n_rays, const float* bg, int image_width, float* rgb, float* depth, float* alpha, float* counter,
+                           void* workspace, size_t workspace_bytes, IaStats* stats, const int* peer_gidx, float* const* peer_rgba,
+                           int n_peers, ia_stream_t stream) {
     IA_REQUIRE(n_rays >= 0);
     if (n_rays == 0) return IA_OK;
     IA_REQUIRE(rays_o && rays_d && near && far && rgb && depth && alpha && counter && workspace);
@@ -958,6 +980,7 @@ int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d
     a.tile_counter = reinterpret_cast<int*>(workspace);
     a.stats = stats;
     a.tile_order = nullptr; a.n_active = nullptr;
+    a.gidx = peer_gidx; a.peer_rgba = peer_rgba; a.n_peers = n_peers;
     cudaStream_t st = (cudaStream_t)stream;
     IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
     // with a large enough workspace the tiles are scheduled longest-first (removes the load-balance tail)
@@ -979,6 +1002,22 @@ int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d
     return IA_OK;
 }
 
+int ia_render_fwd(const IaScene* scene, const float* rays_o, const float* rays_d, const float* near, const float* far,
+                  int n_rays, const float* bg, int image_width, float* rgb, float* depth, float* alpha, float* counter,
+                  void* workspace, size_t workspace_bytes, IaStats* stats, ia_stream_t stream) {
+    return render_fwd_impl(scene, rays_o, rays_d, near, far, n_rays, bg, image_width, rgb, depth, alpha, counter, workspace,
+                           workspace_bytes, stats, nullptr, nullptr, 0, stream);
+}
+
+int ia_render_fwd_peer(const IaScene* scene, const float* rays_o, const float* rays_d, const float* near, const float* far,
+                       int n_rays, const float* bg, int image_width, float* rgb, float* depth, float* alpha, float* counter,
+                       void* workspace, size_t workspace_bytes, IaStats* stats, const int* pixel_index,
+                       float* const* peer_rgba, int n_peers, ia_stream_t stream) {
+    IA_REQUIRE(peer_rgba && n_peers >= 1 && n_peers <= 64);
+    return render_fwd_impl(scene, rays_o, rays_d, near, far, n_rays, bg, image_width, rgb, depth, alpha, counter, workspace,
+                           workspace_bytes, stats, pixel_index, peer_rgba, n_peers, stream);
+}
+
 int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode, float* rgb, float* sigma,
                     float* xc_best, int8_t* best_init, IaStats* stats, ia_stream_t stream) {
     IA_REQUIRE(n >= 0);
@@ -991,13 +1030,14 @@ int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode
     a.best_init = best_init; a.stats = stats;
     a.grid_jitter = nullptr; a.grid_aabb = nullptr; a.G = 0; a.density_max = nullptr; a.passes = 1;
     a.batch_counter = nullptr; a.batch_first = 0; a.batch_stride = 1;
+    a.peer_density = nullptr; a.n_peers = 0;
     return launch_query(a, (cudaStream_t)stream);
 }
 
-extern "C" int ia_occupancy_query(const IaScene* scene, const float* jitter, const float* aabb, int G, int passes,
-                                  float* density_max, void* workspace, int shard, int n_shards, IaStats* stats,
-                                  ia_stream_t stream) {
-    IA_REQUIRE(jitter && aabb && density_max && G > 0 && passes > 0 && passes <= 32);
+static int occupancy_query_impl(const IaScene* scene, const float* jitter, const float* aabb, int G, int passes,
+                                float* density_max, float* const* peer_density, int n_peers, void* workspace, int shard,
+                                int n_shards, IaStats* stats, ia_stream_t stream) {
+    IA_REQUIRE(jitter && aabb && (density_max || peer_density) && G > 0 && passes > 0 && passes <= 32);
     IA_REQUIRE(n_shards >= 1 && shard >= 0 && shard < n_shards);
     QueryArgs a;
     int rc = make_scene_dev(scene, a.sd, false);
@@ -1007,9 +1047,24 @@ extern "C" int ia_occupancy_query(const IaScene* scene, const float* jitter, con
     a.grid_jitter = jitter; a.grid_aabb = aabb; a.G = G; a.density_max = density_max; a.passes = passes;
     a.batch_counter = reinterpret_cast<int*>(workspace);
     a.batch_first = shard; a.batch_stride = n_shards;
+    a.peer_density = peer_density; a.n_peers = n_peers;
     if (workspace) IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream));
-    IA_CHECK_CUDA(cudaMemsetAsync(density_max, 0, sizeof(float) * G * G * G, (cudaStream_t)stream));
+    // peer mode: every rank's buffer is written by all ranks -- the CALLER zeroes it (before the barrier that precedes this launch)
+    if (!peer_density) IA_CHECK_CUDA(cudaMemsetAsync(density_max, 0, sizeof(float) * G * G * G, (cudaStream_t)stream));
     return launch_query(a, (cudaStream_t)stream);
+}
+
+extern "C" int ia_occupancy_query(const IaScene* scene, const float* jitter, const float* aabb, int G, int passes,
+                                  float* density_max, void* workspace, int shard, int n_shards, IaStats* stats,
+                                  ia_stream_t stream) {
+    return occupancy_query_impl(scene, jitter, aabb, G, passes, density_max, nullptr, 0, workspace, shard, n_shards, stats, stream);
+}
+
+extern "C" int ia_occupancy_query_peer(const IaScene* scene, const float* jitter, const float* aabb, int G, int passes,
+                                       float* const* peer_density, int n_peers, void* workspace, int shard, int n_shards,
+                                       IaStats* stats, ia_stream_t stream) {
+    IA_REQUIRE(peer_density && n_peers >= 1 && n_peers <= 64);
+    return occupancy_query_impl(scene, jitter, aabb, G, passes, nullptr, peer_density, n_peers, workspace, shard, n_shards, stats, stream);
 }
 
 int ia_broyden(const IaScene* scene, const float* xd, int n, float* xc, uint8_t* valid, float* j_inv, ia_stream_t stream) {

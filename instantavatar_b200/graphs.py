@@ -154,7 +154,7 @@ class GraphedTrainStep:
 class GraphedShardedFrame:
     """DNeRFModel.render_image_sharded (one frame over several GPUs, two collectives) captured once per rank"""
 
-    def __init__(self, model, batch: dict, img_size, rank, world, jitters, tile=2048, warmup=3):
+    def __init__(self, model, batch: dict, img_size, rank, world, jitters, tile=2048, warmup=3, peer=None):
         self.static_in = {k: v.clone() for k, v in batch.items() if torch.is_tensor(v)}
         self.jitters = jitters.clone()
         model.eval()
@@ -162,12 +162,12 @@ class GraphedShardedFrame:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                model.render_image_sharded(dict(self.static_in), img_size, rank, world, self.jitters, tile)
+                model.render_image_sharded(dict(self.static_in), img_size, rank, world, self.jitters, tile, peer)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = model.render_image_sharded(dict(self.static_in), img_size, rank, world, self.jitters, tile)
+            self.out = model.render_image_sharded(dict(self.static_in), img_size, rank, world, self.jitters, tile, peer)
 
     def __call__(self, batch: dict | None = None):
         if batch is not None:

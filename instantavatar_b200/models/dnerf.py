@@ -254,16 +254,18 @@ class DNeRFModel(torch.nn.Module):
         return losses
 
     @torch.no_grad()
-    def render_image_sharded(self, batch, img_size, rank, world, jitters, tile=2048):
+    def render_image_sharded(self, batch, img_size, rank, world, jitters, tile=2048, peer=None):
         """One frame rendered cooperatively by `world` GPUs (BASELINE.json config 3): per-frame preparation is replicated
         (0.1 ms), the occupancy-grid queries are sharded with one 1 MB max-all-reduce, rays are dealt round-robin in tiles
         of `tile` rays (whole image rows) and the RGBA rows are gathered on rank 0.  `jitters` must be identical on all
-        ranks.  Returns [H*W, 4] (RGBA) on every rank (on rank 0 only when the tiles do not divide evenly)."""
+        ranks.  Returns [H*W, 4] (RGBA) on every rank (on rank 0 only when the tiles do not divide evenly).
+        peer (parallel.PeerFrame): both exchanges happen inside the kernels over NVLink peer memory (atomics into every
+        rank's density grid, RGBA stores into every rank's image); the frame then needs two barriers and no collective."""
         from .. import parallel
         H, W = img_size
         self.deformer.prepare_deformer(batch)
         self.net_coarse.initialize(self.deformer.bbox)
-        self.renderer.density_grid_test.initialize(self.deformer, self.net_coarse, jitters=jitters, shard=(rank, world))
+        self.renderer.density_grid_test.initialize(self.deformer, self.net_coarse, jitters=jitters, shard=(rank, world), peer=peer)
         dev = batch["rays_o"].device
         idx = parallel.shard_tiles_cached(H * W, rank, world, tile, dev)
         # this rank's tiles are picked and moved to the root frame in ONE launch (index form of ia_transform_rays)
@@ -272,6 +274,12 @@ class DNeRFModel(torch.nn.Module):
         rays = Rays(o=o[None], d=d[None], near=near[None], far=far[None])
         self.renderer.image_width = W if tile % (2 * W) == 0 else 0
         bg = batch["bg_color"].reshape(-1, 3)[idx] if batch.get("bg_color", None) is not None else None
+        if peer is not None:
+            # peer-memory path (parallel.PeerFrame): the render kernel stores RGBA into every rank's image over NVLink
+            self.renderer.render_test(rays, BoundModel(self.deformer, self.net_coarse, True), bg,
+                                      peer=peer.image_ptrs(parallel.shard_tiles_cached(H * W, rank, world, tile, dev, torch.int32)))
+            peer.barrier_image()
+            return peer.image
         out = self.renderer.render_test(rays, BoundModel(self.deformer, self.net_coarse, True), bg)
         local = torch.cat([out["rgb_coarse"].reshape(-1, 3), out["alpha_coarse"].reshape(-1, 1)], dim=1)
         img = parallel.all_gather_image(local, H * W, tile)   # every rank ends up with the frame (one all-gather)

@@ -104,9 +104,11 @@ class DensityGrid(torch.nn.Module):
         return density, valid
 
     @torch.no_grad()
-    def initialize(self, deformer, net, iters=5, jitters=None, shard=(0, 1)):
+    def initialize(self, deformer, net, iters=5, jitters=None, shard=(0, 1), peer=None):
         """density_grid.py:94-110 (test-time, per frame).  shard = (rank, world): each rank evaluates every world-th batch
-        of cells and the densities are max-all-reduced (1 MB) -- identical grids on every rank (same jitter required)."""
+        of cells and the densities are max-all-reduced (1 MB) -- identical grids on every rank (same jitter required).
+        peer (parallel.PeerFrame): the reduction happens inside the query kernel with NVLink atomics into every rank's
+        symmetric density buffer, followed by one barrier."""
         self.aabb = deformer.get_bbox_deformed()
         from ..networks.ngp import NeRFNGPNet
         if isinstance(net, NeRFNGPNet) and hasattr(deformer, "scene"):
@@ -114,6 +116,12 @@ class DensityGrid(torch.nn.Module):
             if jitters is None:
                 jitters = torch.rand((iters, *self.coords.shape), device=self.coords.device)
             net.initialize(deformer.bbox)
+            if peer is not None:
+                ops.occupancy_query(deformer.scene(net), jitters[:iters], self.aabb6(), shard=shard, peer=peer.density_ptrs)
+                peer.barrier_density()
+                self.build_from_density(peer.density)
+                peer.density.zero_()   # own buffer, for the next frame: nobody writes into it before the frame-end barrier
+                return
             self._density = ops.occupancy_query(deformer.scene(net), jitters[:iters], self.aabb6(), getattr(self, "_density", None),
                                                 shard=shard)
             if shard[1] > 1:

@@ -66,14 +66,21 @@ def occupancy_build(density: torch.Tensor, bits=None, want_field=True, workspace
     return field, bits
 
 
-def occupancy_query(scene, jitters: torch.Tensor, aabb6: torch.Tensor, density=None, stats=None, workspace=None, shard=(0, 1)):
-    """5-pass density query of DensityGrid.initialize in one launch -> density [G,G,G] (max over passes, >= 0)"""
+def occupancy_query(scene, jitters: torch.Tensor, aabb6: torch.Tensor, density=None, stats=None, workspace=None, shard=(0, 1), peer=None):
+    """5-pass density query of DensityGrid.initialize in one launch -> density [G,G,G] (max over passes, >= 0).
+    peer = (device address of the array of every rank's density pointer, n_ranks): this rank's shard is max-reduced into
+    all ranks' (pre-zeroed) buffers with NVLink atomics; returns None (the caller owns the symmetric buffer)."""
     P, G = jitters.shape[0], jitters.shape[1]
-    if density is None:
-        density = torch.empty((G, G, G), device=jitters.device, dtype=f32)
     if workspace is None:
         workspace = torch.empty(64, device=jitters.device, dtype=torch.int32)
     s = scene.c_struct()
+    if peer is not None:
+        _lib.count(1); check(lib().ia_occupancy_query_peer(C.byref(s), ptr(jitters.contiguous(), f32), ptr(aabb6, f32), C.c_int(G), C.c_int(P),
+                                                           C.c_void_p(int(peer[0])), C.c_int(int(peer[1])), ptr(workspace), C.c_int(shard[0]),
+                                                           C.c_int(shard[1]), ptr(stats), stream()))
+        return None
+    if density is None:
+        density = torch.empty((G, G, G), device=jitters.device, dtype=f32)
     _lib.count(1); check(lib().ia_occupancy_query(C.byref(s), ptr(jitters.contiguous(), f32), ptr(aabb6, f32), C.c_int(G), C.c_int(P),
                                                   ptr(density), ptr(workspace), C.c_int(shard[0]), C.c_int(shard[1]), ptr(stats), stream()))
     return density
@@ -146,8 +153,10 @@ def stats_dict(t: torch.Tensor) -> dict:
 
 
 def render_fwd(scene: Scene, rays_o, rays_d, near, far, bg=None, image_width: int = 0, stats: torch.Tensor | None = None,
-               out: dict | None = None, workspace: torch.Tensor | None = None):
-    """Fused Raymarcher.render_test (raymarcher_acc.py:82-138)."""
+               out: dict | None = None, workspace: torch.Tensor | None = None, peer=None):
+    """Fused Raymarcher.render_test (raymarcher_acc.py:82-138).
+    peer = (pixel_index int32 [n] | None, device address of the array of every rank's RGBA image pointer, n_ranks): the
+    RGBA of every ray is additionally stored into all ranks' [n_pixels, 4] images over NVLink (ia_render_fwd_peer)."""
     n = rays_o.numel() // 3
     dev = rays_o.device
     if out is None:
@@ -156,6 +165,13 @@ def render_fwd(scene: Scene, rays_o, rays_d, near, far, bg=None, image_width: in
     if workspace is None:
         workspace = torch.empty(int(lib().ia_render_workspace_bytes(C.c_int(n))), device=dev, dtype=torch.uint8)
     s = scene.c_struct()
+    if peer is not None:
+        _lib.count(3); check(lib().ia_render_fwd_peer(C.byref(s), ptr(rays_o, f32), ptr(rays_d, f32), ptr(near, f32), ptr(far, f32), C.c_int(n),
+                                  ptr(bg), C.c_int(image_width), ptr(out["rgb"]), ptr(out["depth"]), ptr(out["alpha"]),
+                                  ptr(out["counter"]), ptr(workspace), C.c_size_t(workspace.numel() * workspace.element_size()),
+                                  ptr(stats), ptr(peer[0], torch.int32) if peer[0] is not None else None, C.c_void_p(int(peer[1])),
+                                  C.c_int(int(peer[2])), stream()))
+        return out
     _lib.count(3); check(lib().ia_render_fwd(C.byref(s), ptr(rays_o, f32), ptr(rays_d, f32), ptr(near, f32), ptr(far, f32), C.c_int(n),
                               ptr(bg), C.c_int(image_width), ptr(out["rgb"]), ptr(out["depth"]), ptr(out["alpha"]),
                               ptr(out["counter"]), ptr(workspace), C.c_size_t(workspace.numel() * workspace.element_size()),

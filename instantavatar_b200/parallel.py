@@ -130,3 +130,45 @@ def all_gather_image(local: torch.Tensor, n_rays: int, tile: int, group=None) ->
         dist.all_gather(parts, local.contiguous(), group=group)
         buf.copy_(torch.stack(parts).view(world, per, tile, C))
     return buf.permute(1, 0, 2, 3).reshape(n_rays, C)  # tile (t, r) is global tile t * world + r
+
+
+class PeerFrame:
+    """Symmetric (peer-mapped) buffers for ONE cooperatively rendered frame (BASELINE.json config 3) on the GPUs of one
+    NVLink box: every rank's 64^3 density grid and [n_pixels, 4] RGBA image are mapped into every other rank's address
+    space (torch symmetric memory: cuMem handles exchanged through the process group's store).  The fused kernels then
+
+      * max-reduce their shard of the occupancy queries into EVERY rank's density grid with NVLink atomics
+        (ia_occupancy_query_peer: positive densities only, ~2 % of the cells) -- instead of a 1 MB max-all-reduce, and
+      * store the RGBA of their rays straight into EVERY rank's image (ia_render_fwd_peer) -- instead of gather +
+        scatter / all-gather + permute after the kernel,
+
+    so the frame's only cross-GPU synchronisation is two signal-pad barriers.  Construction is collective; it raises if the
+    platform cannot map peer memory (the caller falls back to the NCCL collectives)."""
+
+    def __init__(self, n_pixels: int, device, group=None, grid: int = 64):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.density = symm.empty((grid, grid, grid), dtype=torch.float32, device=device)
+        self.image = symm.empty((n_pixels, 4), dtype=torch.float32, device=device)
+        self.h_density = symm.rendezvous(self.density, group)
+        self.h_image = symm.rendezvous(self.image, group)
+        self.density.zero_(); self.image.zero_()
+        torch.cuda.synchronize(device)
+        self.h_density.barrier(channel=0)   # every rank's buffers are zeroed before anyone writes into them
+        torch.cuda.synchronize(device)
+
+    @property
+    def density_ptrs(self):
+        return (self.h_density.buffer_ptrs_dev, self.world)
+
+    def image_ptrs(self, pixel_index):
+        return (pixel_index, self.h_image.buffer_ptrs_dev, self.world)
+
+    def barrier_density(self):
+        """all ranks' occupancy-query kernels (which write into every rank's grid) have finished"""
+        self.h_density.barrier(channel=0)
+
+    def barrier_image(self):
+        """all ranks' render kernels have finished storing into every rank's image"""
+        self.h_image.barrier(channel=0)

@@ -112,7 +112,7 @@ class Raymarcher(torch.nn.Module):
                 "alpha_coarse": (1 - acc["no_hit"]).reshape(like), "counter_coarse": acc["counter"].reshape(like)}
 
     @torch.no_grad()
-    def render_test(self, rays, model, bg_color, stats=None):
+    def render_test(self, rays, model, bg_color, stats=None, peer=None):
         bound = _unwrap(model)
         if bound is None:
             return self.render_test_legacy(rays, model, bg_color)
@@ -125,7 +125,7 @@ class Raymarcher(torch.nn.Module):
         near = rays.near.reshape(-1).float().contiguous()
         far = rays.far.reshape(-1).float().contiguous()
         bg = bg_color.reshape(-1, 3).float().contiguous() if bg_color is not None else None
-        out = ops.render_fwd(scene, rays_o, rays_d, near, far, bg, self.image_width, stats)
+        out = ops.render_fwd(scene, rays_o, rays_d, near, far, bg, self.image_width, stats, peer=peer)
         return {
             "rgb_coarse": out["rgb"].reshape(rays.o.shape),
             "depth_coarse": out["depth"].reshape(rays.near.shape),

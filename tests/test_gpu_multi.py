@@ -41,10 +41,36 @@ def _worker(rank, world, port, ret):
     # ---- cooperative frame vs single-GPU frame ----
     img = model.render_image_sharded(dict(batch), (H, W), rank, world, jit, tile=1024)
     rgb, depth, alpha, counter = model.render_image_fast(dict(batch), (H, W), jit)
+    full = torch.cat([rgb.reshape(-1, 3), alpha.reshape(-1, 1)], dim=1)
     if rank == 0:
-        full = torch.cat([rgb.reshape(-1, 3), alpha.reshape(-1, 1)], dim=1)
         ret["frame_equal"] = bool(torch.equal(img, full))
         ret["hit"] = int((alpha > 0.5).sum().item())
+    # ---- the same frame with both exchanges inside the kernels over NVLink peer memory (two frames: a second pose checks
+    #      the buffer-reuse protocol), every rank must end up with the single-GPU image ----
+    try:
+        pf = parallel.PeerFrame(H * W, dev)
+        peer_ok = torch.ones(1, device=dev)
+    except Exception as exc:
+        pf, peer_ok = None, torch.zeros(1, device=dev)
+        if rank == 0:
+            ret["peer_error"] = f"{type(exc).__name__}: {exc}"[:300]
+    dist.all_reduce(peer_ok, op=dist.ReduceOp.MIN)
+    if peer_ok.item() == 1:
+        eq = torch.ones(1, device=dev)
+        pose2 = {k: torch.from_numpy(v).to(dev) for k, v in synthetic.load_pose(57).items()}
+        for b_ in (batch, {**batch, **pose2}, batch):
+            ref_rgb, _, ref_a, _ = model.render_image_fast(dict(b_), (H, W), jit)
+            ref = torch.cat([ref_rgb.reshape(-1, 3), ref_a.reshape(-1, 1)], dim=1)
+            got = model.render_image_sharded(dict(b_), (H, W), rank, world, jit, tile=1024, peer=pf)
+            torch.cuda.synchronize()
+            if not torch.equal(got, ref):
+                eq.zero_()
+            dist.barrier()  # `got` is the symmetric image buffer: everyone has compared before the next frame overwrites it
+        dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ret["peer_frames_equal"] = bool(eq.item() == 1)
+    elif rank == 0:
+        ret["peer_frames_equal"] = None
     # ---- sharded training gradient vs single-GPU gradient ----
     n = 1024
     pick = torch.arange(100 * W + 96, 100 * W + 96 + n, device=dev)
@@ -135,6 +161,9 @@ def test_two_gpu_frame_and_gradient():
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert ret["hit"] > 1000
     assert ret["frame_equal"], "cooperative frame differs from the single-GPU frame"
+    assert ret.get("peer_frames_equal") is not False, "peer-memory frame differs from the single-GPU frame"
+    if ret.get("peer_frames_equal") is None:
+        print("peer memory unavailable on this box:", ret.get("peer_error"))
     assert ret["gnorm"] > 0 and ret["rel_enc"] < 1e-3 and ret["rel_col"] < 1e-3, dict(ret)
     # sharded optimiser == replicated optimiser up to the summation order of the gradient (Adam normalises the update, so
     # an entry whose gradient is pure rounding noise can move by a full lr step in OPPOSITE directions in the two runs:
