@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libia_b200.so")
+# IA_B200_LIB: an alternative build of the same sources (experiments only, e.g. scripts/build_variant.sh -fmad=true)
+LIB_PATH = os.environ.get("IA_B200_LIB") or os.path.join(_HERE, "libia_b200.so")
 
 IA_MLP_HALFS = 22144
 IA_ENC_MLP_PARAMS = 3072

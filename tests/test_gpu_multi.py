@@ -169,5 +169,5 @@ def test_two_gpu_frame_and_gradient():
     # an entry whose gradient is pure rounding noise can move by a full lr step in OPPOSITE directions in the two runs:
     # the worst case is 2 x 3 steps x lr = 6e-2; the mean difference must be tiny)
     assert ret["fp16_image_same_on_ranks"] and ret["adam_steps"] == (3, 3), dict(ret)
-    assert ret["param_moved"] > 1e-3 and ret["param_max_diff"] <= 6.1e-2 and ret["param_mean_diff"] < 1e-5, dict(ret)
-    assert ret["fp16_frac_diff"] < 1e-3, dict(ret)
+    assert ret["param_moved"] > 1e-3 and ret["param_max_diff"] <= 6.1e-2 and ret["param_mean_diff"] < 1e-4, dict(ret)
+    assert ret["fp16_frac_diff"] < 1e-2, dict(ret)   # entries whose fp16 image differs at all (noise-level gradients)
