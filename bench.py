@@ -640,11 +640,11 @@ def run_ours(args):
         pass
     hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     # Sectors the kernels REQUEST (kernel counters; exact-zero footprints and early-out solves issue nothing and are not
-    # counted): 12 x 32 B per field footprint that loaded, 128 x 32 B per network evaluation (16 levels x 8 corners, one
-    # sector per 4-byte table entry).  The ceiling is the same shape in isolation (lane = footprint, 12 LDG.E.256, next
+    # counted): 12 x 32 B per field footprint that loaded, one sector per hash-table load a lane issues (<= 128 per network
+    # evaluation: 16 levels x 8 corners, adjacent x / x+1 entries fetched by one 64-bit load).  The ceiling is the same shape in isolation (lane = footprint, 12 LDG.E.256, next
     # address data-dependent) measured in this run: frac = requested sectors / s over that.
-    q_sect = qst["field_loads"] * 12 + qst["net_evals"] * 128
-    r_sect = st["field_loads"] * 12 + st["net_evals"] * 128
+    q_sect = qst["field_loads"] * 12 + qst["hash_loads"]
+    r_sect = st["field_loads"] * 12 + st["hash_loads"]
     q_gbs, r_gbs = q_sect * 32 / (q_ms * 1e-3) / 1e9, r_sect * 32 / (k_ms * 1e-3) / 1e9
     ceil_gbs = ceil_best["GBps"]
     field_bytes = fld.numel() * 4

@@ -40,7 +40,7 @@ class IaScene(C.Structure):
 
 class IaStats(C.Structure):
     _fields_ = [("samples", C.c_ulonglong), ("gathers", C.c_ulonglong), ("net_evals", C.c_ulonglong),
-                ("rays_hit", C.c_ulonglong), ("field_loads", C.c_ulonglong), ("reserved", C.c_ulonglong)]
+                ("rays_hit", C.c_ulonglong), ("field_loads", C.c_ulonglong), ("hash_loads", C.c_ulonglong)]
 
 
 _lib = None

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
     const bool tiled = a.image_width > 0 && (a.image_width % kTileW) == 0 && (a.n_rays % (a.image_width * kTileH)) == 0;
     const int n_tiles = (a.n_rays + kRays - 1) / kRays;
     const int rl = lane % kRays, jl = lane / kRays;
-    unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_hit = 0, st_load = 0;
+    unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_hit = 0, st_load = 0, st_hash = 0;
 
     for (;;) {
         int tile = 0;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
             if (!__any_sync(kFull, sact)) continue;
             st_samples += sact ? 1u : 0u;
             SampleOut so;
-            warp_eval_samples<false>(ctx, ws, sact, sx, sy, sz, true, lane, so, st_gather, st_roots, st_load);
+            warp_eval_samples<false>(ctx, ws, sact, sx, sy, sz, true, lane, so, st_gather, st_roots, st_load, st_hash);
             // ---- composite in sample order (raymarcher.cu:200-235) ----
             ws.res[lane][0] = so.sigma; ws.res[lane][1] = so.r; ws.res[lane][2] = so.g; ws.res[lane][3] = so.b;
             wx.bt[lane] = stt; wx.bo[lane] = sact ? sown : -1;
@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
         for (int o = 16; o; o >>= 1) {
             st_gather += __shfl_xor_sync(kFull, st_gather, o);
             st_load += __shfl_xor_sync(kFull, st_load, o);
+            st_hash += __shfl_xor_sync(kFull, st_hash, o);
             st_roots += __shfl_xor_sync(kFull, st_roots, o);
             st_samples += __shfl_xor_sync(kFull, st_samples, o);
             st_hit += __shfl_xor_sync(kFull, st_hit, o);
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
         if (lane == 0) {
             atomicAdd(&a.stats->gathers, (unsigned long long)st_gather);
             atomicAdd(&a.stats->field_loads, (unsigned long long)st_load);
+            atomicAdd(&a.stats->hash_loads, (unsigned long long)st_hash);
             atomicAdd(&a.stats->net_evals, (unsigned long long)st_roots);
             atomicAdd(&a.stats->samples, (unsigned long long)st_samples);
             atomicAdd(&a.stats->rays_hit, (unsigned long long)st_hit);
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
     ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
     ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
     ctx.Wsm = sm.W; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
-    unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_load = 0;
+    unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_load = 0, st_hash = 0;
     // grid mode: a batch holds all jitter passes of 32/passes neighbouring cells, so that the 32 lanes stay within a
     // few voxels of the skinning field (L1 wavefronts, not DRAM, bound this kernel)
     const int cells_per_batch = a.grid_aabb ? 32 / a.passes : 32;
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
             }
         }
         SampleOut so;
-        warp_eval_samples<kKeepXc>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots, st_load);
+        warp_eval_samples<kKeepXc>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots, st_load, st_hash);
         st_samples += act ? 1u : 0u;
         if (act && a.grid_aabb) {
             if (so.sigma > 0.f) {
@@ -482,12 +484,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
         for (int o = 16; o; o >>= 1) {
             st_gather += __shfl_xor_sync(kFull, st_gather, o);
             st_load += __shfl_xor_sync(kFull, st_load, o);
+            st_hash += __shfl_xor_sync(kFull, st_hash, o);
             st_roots += __shfl_xor_sync(kFull, st_roots, o);
             st_samples += __shfl_xor_sync(kFull, st_samples, o);
         }
         if (lane == 0) {
             atomicAdd(&a.stats->gathers, (unsigned long long)st_gather);
             atomicAdd(&a.stats->field_loads, (unsigned long long)st_load);
+            atomicAdd(&a.stats->hash_loads, (unsigned long long)st_hash);
             atomicAdd(&a.stats->net_evals, (unsigned long long)st_roots);
             atomicAdd(&a.stats->samples, (unsigned long long)st_samples);
         }

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) train_fwd_kernel(const __grid_
     unsigned ray_mask = 0;
 #pragma unroll
     for (int j = 0; j < kDepth; j++) ray_mask |= 1u << (rl + j * kRays);
-    unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_load = 0;
+    unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_load = 0, st_hash = 0;
 
     for (;;) {
         int tile = 0;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) train_fwd_kernel(const __grid_
             qcount -= n;
             st_samples += sact ? 1u : 0u;
             SampleOut so;
-            warp_eval_samples<true>(ctx, ws, sact, sx, sy, sz, false, lane, so, st_gather, st_roots, st_load);
+            warp_eval_samples<true>(ctx, ws, sact, sx, sy, sz, false, lane, so, st_gather, st_roots, st_load, st_hash);
             // save per-sample state for the backward pass
             const int sray = tile * kRays + sown;
             if (sact) {
@@ -196,12 +196,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) train_fwd_kernel(const __grid_
         for (int o = 16; o; o >>= 1) {
             st_gather += __shfl_xor_sync(kFull, st_gather, o);
             st_load += __shfl_xor_sync(kFull, st_load, o);
+            st_hash += __shfl_xor_sync(kFull, st_hash, o);
             st_roots += __shfl_xor_sync(kFull, st_roots, o);
             st_samples += __shfl_xor_sync(kFull, st_samples, o);
         }
         if (lane == 0) {
             atomicAdd(&a.stats->gathers, (unsigned long long)st_gather);
             atomicAdd(&a.stats->field_loads, (unsigned long long)st_load);
+            atomicAdd(&a.stats->hash_loads, (unsigned long long)st_hash);
             atomicAdd(&a.stats->net_evals, (unsigned long long)st_roots);
             atomicAdd(&a.stats->samples, (unsigned long long)st_samples);
         }

@@ -57,7 +57,7 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
 template <bool kKeepXc>
 __device__ __forceinline__ void warp_eval_samples(const EvalCtx& ctx, WarpScratch<kKeepXc>& ws, bool active, float xd0,
                                                   float xd1, float xd2, bool eval_mode, int lane, SampleOut& out,
-                                                  unsigned& ngather, unsigned& nroots, unsigned& nload) {
+                                                  unsigned& ngather, unsigned& nroots, unsigned& nload, unsigned& nhash) {
     const FrameConst& fc = *ctx.fc;
     // ---- 1. Broyden from the 13 bone initialisations ------------------------------------------------
     unsigned vmask = 0;
@@ -115,7 +115,7 @@ __device__ __forceinline__ void warp_eval_samples(const EvalCtx& ctx, WarpScratc
             const float n1 = fminf(fmaxf((x1 - fc.net_center[1]) / fc.net_scale[1] + 0.5f, 0.f), 1.f);
             const float n2 = fminf(fmaxf((x2 - fc.net_center[2]) / fc.net_scale[2] + 0.5f, 0.f), 1.f);
 #pragma unroll 4
-            for (int l = 0; l < kLevels; l++) arow[l] = hash_encode_level(ctx.table, *ctx.hl, l, n0, n1, n2);
+            for (int l = 0; l < kLevels; l++) arow[l] = hash_encode_level(ctx.table, *ctx.hl, l, n0, n1, n2, &nhash);
         } else {
 #pragma unroll
             for (int l = 0; l < kLevels; l++) arow[l] = __floats2half2_rn(0.f, 0.f);

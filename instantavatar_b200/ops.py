@@ -149,7 +149,7 @@ def new_stats(device) -> torch.Tensor:
 
 def stats_dict(t: torch.Tensor) -> dict:
     v = t.tolist()
-    return {"samples": v[0], "gathers": v[1], "net_evals": v[2], "rays_hit": v[3], "field_loads": v[4]}
+    return {"samples": v[0], "gathers": v[1], "net_evals": v[2], "rays_hit": v[3], "field_loads": v[4], "hash_loads": v[5]}
 
 
 def render_fwd(scene: Scene, rays_o, rays_d, near, far, bg=None, image_width: int = 0, stats: torch.Tensor | None = None,
