@@ -24,6 +24,25 @@ class GraphedFrame:
     def __init__(self, model, batch: dict, img_size, warmup: int = 3, jitters=None):
         self.model, self.img_size = model, img_size
         self.static_in = {k: v.clone() for k, v in batch.items() if torch.is_tensor(v)}
+        # the small per-frame inputs (SMPL pose: betas, global_orient, body_pose, transl, ...) live in ONE device buffer fed by
+        # ONE pinned staging buffer: a single host->device copy per frame instead of one ~10 us copy per tensor
+        small = [k for k, v in self.static_in.items() if k not in RAY_KEYS and v.dtype == torch.float32]
+        n_small = sum(self.static_in[k].numel() for k in small)
+        self._small_keys, self._small_dev = small, None
+        if small:
+            dev = self.static_in[small[0]].device
+            self._small_dev = torch.empty(n_small, device=dev, dtype=torch.float32)
+            # two staging buffers, each guarded by an event: the host never overwrites one an enqueued copy still reads
+            self._small_host = [torch.empty(n_small, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._small_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._small_turn = 0
+            off = 0
+            for k in small:
+                v = self.static_in[k]
+                view = self._small_dev[off:off + v.numel()].view(v.shape)
+                view.copy_(v)
+                self.static_in[k] = view
+                off += v.numel()
         self.jitters = jitters.clone() if jitters is not None else None  # None: fresh torch.rand inside the graph
         model.eval()
         s = torch.cuda.Stream()
@@ -57,8 +76,28 @@ class GraphedFrame:
                         self.static_in[k].copy_(batch[k], non_blocking=True)
                         overlap = True
                 self.rays_ready.record(self.copy_stream)
+            off, staged = 0, False
+            if self._small_keys:
+                self._small_turn ^= 1
+                self._small_done[self._small_turn].synchronize()  # (recorded two frames ago: already complete in steady state)
+                stage = self._small_host[self._small_turn]
+            for k in self._small_keys:
+                n = self.static_in[k].numel()
+                if k in batch:
+                    v = batch[k]
+                    if v.is_cuda:
+                        self.static_in[k].copy_(v, non_blocking=True)
+                    else:
+                        stage[off:off + n].copy_(v.reshape(-1))
+                        staged = True
+                off += n
+            if staged:
+                if not all(k in batch and not batch[k].is_cuda for k in self._small_keys):
+                    raise ValueError("GraphedFrame: pass all small per-frame inputs from the host or all from the device")
+                self._small_dev.copy_(stage, non_blocking=True)
+                self._small_done[self._small_turn].record(main)
             for k, v in batch.items():
-                if k in self.static_in and k not in RAY_KEYS:
+                if k in self.static_in and k not in RAY_KEYS and k not in self._small_keys:
                     self.static_in[k].copy_(v, non_blocking=True)
         self.graph_a.replay()
         if overlap:
