@@ -308,11 +308,21 @@ def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, u
         b["bg_color"], b["alpha"], b["rgb"] = torch.rand((1, n, 3), device=device), a, rgb_gt[pick][None].clone()
         graphed = GraphedTrainStep(model, b)
 
-    def one():
+    # per-step data (random background per pixel, peoplesnapshot.py:109-114 -- the reference composes it in the CPU data
+    # loader, off the step's critical path): a pool of prebuilt device batches; a step copies three small tensors
+    pool = []
+    for _ in range(8):
         bg = torch.rand((1, n, 3), device=device)
-        b["bg_color"], b["alpha"] = bg, a
-        b["rgb"] = rgb_gt[pick][None] - (1 - a[..., None]) + (1 - a[..., None]) * bg
-        return graphed(b) if graphed is not None else model.training_step(b)
+        pool.append({"bg_color": bg, "rgb": rgb_gt[pick][None] - (1 - a[..., None]) + (1 - a[..., None]) * bg})
+    counter = [0]
+
+    def one():
+        cur = pool[counter[0] % len(pool)]
+        counter[0] += 1
+        if graphed is not None:
+            return graphed(cur)   # copies bg_color / rgb into the graph's static buffers, replays
+        b["bg_color"], b["rgb"], b["alpha"] = cur["bg_color"], cur["rgb"], a
+        return model.training_step(b)
 
     for _ in range(warmup):
         one()
