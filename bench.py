@@ -650,8 +650,8 @@ def run_ours(args):
         pass
     hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     # Sectors the kernels REQUEST (kernel counters; exact-zero footprints and early-out solves issue nothing and are not
-    # counted): 12 x 32 B per field footprint that loaded, one sector per hash-table load a lane issues (<= 128 per network
-    # evaluation: 16 levels x 8 corners, adjacent x / x+1 entries fetched by one 64-bit load).  The ceiling is the same shape in isolation (lane = footprint, 12 LDG.E.256, next
+    # counted): 12 x 32 B per field footprint that loaded, one sector per hash-table load a lane issues (128 per network
+    # evaluation: 16 levels x 8 corners).  The ceiling is the same shape in isolation (lane = footprint, 12 LDG.E.256, next
     # address data-dependent) measured in this run: frac = requested sectors / s over that.
     q_sect = qst["field_loads"] * 12 + qst["hash_loads"]
     r_sect = st["field_loads"] * 12 + st["hash_loads"]

@@ -56,8 +56,8 @@ typedef struct IaStats {
     unsigned long long rays_hit;  /* rays with at least one occupied sample */
     unsigned long long field_loads; /* of `gathers`, those that issued loads (12 sectors of 32 B each): footprints outside the
                                      * skinning volume and early-out solves are exact zeros computed without memory traffic */
-    unsigned long long hash_loads; /* hash-table load instructions issued per lane (one sector each): <= 128 per network
-                                    * evaluation; the x / x+1 corners of a cell share one 64-bit load where they are adjacent */
+    unsigned long long hash_loads; /* hash-table loads issued per lane (one 32-byte sector each): 16 levels x 8 corners = 128 per
+                                    * network evaluation */
 } IaStats;
 
 int ia_abi_version(void);
