@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--rays-per-warp", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--train-rays-per-warp", type=int, default=0)
-    ap.add_argument("--render-warps", type=int, default=0, help="warps per CTA of the fused renderer (12 / 16)")
+    ap.add_argument("--render-warps", type=int, default=0, help="warps per CTA of the fused renderer (12)")
     ap.add_argument("--query-warps", type=int, default=0, help="warps per CTA of the point-query kernel (12 / 16 / 20)")
     return ap.parse_args()
 

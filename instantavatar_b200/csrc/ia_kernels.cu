@@ -10,7 +10,6 @@ using namespace ia;
 
 static int g_render_rays = 4;  // rays per warp (32 / 16 / 8 / 4), tunable through ia_set_option
 static int g_render_plan = 1;  // longest-first tile scheduling (needs the large workspace)
-static int g_render_warps = 12;  // warps per persistent CTA of the fused renderer (12: 168 registers / thread, 16: 128)
 static int g_query_warps = 12;   // same for the point-query kernel (12 / 16 / 20; 16 and 20 only without xc output)
 static int g_train_rays = 2;   // rays per warp of the training forward (4 / 2 / 1)
 int ia_train_rays_per_warp() { return g_train_rays; }
@@ -56,6 +55,7 @@ template <int kWarps>
 struct RenderSmem {
     __align__(128) uint32_t occ[64 * 64 * 64 / 32];
     __align__(16) __half W[kMlpHalfs];
+    __align__(16) __half2 hash0[kHash0Entries];
     FrameConst fc;
     __align__(8) uint64_t mbar;
     WarpScratch<false> ws[kWarps];
@@ -215,9 +215,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
     const uint32_t occ_bytes = (uint32_t)(G * G * G / 8);
     if (threadIdx.x == 0) {
         mbar_init(&sm.mbar, 1);
-        mbar_expect_tx(&sm.mbar, occ_bytes + kMlpHalfs * 2);
+        mbar_expect_tx(&sm.mbar, occ_bytes + kMlpHalfs * 2 + kHash0Entries * 4);
         bulk_g2s(sm.occ, a.sd.s.occ_bits, occ_bytes, &sm.mbar);
         bulk_g2s(sm.W, a.sd.s.mlp_h, kMlpHalfs * 2, &sm.mbar);
+        bulk_g2s(sm.hash0, reinterpret_cast<const __half2*>(a.sd.s.table_h) + a.sd.hl.offset[0], kHash0Entries * 4, &sm.mbar);
     }
     load_frame_const(sm.fc, a.sd);
     __syncthreads();
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
     ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
     ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
     ctx.Wsm = sm.W;
+    ctx.hash0 = sm.hash0;
     ctx.fc = &sm.fc;
     ctx.hl = &a.sd.hl;
     WarpScratch<false>& ws = sm.ws[warp];
@@ -394,6 +396,7 @@ struct QueryArgs {
 template <int kWarps, bool kKeepXc>
 struct QuerySmem {
     __align__(16) __half W[kMlpHalfs];
+    __align__(16) __half2 hash0[kHash0Entries];
     FrameConst fc;
     __align__(8) uint64_t mbar;
     WarpScratch<kKeepXc> ws[kWarps];
@@ -408,8 +411,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         mbar_init(&sm.mbar, 1);
-        mbar_expect_tx(&sm.mbar, kMlpHalfs * 2);
+        mbar_expect_tx(&sm.mbar, kMlpHalfs * 2 + kHash0Entries * 4);
         bulk_g2s(sm.W, a.sd.s.mlp_h, kMlpHalfs * 2, &sm.mbar);
+        bulk_g2s(sm.hash0, reinterpret_cast<const __half2*>(a.sd.s.table_h) + a.sd.hl.offset[0], kHash0Entries * 4, &sm.mbar);
     }
     load_frame_const(sm.fc, a.sd);
     __syncthreads();
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
     ctx.field.data = a.sd.s.field;
     ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
     ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
-    ctx.Wsm = sm.W; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
+    ctx.Wsm = sm.W; ctx.hash0 = sm.hash0; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
     unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_load = 0, st_hash = 0;
     // grid mode: a batch holds all jitter passes of 32/passes neighbouring cells, so that the 32 lanes stay within a
     // few voxels of the skinning field (L1 wavefronts, not DRAM, bound this kernel)
@@ -832,8 +836,9 @@ int ia_set_option(const char* name, int value) {
         return IA_OK;
     }
     if (!strcmp(name, "render_warps")) {
-        IA_REQUIRE(value == 12 || value == 16);
-        g_render_warps = value;
+        // 12 only: the 16-warp build (128 registers) was measured slower (profiles/sweep_warps_r2.jsonl) and does not fit
+        // next to the staged hash level; the name stays so that old sweep scripts fail loudly on other values
+        IA_REQUIRE(value == 12);
         return IA_OK;
     }
     if (!strcmp(name, "query_warps")) {
@@ -992,14 +997,14 @@ static int render_fwd_impl(const IaScene* scene, const float* rays_o, const floa
     int* ws_cost = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + 256);
     int* ws_order = ws_cost + (n_rays + 1);
     const int rpw = g_render_rays;
-    const bool w16 = g_render_warps == 16 && (rpw == 4 || rpw == 8);  // the 16-warp build exists for the two useful tile shapes
+    // (a 16-warp renderer was measured slower, profiles/sweep_warps_r2.jsonl, and no longer fits next to the staged hash level)
     switch (rpw) {
         case 32: rc = launch_render<12, 32>(a, plan, ws_cost, ws_order, st); break;
         case 16: rc = launch_render<12, 16>(a, plan, ws_cost, ws_order, st); break;
-        case 4: rc = w16 ? launch_render<16, 4>(a, plan, ws_cost, ws_order, st) : launch_render<12, 4>(a, plan, ws_cost, ws_order, st); break;
+        case 4: rc = launch_render<12, 4>(a, plan, ws_cost, ws_order, st); break;
         case 2: rc = launch_render<12, 2>(a, plan, ws_cost, ws_order, st); break;
         case 1: rc = launch_render<12, 1>(a, plan, ws_cost, ws_order, st); break;
-        default: rc = w16 ? launch_render<16, 8>(a, plan, ws_cost, ws_order, st) : launch_render<12, 8>(a, plan, ws_cost, ws_order, st); break;
+        default: rc = launch_render<12, 8>(a, plan, ws_cost, ws_order, st); break;
     }
     if (rc) return rc;
     IA_CHECK_CUDA(cudaPeekAtLastError());

@@ -40,6 +40,7 @@ template <int kWarps>
 struct TrainSmem {
     __align__(128) uint32_t occ[64 * 64 * 64 / 32];
     __align__(16) __half W[kMlpHalfs];
+    __align__(16) __half2 hash0[kHash0Entries];
     FrameConst fc;
     __align__(8) uint64_t mbar;
     WarpScratch<true> ws[kWarps];
@@ -56,9 +57,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) train_fwd_kernel(const __grid_
     const uint32_t occ_bytes = (uint32_t)(G * G * G / 8);
     if (threadIdx.x == 0) {
         mbar_init(&sm.mbar, 1);
-        mbar_expect_tx(&sm.mbar, occ_bytes + kMlpHalfs * 2);
+        mbar_expect_tx(&sm.mbar, occ_bytes + kMlpHalfs * 2 + kHash0Entries * 4);
         bulk_g2s(sm.occ, a.sd.s.occ_bits, occ_bytes, &sm.mbar);
         bulk_g2s(sm.W, a.sd.s.mlp_h, kMlpHalfs * 2, &sm.mbar);
+        bulk_g2s(sm.hash0, reinterpret_cast<const __half2*>(a.sd.s.table_h) + a.sd.hl.offset[0], kHash0Entries * 4, &sm.mbar);
     }
     load_frame_const(sm.fc, a.sd);
     __syncthreads();
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) train_fwd_kernel(const __grid_
     ctx.field.data = a.sd.s.field;
     ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
     ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
-    ctx.Wsm = sm.W; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
+    ctx.Wsm = sm.W; ctx.hash0 = sm.hash0; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
     WarpScratch<true>& ws = sm.ws[warp];
     TrainWarpExtra& wx = sm.wx[warp];
     const FrameConst& fc = sm.fc;
@@ -931,24 +933,32 @@ __global__ void adam_prepare_kernel(float* state, float inv_world, const float* 
     state[7] = grad_scale_dev ? inv_world / *grad_scale_dev : inv_world;
 }
 
-// 4 elements per thread (128-bit loads/stores; the flat tensors are multiples of 4 long and 16-byte aligned)
+// 4 elements per thread (128-bit loads/stores; the flat tensors are multiples of 4 long and 16-byte aligned).
+// HBM-bound streaming pass: 34 bytes per parameter (g, p, m, v read; g, p, m, v written; fp16 image written).  All four
+// loads are issued up front -- they do not wait for the overflow flag or the step state, which sit in shared memory -- and
+// every access carries the evict-first hint (ld.global.cs / st.global.cs): nothing here is reused, and without the hint
+// the 443 MB stream thrashes the L2 that it shares with its own write-backs.  Measured on the 13 M-parameter vector
+// (scripts/adam_variants.cu, profiles/adam_variants_r2.jsonl): 0.203 ms (2.2 TB/s) for the round-1 shape -> 0.075 ms
+// (5.9 TB/s, 0.91 of the measured copy bandwidth).
 __global__ void __launch_bounds__(256) adam_dev_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                                         float4* __restrict__ v, long n4, const float* __restrict__ state,
-                                                        const float* __restrict__ found_inf, __half2* __restrict__ half_out,
+                                                        const float* __restrict__ found_inf, uint2* __restrict__ half_out,
                                                         long half_skip4) {
+    __shared__ float st[8];
+    __shared__ float fi;
+    if (threadIdx.x < 8) st[threadIdx.x] = state[threadIdx.x];
+    if (threadIdx.x == 8) fi = found_inf ? *found_inf : 0.f;
+    __syncthreads();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
-    const float4 gr = g[i];
-    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // zero_grad fused into the step
-    const bool skip = found_inf && *found_inf != 0.f;
-    float4 pi = p[i];
-    if (!skip) {
-        const float lr = state[0], beta1 = state[1], beta2 = state[2], eps = state[3], bc1 = state[5], bc2_sqrt = state[6],
-                    inv = state[7];
-        float4 mi = m[i], vi = v[i];
+    const float4 gr = __ldcs(g + i);
+    float4 pi = __ldcs(p + i);
+    float4 mi = __ldcs(m + i), vi = __ldcs(v + i);
+    __stcs(g + i, make_float4(0.f, 0.f, 0.f, 0.f));  // zero_grad fused into the step
+    if (fi == 0.f) {
+        const float lr = st[0], beta1 = st[1], beta2 = st[2], eps = st[3], bc1 = st[5], bc2_sqrt = st[6], inv = st[7];
         const float step_size = lr / bc1, inv_bc2 = 1.0f / bc2_sqrt;
-        // MUFU sqrt / reciprocal (<= 2 ulp): the IEEE division + sqrt sequences made this kernel instruction-bound
-        // (555 instructions per thread, 1.9 TB/s); Adam's update tolerates 1e-6 relative error
+        // MUFU sqrt / reciprocal (<= 2 ulp): Adam's update tolerates 1e-6 relative error
         auto upd = [&](float& pp, float gg, float& mm, float& vv) {
             const float gi = gg * inv;
             mm = __fmaf_rn(beta1, mm, (1.f - beta1) * gi);
@@ -958,11 +968,11 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float4* __restrict__ p, f
             pp = __fmaf_rn(-step_size, __fdividef(mm, __fmaf_rn(sq, inv_bc2, eps)), pp);
         };
         upd(pi.x, gr.x, mi.x, vi.x); upd(pi.y, gr.y, mi.y, vi.y); upd(pi.z, gr.z, mi.z, vi.z); upd(pi.w, gr.w, mi.w, vi.w);
-        m[i] = mi; v[i] = vi; p[i] = pi;
+        __stcs(m + i, mi); __stcs(v + i, vi); __stcs(p + i, pi);
     }
     if (half_out && i >= half_skip4) {
-        half_out[2 * (i - half_skip4)] = __floats2half2_rn(pi.x, pi.y);
-        half_out[2 * (i - half_skip4) + 1] = __floats2half2_rn(pi.z, pi.w);
+        const __half2 h0 = __floats2half2_rn(pi.x, pi.y), h1 = __floats2half2_rn(pi.z, pi.w);
+        __stcs(half_out + (i - half_skip4), make_uint2(*reinterpret_cast<const unsigned*>(&h0), *reinterpret_cast<const unsigned*>(&h1)));
     }
 }
 
@@ -1393,7 +1403,7 @@ int ia_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg
     if (n4 > 0)
         adam_dev_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
             reinterpret_cast<float4*>(params), reinterpret_cast<float4*>(grads), reinterpret_cast<float4*>(exp_avg),
-            reinterpret_cast<float4*>(exp_avg_sq), n4, state, found_inf, reinterpret_cast<__half2*>(half_out), half_skip / 4);
+            reinterpret_cast<float4*>(exp_avg_sq), n4, state, found_inf, reinterpret_cast<uint2*>(half_out), half_skip / 4);
     if (rem)
         adam_dev_tail_kernel<<<1, 4, 0, (cudaStream_t)stream>>>(params + n4 * 4, grads + n4 * 4, exp_avg + n4 * 4, exp_avg_sq + n4 * 4,
                                                                rem, state, found_inf);
