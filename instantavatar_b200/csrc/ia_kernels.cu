@@ -55,7 +55,6 @@ template <int kWarps>
 struct RenderSmem {
     __align__(128) uint32_t occ[64 * 64 * 64 / 32];
     __align__(16) __half W[kMlpHalfs];
-    __align__(16) __half2 hash0[kHash0Entries];
     FrameConst fc;
     __align__(8) uint64_t mbar;
     WarpScratch<false> ws[kWarps];
@@ -215,10 +214,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
     const uint32_t occ_bytes = (uint32_t)(G * G * G / 8);
     if (threadIdx.x == 0) {
         mbar_init(&sm.mbar, 1);
-        mbar_expect_tx(&sm.mbar, occ_bytes + kMlpHalfs * 2 + kHash0Entries * 4);
+        mbar_expect_tx(&sm.mbar, occ_bytes + kMlpHalfs * 2);
         bulk_g2s(sm.occ, a.sd.s.occ_bits, occ_bytes, &sm.mbar);
         bulk_g2s(sm.W, a.sd.s.mlp_h, kMlpHalfs * 2, &sm.mbar);
-        bulk_g2s(sm.hash0, reinterpret_cast<const __half2*>(a.sd.s.table_h) + a.sd.hl.offset[0], kHash0Entries * 4, &sm.mbar);
     }
     load_frame_const(sm.fc, a.sd);
     __syncthreads();
@@ -229,7 +227,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) render_fwd_kernel(const __grid
     ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
     ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
     ctx.Wsm = sm.W;
-    ctx.hash0 = sm.hash0;
+   
     ctx.fc = &sm.fc;
     ctx.hl = &a.sd.hl;
     WarpScratch<false>& ws = sm.ws[warp];
@@ -396,7 +394,6 @@ struct QueryArgs {
 template <int kWarps, bool kKeepXc>
 struct QuerySmem {
     __align__(16) __half W[kMlpHalfs];
-    __align__(16) __half2 hash0[kHash0Entries];
     FrameConst fc;
     __align__(8) uint64_t mbar;
     WarpScratch<kKeepXc> ws[kWarps];
@@ -411,9 +408,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         mbar_init(&sm.mbar, 1);
-        mbar_expect_tx(&sm.mbar, kMlpHalfs * 2 + kHash0Entries * 4);
+        mbar_expect_tx(&sm.mbar, kMlpHalfs * 2);
         bulk_g2s(sm.W, a.sd.s.mlp_h, kMlpHalfs * 2, &sm.mbar);
-        bulk_g2s(sm.hash0, reinterpret_cast<const __half2*>(a.sd.s.table_h) + a.sd.hl.offset[0], kHash0Entries * 4, &sm.mbar);
     }
     load_frame_const(sm.fc, a.sd);
     __syncthreads();
@@ -422,7 +418,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
     ctx.field.data = a.sd.s.field;
     ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
     ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
-    ctx.Wsm = sm.W; ctx.hash0 = sm.hash0; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
+    ctx.Wsm = sm.W; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
     unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_load = 0, st_hash = 0;
     // grid mode: a batch holds all jitter passes of 32/passes neighbouring cells, so that the 32 lanes stay within a
     // few voxels of the skinning field (L1 wavefronts, not DRAM, bound this kernel)

@@ -40,7 +40,6 @@ template <int kWarps>
 struct TrainSmem {
     __align__(128) uint32_t occ[64 * 64 * 64 / 32];
     __align__(16) __half W[kMlpHalfs];
-    __align__(16) __half2 hash0[kHash0Entries];
     FrameConst fc;
     __align__(8) uint64_t mbar;
     WarpScratch<true> ws[kWarps];
@@ -57,10 +56,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) train_fwd_kernel(const __grid_
     const uint32_t occ_bytes = (uint32_t)(G * G * G / 8);
     if (threadIdx.x == 0) {
         mbar_init(&sm.mbar, 1);
-        mbar_expect_tx(&sm.mbar, occ_bytes + kMlpHalfs * 2 + kHash0Entries * 4);
+        mbar_expect_tx(&sm.mbar, occ_bytes + kMlpHalfs * 2);
         bulk_g2s(sm.occ, a.sd.s.occ_bits, occ_bytes, &sm.mbar);
         bulk_g2s(sm.W, a.sd.s.mlp_h, kMlpHalfs * 2, &sm.mbar);
-        bulk_g2s(sm.hash0, reinterpret_cast<const __half2*>(a.sd.s.table_h) + a.sd.hl.offset[0], kHash0Entries * 4, &sm.mbar);
     }
     load_frame_const(sm.fc, a.sd);
     __syncthreads();
@@ -70,7 +68,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) train_fwd_kernel(const __grid_
     ctx.field.data = a.sd.s.field;
     ctx.field.D = a.sd.s.D; ctx.field.H = a.sd.s.H; ctx.field.W = a.sd.s.W;
     ctx.table = reinterpret_cast<const __half2*>(a.sd.s.table_h);
-    ctx.Wsm = sm.W; ctx.hash0 = sm.hash0; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
+    ctx.Wsm = sm.W; ctx.fc = &sm.fc; ctx.hl = &a.sd.hl;
     WarpScratch<true>& ws = sm.ws[warp];
     TrainWarpExtra& wx = sm.wx[warp];
     const FrameConst& fc = sm.fc;
@@ -995,9 +993,20 @@ __global__ void adam_dev_tail_kernel(float* __restrict__ p, float* __restrict__ 
 }
 
 __global__ void grad_finite_kernel(const float* __restrict__ g, long n, float* __restrict__ found_inf) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
     bool bad = false;
-    for (long j = i; j < n; j += (long)gridDim.x * blockDim.x) bad |= !isfinite(g[j]);
+    if ((reinterpret_cast<size_t>(g) & 15) == 0) {  // 128-bit streaming reads (the gradient is consumed by the Adam pass next)
+        const long n4 = n / 4;
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        for (long j = i; j < n4; j += stride) {
+            const float4 x = g4[j];
+            // a finite float has an exponent field below 0xff: (bits & 0x7f800000) != 0x7f800000
+            bad |= !(isfinite(x.x) && isfinite(x.y) && isfinite(x.z) && isfinite(x.w));
+        }
+        for (long j = n4 * 4 + i; j < n; j += stride) bad |= !isfinite(g[j]);
+    } else {
+        for (long j = i; j < n; j += stride) bad |= !isfinite(g[j]);
+    }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *found_inf = 1.f;
 }
 

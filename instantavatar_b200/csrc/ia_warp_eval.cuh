@@ -39,7 +39,6 @@ struct EvalCtx {
     FieldDesc field;
     const __half2* __restrict__ table;
     const __half* Wsm;        // padded fp16 weights in shared memory
-    const __half2* hash0;     // level 0 of the hash grid in shared memory
     const FrameConst* fc;     // shared memory
     const HashLevels* hl;     // kernel-parameter (constant bank) copy
 };
@@ -115,9 +114,8 @@ __device__ __forceinline__ void warp_eval_samples(const EvalCtx& ctx, WarpScratc
             const float n0 = fminf(fmaxf((x0 - fc.net_center[0]) / fc.net_scale[0] + 0.5f, 0.f), 1.f);
             const float n1 = fminf(fmaxf((x1 - fc.net_center[1]) / fc.net_scale[1] + 0.5f, 0.f), 1.f);
             const float n2 = fminf(fmaxf((x2 - fc.net_center[2]) / fc.net_scale[2] + 0.5f, 0.f), 1.f);
-            arow[0] = hash_encode_level0_smem(ctx.hash0, *ctx.hl, n0, n1, n2);
-#pragma unroll 5
-            for (int l = 1; l < kLevels; l++) arow[l] = hash_encode_level(ctx.table, *ctx.hl, l, n0, n1, n2, &nhash);
+#pragma unroll 4
+            for (int l = 0; l < kLevels; l++) arow[l] = hash_encode_level(ctx.table, *ctx.hl, l, n0, n1, n2, &nhash);
         } else {
 #pragma unroll
             for (int l = 0; l < kLevels; l++) arow[l] = __floats2half2_rn(0.f, 0.f);
