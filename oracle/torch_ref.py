@@ -119,12 +119,14 @@ def render_train_torch(out_np: dict, net, enc_params: torch.Tensor, col_params: 
 
 
 def pose_grad_reference(xd, best, xc_opt, j_inv, lbs_voxel, offset_k, scale_k, tfs, center, scale, enc_params, col_params,
-                        g_sigma, g_rgb, emulate=True):
+                        g_sigma, g_rgb, emulate=True, g_xc=None):
     """d loss / d tfs of the selected roots, restating deformers/fast_snarf/deformer_torch.py:50-67 (version 1) literally:
     x_c = x_c*.detach() + bmv(-J_inv, x_d* - x_d*.detach()),  x_d* = forward_skinning(x_c*, tfs) (:171-188) with weights
     from F.grid_sample(lbs_voxel, scale*(x_c+offset), align_corners=True, padding_mode='border') (:190-201), followed by
     the network (ngp.py:73-83) whose positional gradient is tiny-cuda-nn's.  All inputs CPU torch tensors; `best` [P]
-    selects the initialisation per point (-1: none).  Returns grad [24,4,4] for loss = sum(g_sigma*sigma + g_rgb*rgb)."""
+    selects the initialisation per point (-1: none).  Returns grad [24,4,4] for loss = sum(g_sigma*sigma + g_rgb*rgb).
+    g_xc [P,3] (optional): d loss / d x_c handed over instead of differentiating the network here -- isolates the
+    implicit-differentiation algebra (J_inv, skinning weights, outer products) from the network's fp16 gradient chain."""
     import torch.nn.functional as F
     sel = best >= 0
     idx = best.clamp(min=0).long()
@@ -139,7 +141,10 @@ def pose_grad_reference(xd, best, xc_opt, j_inv, lbs_voxel, offset_k, scale_k, t
     xd_opt = torch.einsum("pn,nij,pj->pi", w, tfs.reshape(24, 4, 4), xh)[:, :3]
     corr = torch.einsum("pij,pj->pi", -Ji, xd_opt - xd_opt.detach())
     xc = xc0 + corr
-    sigma, rgb = ngp_forward(xc, center, scale, enc_params, col_params, emulate, pos_grad=True)
-    loss = (sigma * g_sigma[sel]).sum() + (rgb * g_rgb[sel]).sum()
+    if g_xc is not None:
+        loss = (xc * g_xc[sel].detach()).sum()
+    else:
+        sigma, rgb = ngp_forward(xc, center, scale, enc_params, col_params, emulate, pos_grad=True)
+        loss = (sigma * g_sigma[sel]).sum() + (rgb * g_rgb[sel]).sum()
     loss.backward()
     return tfs.grad.reshape(24, 4, 4)

@@ -241,3 +241,38 @@ def test_transform_rays_kernel_matches_torch_expression():
     # empty input
     e = ops.transform_rays(w2s, torch.empty((0, 3), device="cuda"), torch.empty((0, 3), device="cuda"))
     assert e[0].shape == (0, 3) and e[2].shape == (0,)
+
+
+def test_model_from_reference_config_renders_like_the_keyword_form():
+    """`DNeRFModel(opt, datamodule)` with the reference's `model.opt` node (confs/SNARF_NGP.yaml + the network / deformer /
+    renderer groups, `_target_` strings resolved through the instant_avatar alias package) behaves like the keyword form"""
+    import torch
+    from instantavatar_b200 import synthetic
+    from instantavatar_b200.models.dnerf import DNeRFModel
+    opt = {
+        "network": {"_target_": "instant_avatar.models.networks.ngp.NeRFNGPNet",
+                    "opt": {"use_viewdir": False, "cond_dim": 0, "center": [0, -0.3, 0], "scale": [2.5, 2.5, 2.5]}},
+        "deformer": {"_target_": "instant_avatar.deformers.snarf_deformer.SNARFDeformer", "model_path": None, "gender": "male",
+                     "opt": {"softmax_mode": "hierarchical", "resolution": 128, "cano_pose": "A_pose", "precision": 32}},
+        "renderer": {"_target_": "instant_avatar.renderers.raymarcher_acc.Raymarcher", "MAX_SAMPLES": 256, "MAX_BATCH_SIZE": 291600},
+        "optimize_SMPL": {"enable": False, "is_refine": False},
+        "loss": {"_target_": "instant_avatar.utils.loss.NeRFLoss", "opt": {"w_rgb": 1.0, "w_alpha": 0.1, "w_reg": 0.1}},
+        "optimizer": {"lr": 1e-2, "betas": [0.9, 0.99], "eps": 1e-15},
+        "scheduler": {"max_epochs": 30},
+    }
+
+    class _DM:  # `len(datamodule.trainset)` is all the constructor reads without pose optimisation (DNeRF.py:27)
+        trainset = [0] * 7
+
+    a = DNeRFModel(opt, _DM(), smpl_data=synthetic.smpl_dict_cached(0), device="cuda").eval()
+    b, batch, idx = make_model(0)
+    b.eval()
+    assert type(a.renderer).__name__ == "Raymarcher" and a.optimizer.max_epochs == 30 and a.loss_fn.w_alpha == 0.1
+    torch.manual_seed(3)
+    jit = torch.rand((5, 64, 64, 64, 3), device="cuda")
+    out_a = a.render_image_fast(dict(batch), (H, W), jitters=jit)
+    out_b = b.render_image_fast(dict(batch), (H, W), jitters=jit)
+    for x, y in zip(out_a, out_b):
+        assert torch.equal(x, y)
+    a.scheduler_step()
+    assert abs(a.optimizer.lr - 1e-2 * (1 - 1 / 30) ** 1.5) < 1e-12

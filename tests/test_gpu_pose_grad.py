@@ -57,7 +57,18 @@ def test_pose_grad_matches_torch_restatement():
     assert np.all(got[:, 3, :] == 0) and np.linalg.norm(ref[:, :3]) > 0
     assert np.isfinite(got).all()
     err = rel_err(got[:, :3], ref[:, :3])
+    # (a) against the restatement that differentiates the network in fp32 PyTorch: the gap is the fp16 dgrad chain of the MLPs
     assert err < 5e-2, err
+    # (b) the implicit-differentiation algebra alone: hand the restatement the product's d loss / d x_c (ia_ngp_input_grad of
+    #     the same d loss / d features) -- J_inv of the bit-exact Broyden solve, border-padded skinning weights and the outer
+    #     products are fp32 on both sides
+    g_xc = ops.ngp_input_grad(scene, xc_best, denc).cpu()
+    ref_b = torch_ref.pose_grad_reference(xd, best.cpu(), xc.cpu(), jinv.cpu(), lbs, off, scl, tfs, net.center, net.scale,
+                                          torch.from_numpy(net.enc), torch.from_numpy(net.col), torch.from_numpy(g_sigma),
+                                          torch.from_numpy(g_rgb), True, g_xc=g_xc).numpy()
+    err_b = rel_err(got[:, :3], ref_b[:, :3])
+    print(f"pose_grad vs restatement: full {err:.3e}, algebra only {err_b:.3e}")
+    assert err_b < 2e-3, err_b
     # accumulation semantics (+=): a second call doubles the result
     ops.pose_grad(scene, t(subj.lbs_voxel), xd_g, best, denc, count, g_tfs)
     np.testing.assert_allclose(g_tfs.cpu().numpy(), 2 * got, rtol=1e-3, atol=1e-7 * np.abs(got).max())
