@@ -68,6 +68,43 @@ for it in range(iters + 3):
         acc += ms.cpu().numpy()
 if rank == 0:
     per = dict(zip(names, (acc / iters).round(4).tolist()))
-    print(json.dumps({"n_gpus": world, "eager_phase_ms_max_over_ranks": per, "sum_ms": float(acc.sum() / iters)}))
+    print(json.dumps({"n_gpus": world, "eager_phase_ms_max_over_ranks": per, "sum_ms": float(acc.sum() / iters)}), flush=True)
+
+# ---- whole cooperative frame (CUDA graph), NCCL and peer-memory paths, rays per warp of the renderer swept: with 1/N of the
+#      rays a rank has fewer active ray tiles than resident warps, so smaller tiles (more look-ahead per ray) may pay ----
 if world > 1:
+    from instantavatar_b200.graphs import GraphedShardedFrame
+    b = {k: v.clone() for k, v in batch.items()}
+    for k in ("betas", "body_pose", "global_orient", "transl"):
+        dist.broadcast(b[k], 0)
+    peer = None
+    try:
+        peer = parallel.PeerFrame(H * W, dev)
+    except Exception as exc:
+        if rank == 0:
+            print(json.dumps({"peer_unavailable": str(exc)[:200]}), flush=True)
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for path, pf in (("nccl", None), ("peer", peer)):
+        if path == "peer" and pf is None:
+            continue
+        for rpw in (4, 2, 1, 8):
+            ops.set_option("render_rays_per_warp", rpw)
+            try:
+                g = GraphedShardedFrame(model, b, (H, W), rank, world, jit, peer=pf)
+                run = lambda: g()
+            except Exception:
+                torch.cuda.synchronize()
+                run = lambda: model.render_image_sharded(b, (H, W), rank, world, jit, peer=pf)
+            for _ in range(3):
+                run()
+            dist.barrier(); torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(15)]
+            for a_, e_ in ev:
+                flush.zero_(); a_.record(); run(); e_.record()
+            dist.barrier(); torch.cuda.synchronize()
+            ms = torch.tensor([sum(a_.elapsed_time(e_) for a_, e_ in ev) / len(ev)], device=dev, dtype=torch.float64)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(json.dumps({"n_gpus": world, "path": path, "render_rays_per_warp": rpw, "frame_ms": float(ms.item())}), flush=True)
+    ops.set_option("render_rays_per_warp", 4)
     dist.destroy_process_group()
