@@ -311,6 +311,23 @@ int ia_grad_check_finite(const float* grads, long n, float* found_inf, ia_stream
 int ia_adam_prepare(float* state, float inv_world, const float* grad_scale_dev, const float* found_inf, ia_stream_t stream);
 int ia_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long n, const float* state,
                      const float* found_inf, void* half_out, long half_skip, ia_stream_t stream);
+/* Sharded optimiser over NVLink peer memory (one process per GPU; every rank's flat gradient, flat fp16 image and a
+ * G-float flag array mapped into every peer, e.g. torch symmetric memory).  Replaces ncclReduceScatter + finite check +
+ * Adam + ncclAllGather of the NCCL path by two kernels with the exchanges inside:
+ *   ia_peer_reduce_check : shard_sum[i] = sum_r peer_grads[r][shard_off + i] (rank order; read through the peer
+ *                          mappings), tested for non-finite values; on a hit (or *found_in != 0) flag[rank] = 1 is stored
+ *                          into EVERY rank's flag array.                          -- cross-GPU barrier --
+ *   ia_peer_flags_to_found: *found_inf = OR of this rank's flag array; flags reset.
+ *   ia_adam_step_dev_peer: ia_adam_step_dev on the shard (grads = shard_sum) whose fp16 image is stored into EVERY rank's
+ *                          flat image at element shard_off + i.                   -- cross-GPU barrier --
+ * peer_grads / peer_flags / peer_half: DEVICE arrays of n_peers pointers.  The caller zeroes its gradient buffer after the
+ * first barrier (all peers have read it). */
+int ia_peer_reduce_check(const float* const* peer_grads, int n_peers, long shard_off, long shard_elems, float* shard_sum,
+                         float* const* peer_flags, int rank, const float* found_in /*nullable*/, ia_stream_t stream);
+int ia_peer_flags_to_found(float* flags, int n_peers, float* found_inf, ia_stream_t stream);
+int ia_adam_step_dev_peer(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long n, const float* state,
+                          const float* found_inf, void* const* peer_half, int n_peers, long shard_off, ia_stream_t stream);
+
 /* fp16 refresh of the padded MLP weight block only (the hash table is refreshed by ia_adam_step_dev) */
 int ia_mlp_to_half(const float* enc_params, const float* col_params, void* mlp_h, ia_stream_t stream);
 /* the same block built from the flat fp16 image of the parameters (enc_mlp_h: the first 3072 halfs of the image of

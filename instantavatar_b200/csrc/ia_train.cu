@@ -941,7 +941,8 @@ __global__ void adam_prepare_kernel(float* state, float inv_world, const float* 
 __global__ void __launch_bounds__(256) adam_dev_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                                         float4* __restrict__ v, long n4, const float* __restrict__ state,
                                                         const float* __restrict__ found_inf, uint2* __restrict__ half_out,
-                                                        long half_skip4) {
+                                                        long half_skip4, void* const* __restrict__ peer_half, int n_peers,
+                                                        long peer_off4) {
     __shared__ float st[8];
     __shared__ float fi;
     if (threadIdx.x < 8) st[threadIdx.x] = state[threadIdx.x];
@@ -968,10 +969,47 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float4* __restrict__ p, f
         upd(pi.x, gr.x, mi.x, vi.x); upd(pi.y, gr.y, mi.y, vi.y); upd(pi.z, gr.z, mi.z, vi.z); upd(pi.w, gr.w, mi.w, vi.w);
         __stcs(m + i, mi); __stcs(v + i, vi); __stcs(p + i, pi);
     }
-    if (half_out && i >= half_skip4) {
+    if ((half_out && i >= half_skip4) || peer_half) {
         const __half2 h0 = __floats2half2_rn(pi.x, pi.y), h1 = __floats2half2_rn(pi.z, pi.w);
-        __stcs(half_out + (i - half_skip4), make_uint2(*reinterpret_cast<const unsigned*>(&h0), *reinterpret_cast<const unsigned*>(&h1)));
+        const uint2 hh = make_uint2(*reinterpret_cast<const unsigned*>(&h0), *reinterpret_cast<const unsigned*>(&h1));
+        if (half_out && i >= half_skip4) __stcs(half_out + (i - half_skip4), hh);
+        // sharded optimiser over peer memory: the updated fp16 image of this rank's shard goes straight into EVERY rank's
+        // flat image (NVLink stores) -- the all-gather of the step happens inside the Adam pass
+        if (peer_half)
+            for (int pr = 0; pr < n_peers; pr++) reinterpret_cast<uint2*>(peer_half[pr])[peer_off4 + i] = hh;
     }
+}
+
+// Sharded optimiser over peer memory, part 1 (replaces ncclReduceScatter + the finite check): this rank's shard of the flat
+// gradient is summed over EVERY rank's gradient buffer read through its NVLink peer mapping (rank order 0..G-1: every rank
+// would compute the same bits), stored locally for the Adam pass, and tested for non-finite values; a rank that finds one
+// (or whose own flag is already set) raises a flag in every rank's flag array, so that all ranks skip the step together.
+__global__ void __launch_bounds__(256) peer_reduce_check_kernel(const float* const* __restrict__ peer_g, int n_peers, long off4,
+                                                                 long n4, float4* __restrict__ shard_sum,
+                                                                 float* const* __restrict__ peer_flags, int rank,
+                                                                 const float* __restrict__ found_in) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int pr = 0; pr < n_peers; pr++) {
+            const float4 x = __ldcv(reinterpret_cast<const float4*>(peer_g[pr]) + off4 + i);  // never a stale cached line
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+        bad |= !(isfinite(acc.x) && isfinite(acc.y) && isfinite(acc.z) && isfinite(acc.w));
+        shard_sum[i] = acc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && found_in && *found_in != 0.f) bad = true;
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0)
+        for (int pr = 0; pr < n_peers; pr++) peer_flags[pr][rank] = 1.f;
+}
+
+// part 2: OR of the flags every rank may have raised in this rank's flag array -> found_inf; flags reset for the next step
+__global__ void peer_flags_to_found_kernel(float* __restrict__ flags, int n_peers, float* __restrict__ found_inf) {
+    if (threadIdx.x != 0) return;
+    float f = 0.f;
+    for (int pr = 0; pr < n_peers; pr++) { if (flags[pr] != 0.f) f = 1.f; flags[pr] = 0.f; }
+    *found_inf = f;
 }
 
 // the last n % 4 elements of a tensor whose length is not a multiple of 4 (small pose tables); same update as above
@@ -1412,10 +1450,43 @@ int ia_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg
     if (n4 > 0)
         adam_dev_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
             reinterpret_cast<float4*>(params), reinterpret_cast<float4*>(grads), reinterpret_cast<float4*>(exp_avg),
-            reinterpret_cast<float4*>(exp_avg_sq), n4, state, found_inf, reinterpret_cast<uint2*>(half_out), half_skip / 4);
+            reinterpret_cast<float4*>(exp_avg_sq), n4, state, found_inf, reinterpret_cast<uint2*>(half_out), half_skip / 4, nullptr, 0, 0);
     if (rem)
         adam_dev_tail_kernel<<<1, 4, 0, (cudaStream_t)stream>>>(params + n4 * 4, grads + n4 * 4, exp_avg + n4 * 4, exp_avg_sq + n4 * 4,
                                                                rem, state, found_inf);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_peer_reduce_check(const float* const* peer_grads, int n_peers, long shard_off, long shard_elems, float* shard_sum,
+                         float* const* peer_flags, int rank, const float* found_in, ia_stream_t stream) {
+    IA_REQUIRE(peer_grads && shard_sum && peer_flags && n_peers >= 1 && n_peers <= 64 && rank >= 0 && rank < n_peers);
+    IA_REQUIRE(shard_off >= 0 && shard_elems > 0 && shard_off % 4 == 0 && shard_elems % 4 == 0);
+    const int sms = sm_count();
+    if (sms <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
+    peer_reduce_check_kernel<<<sms * 8, 256, 0, (cudaStream_t)stream>>>(peer_grads, n_peers, shard_off / 4, shard_elems / 4,
+                                                                        reinterpret_cast<float4*>(shard_sum), peer_flags, rank, found_in);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_peer_flags_to_found(float* flags, int n_peers, float* found_inf, ia_stream_t stream) {
+    IA_REQUIRE(flags && found_inf && n_peers >= 1 && n_peers <= 64);
+    peer_flags_to_found_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n_peers, found_inf);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+int ia_adam_step_dev_peer(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long n, const float* state,
+                          const float* found_inf, void* const* peer_half, int n_peers, long shard_off, ia_stream_t stream) {
+    IA_REQUIRE(n > 0 && n % 4 == 0 && shard_off >= 0 && shard_off % 4 == 0);
+    IA_REQUIRE(params && grads && exp_avg && exp_avg_sq && state && peer_half && n_peers >= 1 && n_peers <= 64);
+    IA_REQUIRE((reinterpret_cast<size_t>(params) | reinterpret_cast<size_t>(grads) | reinterpret_cast<size_t>(exp_avg) |
+                reinterpret_cast<size_t>(exp_avg_sq)) % 16 == 0);
+    const long n4 = n / 4;
+    adam_dev_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(params), reinterpret_cast<float4*>(grads), reinterpret_cast<float4*>(exp_avg),
+        reinterpret_cast<float4*>(exp_avg_sq), n4, state, found_inf, nullptr, 0, peer_half, n_peers, shard_off / 4);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

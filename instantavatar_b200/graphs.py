@@ -151,6 +151,7 @@ class GraphedTrainStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             model.net_coarse.half_params()
+            model.optimizer.prepare(model.world_size)   # sharded step: peer mappings exist before the snapshot / capture
             grid = model.renderer.density_grid_train
             if grid.aabb is not None:
                 grid.occupancy_bits()  # allocate + pack now so that the bit field is part of the snapshot

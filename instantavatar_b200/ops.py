@@ -305,6 +305,21 @@ def grad_poison_shards(grads, shard_elems: int, n_shards: int, found_inf):
     _lib.count(1); check(lib().ia_grad_poison_shards(ptr(grads, f32), C.c_long(shard_elems), C.c_int(n_shards), ptr(found_inf, f32), stream()))
 
 
+def peer_reduce_check(peer_grads_dev: int, n_peers: int, shard_off: int, shard_sum, peer_flags_dev: int, rank: int, found_in=None):
+    _lib.count(1); check(lib().ia_peer_reduce_check(C.c_void_p(int(peer_grads_dev)), C.c_int(n_peers), C.c_long(shard_off), C.c_long(shard_sum.numel()),
+                                                    ptr(shard_sum, f32), C.c_void_p(int(peer_flags_dev)), C.c_int(rank), ptr(found_in), stream()))
+
+
+def peer_flags_to_found(flags, n_peers: int, found_inf):
+    _lib.count(1); check(lib().ia_peer_flags_to_found(ptr(flags, f32), C.c_int(n_peers), ptr(found_inf, f32), stream()))
+
+
+def adam_step_dev_peer(params, grads, exp_avg, exp_avg_sq, state, found_inf, peer_half_dev: int, n_peers: int, shard_off: int):
+    _lib.count(1); check(lib().ia_adam_step_dev_peer(ptr(params, f32), ptr(grads, f32), ptr(exp_avg, f32), ptr(exp_avg_sq, f32),
+                                                     C.c_long(params.numel()), ptr(state, f32), ptr(found_inf), C.c_void_p(int(peer_half_dev)),
+                                                     C.c_int(n_peers), C.c_long(shard_off), stream()))
+
+
 def mlp_to_half(enc_params, col_params, mlp_h):
     _lib.count(1); check(lib().ia_mlp_to_half(ptr(enc_params, f32), ptr(col_params, f32), ptr(mlp_h), stream()))
 

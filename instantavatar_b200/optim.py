@@ -45,8 +45,10 @@ class FusedAdam:
     tensor: the step is a fixed launch sequence that can be captured in a CUDA graph.
 
     world_size > 1 (sharded): reduce-scatter (sum) of the flat gradient -> Adam on this rank's 1/G of the
-    parameters (fp32 master, m, v touched only there: 365 MB / G of HBM traffic instead of 365 MB replicated) ->
-    all-gather of the flat fp16 image (26 MB) that the forward kernels read.  The fp32 masters of the other shards go
+    parameters (fp32 master, m, v touched only there: 443 MB / G of HBM traffic instead of 443 MB replicated) ->
+    all-gather of the flat fp16 image (26 MB) that the forward kernels read.  On an NVLink box both exchanges run INSIDE two
+    kernels over peer memory (`_step_peer`: every rank's gradient vector and fp16 image are symmetric-memory mappings; the
+    shard sum reads all peers' gradients, the Adam pass stores its fp16 result into all peers' images); otherwise NCCL.  The fp32 masters of the other shards go
     stale on this rank; `gather_master_params()` all-gathers them (checkpointing / state_dict).  A local overflow is
     broadcast inside the reduce-scatter (ia_grad_poison_shards), so every rank skips the same steps."""
 
@@ -76,6 +78,8 @@ class FusedAdam:
         self.state_t = torch.tensor([lr, betas[0], betas[1], eps, 0.0, 1.0, 1.0, 1.0], dtype=torch.float32).to(dev)
         self._shard_g = None
         self.masters_stale = False
+        self.use_peer = True   # sharded step: exchange over NVLink peer memory when the platform can map it (else NCCL)
+        self._peer = None      # None: not tried yet; False: unavailable; dict: symmetric-memory handles
 
     @property
     def lr_factor(self):  # LambdaLR of DNeRF.py:52-55, stepped in on_validation_epoch_end only
@@ -108,6 +112,70 @@ class FusedAdam:
         ops.mlp_to_half_from_half(self.flat_h[:self.n_mlp], self.flat_h[self.n_enc:self.n], mlp_h)
         self.net.mark_clean()
 
+    def _try_enable_peer(self, world_size: int, group=None):
+        """Move the gradient vector and the fp16 image into symmetric (peer-mapped) memory; collective.  All ranks agree."""
+        import os
+        import torch.distributed as dist
+        ok, handles = False, None
+        dev = self.flat_g.device
+        if self.use_peer and dev.type == "cuda" and dist.get_backend(group) == "nccl" and not os.environ.get("IA_B200_NO_PEER"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                grp = group if group is not None else dist.group.WORLD
+                g = symm.empty(self.flat_g.numel(), dtype=torch.float32, device=dev)
+                h = symm.empty(self.flat_h.numel(), dtype=torch.float16, device=dev)
+                fl = symm.empty(64, dtype=torch.float32, device=dev)
+                handles = {"g": symm.rendezvous(g, grp), "h": symm.rendezvous(h, grp), "f": symm.rendezvous(fl, grp), "flags": fl,
+                           "bufs": (g, h)}
+                ok = True
+            except Exception as exc:  # no peer mapping on this platform
+                self._peer_error = f"{type(exc).__name__}: {exc}"[:200]
+        flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if flag.item() != 1.0:
+            self._peer = False
+            return
+        g, h = handles["bufs"]
+        g.copy_(self.flat_g); h.copy_(self.flat_h); handles["flags"].zero_()
+        enc, col = self.params
+        self.flat_g, self.flat_h = g, h
+        enc.grad, col.grad = g[:self.n_enc], g[self.n_enc:self.n]
+        if hasattr(self.net, "adopt_half_table"):
+            dirty = getattr(self.net, "_dirty", True)
+            self.net.adopt_half_table(h[self.n_mlp:self.n_enc].view((self.n_enc - self.n_mlp) // 2, 2))
+            self.net._dirty = dirty  # the contents were copied: no refresh from the masters needed
+        torch.cuda.synchronize(dev)
+        handles["g"].barrier(channel=0)
+        torch.cuda.synchronize(dev)
+        self._peer = handles
+
+    def prepare(self, world_size: int, group=None):
+        """one-time collective set-up of the sharded step (shard buffer, peer mappings); call it before capturing a CUDA
+        graph or snapshotting optimiser state -- `step` does it lazily otherwise"""
+        if world_size <= 1:
+            return
+        S, _ = shard_layout(self.n, world_size)
+        if self._shard_g is None or self._shard_g.numel() != S:
+            self._shard_g = torch.zeros(S, device=self.flat_g.device, dtype=torch.float32)
+        if self._peer is None:
+            self._try_enable_peer(world_size, group)
+
+    def _step_peer(self, found, scale_t, world_size, rank, S):
+        """reduce-scatter, overflow agreement and all-gather INSIDE two kernels over NVLink peer memory (3 barriers)"""
+        pr = self._peer
+        lo, hi = rank * S, (rank + 1) * S
+        pr["g"].barrier(channel=0)                       # every rank's backward has finished writing its gradient
+        ops.peer_reduce_check(pr["g"].buffer_ptrs_dev, world_size, lo, self._shard_g, pr["f"].buffer_ptrs_dev, rank, found)
+        pr["f"].barrier(channel=0)                       # every rank has read all gradients and raised its flag
+        ops.peer_flags_to_found(pr["flags"], world_size, found)
+        self.flat_g.zero_()
+        ops.adam_prepare(self.state_t, 1.0 / world_size, scale_t, found)
+        ops.adam_step_dev_peer(self.flat_p[lo:hi], self._shard_g, self.flat_m[lo:hi], self.flat_v[lo:hi], self.state_t, found,
+                               pr["h"].buffer_ptrs_dev, world_size, lo)
+        pr["h"].barrier(channel=0)                       # every rank's shard of the fp16 image has landed everywhere
+        self._refresh_mlp()
+        self.masters_stale = True
+
     def step(self, scaler: GradScaler | None = None, world_size: int = 1, group=None):
         found = scaler.found_inf if scaler is not None else None
         scale_t = scaler.scale_t if scaler is not None else None
@@ -124,8 +192,11 @@ class FusedAdam:
         from . import parallel
         rank = dist.get_rank(group)
         S, L = shard_layout(self.n, world_size)
-        if self._shard_g is None or self._shard_g.numel() != S:
-            self._shard_g = torch.zeros(S, device=self.flat_g.device, dtype=torch.float32)
+        self.prepare(world_size, group)
+        if self._peer:
+            if found is None:
+                found = self._own_found = getattr(self, "_own_found", None) or torch.zeros(1, device=self.flat_g.device)
+            return self._step_peer(found, scale_t, world_size, rank, S)
         if found is not None:  # a local overflow must skip the step on EVERY rank: it rides inside the reduce-scatter
             ops.grad_check_finite(self.flat_g[:self.n], found)
             ops.grad_poison_shards(self.flat_g[:L], S, world_size, found)  # `found` may already carry the pose group's flag

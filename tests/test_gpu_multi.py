@@ -137,6 +137,14 @@ def _worker(rank, world, port, ret):
     sharded_m = fresh_model(); sharded_m.world_size = world
     steps(sharded_m, sb, jitter[sl].contiguous(), noise[sl].contiguous())
     torch.cuda.synchronize()
+    # the same steps with the NCCL collectives instead of the peer-memory kernels (both paths must agree; with two ranks the
+    # two-term sums are identical whatever the order)
+    nccl_m = fresh_model(); nccl_m.world_size = world; nccl_m.optimizer.use_peer = False
+    steps(nccl_m, sb, jitter[sl].contiguous(), noise[sl].contiguous())
+    torch.cuda.synchronize()
+    if rank == 0:
+        ret["peer_optimizer_used"] = bool(sharded_m.optimizer._peer)
+        ret["peer_vs_nccl_fp16_equal_frac"] = float((sharded_m.optimizer.flat_h[: single.optimizer.n] == nccl_m.optimizer.flat_h[: single.optimizer.n]).float().mean())
     h_single, h_shard = single.optimizer.flat_h[: single.optimizer.n].float(), sharded_m.optimizer.flat_h[: single.optimizer.n].float()
     gathered = [torch.empty_like(h_shard) for _ in range(world)]
     dist.all_gather(gathered, h_shard)
@@ -170,4 +178,6 @@ def test_two_gpu_frame_and_gradient():
     # the worst case is 2 x 3 steps x lr = 6e-2; the mean difference must be tiny)
     assert ret["fp16_image_same_on_ranks"] and ret["adam_steps"] == (3, 3), dict(ret)
     assert ret["param_moved"] > 1e-3 and ret["param_max_diff"] <= 6.1e-2 and ret["param_mean_diff"] < 1e-4, dict(ret)
-    assert ret["fp16_frac_diff"] < 1e-2, dict(ret)   # entries whose fp16 image differs at all (noise-level gradients)
+    assert ret["fp16_frac_diff"] < 1e-2, dict(ret)
+    print("sharded optimiser:", {k: ret[k] for k in ("peer_optimizer_used", "peer_vs_nccl_fp16_equal_frac", "param_max_diff", "param_mean_diff", "fp16_frac_diff")})
+    assert ret["peer_vs_nccl_fp16_equal_frac"] > 0.9999, dict(ret)   # entries whose fp16 image differs at all (noise-level gradients)
