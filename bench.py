@@ -298,7 +298,7 @@ def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, u
     for k in ("rays_o", "rays_d", "near", "far"):
         b[k] = batch[k][:, pick].contiguous()
     a = alpha_gt[pick][None]
-    model.world_size = world
+    model.configure_parallel(world)
     model.global_step = 2000  # steady state: no density noise, grid refresh uses the previous field as `valid`
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 

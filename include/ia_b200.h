@@ -289,7 +289,9 @@ int ia_pose_grad(const IaScene* scene /*[host]*/, const float* lbs_voxel, const 
 
 /* NeRFLoss forward + analytic backward in one pass (instant_avatar/utils/loss.py:53-79):
  * loss = w_rgb mse(rgb) + w_alpha mse(alpha) + w_reg (mean reg(alpha) + mean reg(weights) + 2*0.313262),
- * reg(x) = -log(exp(-x) + exp(x-1)).  sums [4] receives {sum (rgb-t)^2, sum (alpha-a)^2, sum reg(alpha), sum reg(w)};
+ * reg(x) = -log(exp(-x) + exp(x-1)).  sums [12] (zeroed by the library): [0..3] = {sum (rgb-t)^2, sum (alpha-a)^2,
+ * sum reg(alpha), sum reg(w)}, [4..8] = {mse_loss, loss_alpha_coarse, reg_alpha, reg_density, loss} as the reference logs
+ * them (written by the last block to finish: no element-wise launches follow), [11] = block ticket.
  * g_* receive d loss / d output times *scale_dev (GradScaler scale; NULL = 1). */
 int ia_nerf_loss(int n_rays, int n_samples, const float* rgb, const float* alpha, const float* weights,
                  const float* target_rgb, const float* target_alpha, float w_rgb, float w_alpha, float w_reg,

@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(256) precompute_kernel(const float* __restrict
         for (int c = 0; c < 12; c++) J[c] = 0.f;
 #pragma unroll 4
         for (int j = 0; j < 24; j++) {
-            const float w = __ldg(voxel_w + (long)j * V + index);
+            const float w = __ldcs(voxel_w + (long)j * V + index);  // evict-first: the 50 MB of weights must not push the field out of L2
 #pragma unroll
             for (int c = 0; c < 12; c++) J[c] = __fmaf_rn(w, T[j][c], J[c]);
         }
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(256) precompute_kernel(const float* __restrict
 #pragma unroll
         for (int i0 = 0; i0 < 3; i0++) {
             vd[i0] = aff3f(J[i0 * 4 + 0], cx, J[i0 * 4 + 1], cy, J[i0 * 4 + 2], cz, J[i0 * 4 + 3]);
-            if (voxel_d) voxel_d[(long)i0 * V + index] = vd[i0];
+            if (voxel_d) __stcs(voxel_d + (long)i0 * V + index, vd[i0]);
         }
     }
     if (aabb) {

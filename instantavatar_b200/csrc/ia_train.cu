@@ -1535,12 +1535,34 @@ __global__ void __launch_bounds__(256) nerf_loss_kernel(int n_rays, int S, const
         s_ra += v;
         g_alpha[r] = scale * (w_alpha * 2.f * da / (float)n_rays + w_reg * dv / (float)n_rays);
     }
+    // block reduction, then ONE atomic per block and value (19 k same-address atomics serialised at L2 were 30 us of this
+    // kernel); the last block to finish turns the four sums into the loss terms the reference logs (loss.py:58-79), so no
+    // element-wise torch launches follow
     float vals[4] = {s_rgb, s_a, s_ra, s_rw};
+    __shared__ float red[8][4];
+    __shared__ bool last;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         float v = vals[k];
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sums[k], v);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float v = 0.f;
+        for (int w = 0; w < 8; w++) v += red[w][threadIdx.x];
+        atomicAdd(&sums[threadIdx.x], v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<unsigned*>(sums) + 11, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        const volatile float* sv = sums;
+        const float OFFSET = 0.313262f, n = (float)n_rays;
+        const float mse = sv[0] / (3.0f * n), msa = sv[1] / n, ra = sv[2] / n + OFFSET, rw = sv[3] / (n * (float)S) + OFFSET;
+        sums[4] = mse; sums[5] = msa; sums[6] = ra; sums[7] = rw;
+        sums[8] = ((w_rgb * mse + w_alpha * msa) + w_reg * ra) + w_reg * rw;
     }
 }
 
@@ -1553,7 +1575,7 @@ extern "C" int ia_nerf_loss(int n_rays, int n_samples, const float* rgb, const f
     IA_REQUIRE(n_rays > 0 && n_samples > 0);
     IA_REQUIRE(rgb && alpha && weights && target_rgb && target_alpha && g_rgb && g_alpha && g_weights && sums);
     cudaStream_t st = (cudaStream_t)stream;
-    IA_CHECK_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(float), st));
+    IA_CHECK_CUDA(cudaMemsetAsync(sums, 0, 12 * sizeof(float), st));
     const int sms = sm_count() > 0 ? sm_count() : 148;
     nerf_loss_kernel<<<sms * 4, 256, 0, st>>>(n_rays, n_samples, rgb, alpha, weights, target_rgb, target_alpha, w_rgb, w_alpha, w_reg,
                                               scale_dev, g_rgb, g_alpha, g_weights, sums);

@@ -71,6 +71,14 @@ class DNeRFModel(torch.nn.Module):
             self.enable_pose_optimisation(datamodule.trainset.get_SMPL_params(), lr=float(self._pose_cfg.get("lr", 5e-4)),
                                           is_refine=bool(self._pose_cfg.get("is_refine", False)))
 
+    def configure_parallel(self, world_size: int):
+        """Ray-sharded training over `world_size` ranks.  With 1/G of the step's rays a rank has fewer ray tiles than resident
+        warps and the forward kernel's time is the critical path of its heaviest tile, so from 4 ranks on the tiles shrink to
+        one ray with 32-deep look-ahead (measured: profiles/launches_train_512*_r2.csv; results do not depend on the tile)."""
+        self.world_size = int(world_size)
+        ops.set_option("train_rays_per_warp", 1 if self.world_size >= 4 else 2)
+        self.optimizer.prepare(self.world_size)
+
     def scheduler_step(self):
         """LambdaLR (1 - epoch / max_epochs)^1.5 of DNeRF.py:52-55: ONE schedule for every parameter group, the SMPL
         pose group (base lr 5e-4) included; the reference steps it in on_validation_epoch_end (DNeRF.py:163-166)."""
