@@ -275,7 +275,7 @@ def bench_ref_structure(model, batch, device, iters=5):
         return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
-def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, use_graph=True):
+def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, use_graph=True, train_rays_per_warp=None):
     """second half of BASELINE.json's metric: ms per training step (DNeRF.py:112-161) at 4096 rays per step
     (4 patches of 32x32, confs/sampler/patch.yaml), rays sharded over the ranks, one gradient all-reduce per step;
     includes the every-20-steps occupancy-grid refresh amortised over the timed steps."""
@@ -299,6 +299,9 @@ def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, u
         b[k] = batch[k][:, pick].contiguous()
     a = alpha_gt[pick][None]
     model.configure_parallel(world)
+    if train_rays_per_warp:  # sweeps (scripts/train_scaling.py) override the tile size configure_parallel picked
+        from instantavatar_b200 import ops as _ops
+        _ops.set_option("train_rays_per_warp", train_rays_per_warp)
     model.global_step = 2000  # steady state: no density noise, grid refresh uses the previous field as `valid`
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 

@@ -22,11 +22,9 @@ if world > 1:
 model, hb, batch = bench.build_model(dev, bench.FRAMES[rank % len(bench.FRAMES)])
 flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
 out = {"n_gpus": world}
-for trpw in (2, 1, 4):
-    ops.set_option("train_rays_per_warp", trpw)
-    r = bench.bench_train(model, batch, dev, rank, world, flush, steps=40, warmup=25)
+for trpw in (2, 1):
+    r = bench.bench_train(model, batch, dev, rank, world, flush, steps=40, warmup=25, train_rays_per_warp=trpw)
     out[f"train_ms_rays_per_warp_{trpw}"] = r["ms_per_step"]
-ops.set_option("train_rays_per_warp", 2)
 
 
 def graph_ms(fn, iters=30):
@@ -64,10 +62,8 @@ _step, _upd = model.optimizer.step, model.scaler.update
 model.optimizer.step = lambda *a, **k: None
 model.scaler.update = lambda: None
 for trpw in (2, 1):
-    ops.set_option("train_rays_per_warp", trpw)
-    r = bench.bench_train(model, batch, dev, rank, world, flush, steps=40, warmup=25)
+    r = bench.bench_train(model, batch, dev, rank, world, flush, steps=40, warmup=25, train_rays_per_warp=trpw)
     out[f"train_compute_only_ms_rays_per_warp_{trpw}"] = r["ms_per_step"]
-ops.set_option("train_rays_per_warp", 2)
 model.optimizer.step, model.scaler.update = _step, _upd
 model.optimizer.zero_grad()
 model.world_size = world
