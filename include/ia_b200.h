@@ -187,6 +187,17 @@ int ia_occupancy_query_peer(const IaScene* scene /*[host]*/, const float* jitter
                             float* const* peer_density, int n_peers, void* workspace, int shard, int n_shards,
                             IaStats* stats, ia_stream_t stream);
 
+/* ia_occupancy_query / _peer with an explicit schedule.  batch_order (nullable): DEVICE list of n_order batch indices
+ * (a batch = 32/passes neighbouring cells with all their passes; batch b holds cells b*(32/passes) ...), started in that
+ * order by the kernel's dynamic queue; it replaces the (shard, n_shards) selection.  batch_cost (nullable): DEVICE
+ * [ceil(G^3 / (32/passes))] uint32, receives the SM cycles each evaluated batch took.  Results do not depend on the order
+ * (max-reduction).  With few batches per warp (a frame split over 8 GPUs: ~3) starting last frame's most expensive
+ * batches first removes most of the load-balance tail.  Exactly one of density_max / peer_density is non-NULL. */
+int ia_occupancy_query_ordered(const IaScene* scene /*[host]*/, const float* jitter, const float* aabb, int G, int passes,
+                               float* density_max, float* const* peer_density, int n_peers, void* workspace, int shard,
+                               int n_shards, const int* batch_order, int n_order, unsigned* batch_cost, IaStats* stats,
+                               ia_stream_t stream);
+
 /* Measurement aid (bench.py `roofline.peak`): the fused kernels' memory access shape in isolation -- every lane gathers
  * trilinear footprints (4 x-pair records = 12 x 32-byte sectors, 12 LDG.E.256) from the L2-resident field `field`
  * [D][H][W][24], the next footprint depending on the loaded data -- at one persistent CTA of `warps` (12 / 16 / 24 / 32)

@@ -389,6 +389,10 @@ struct QueryArgs {
     int* batch_counter;  // optional: dynamic batch scheduling (zeroed by the launcher)
     int batch_first, batch_stride;  // grid mode: this launch handles batches first, first+stride, ... (multi-GPU sharding)
     float* const* peer_density; int n_peers;  // grid mode over peer memory: max-reduce into EVERY rank's density (NVLink atomics)
+    // grid mode, optional: an explicit list of the batches of this launch in the order they should be started (longest
+    // first removes the load-balance tail when a rank holds only a few batches per warp), and the measured cost of each
+    // batch (SM cycles) that the next frame's order can be built from
+    const int* batch_order; int n_order; unsigned* batch_cost;
 };
 
 template <int kWarps, bool kKeepXc>
@@ -431,8 +435,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
             if (lane == 0) nb = atomicAdd(a.batch_counter, 1);
             lidx = __shfl_sync(kFull, nb, 0);
         }
-        const int bidx = a.batch_first + lidx * a.batch_stride;
-        if (bidx >= n_batches) break;
+        int bidx = a.batch_first + lidx * a.batch_stride;
+        if (a.batch_order) {
+            if (lidx >= a.n_order) break;
+            bidx = a.batch_order[lidx];
+        }
+        if (bidx >= n_batches || bidx < 0) break;
+        const long long t_start = a.batch_cost ? clock64() : 0;
         int p = bidx * 32 + lane;
         bool act = p < a.n;
         float x = 0, y = 0, z = 0;
@@ -477,6 +486,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
                 if (a.xc_best) { a.xc_best[p * 3] = so.xc[0]; a.xc_best[p * 3 + 1] = so.xc[1]; a.xc_best[p * 3 + 2] = so.xc[2]; }
             }
             if (a.best_init) a.best_init[p] = (int8_t)so.best;
+        }
+        if (a.batch_cost) {
+            __syncwarp();
+            if (lane == 0) a.batch_cost[bidx] = (unsigned)min((long long)0xffffffffll, clock64() - t_start);
         }
     }
     if (a.stats) {
@@ -1036,12 +1049,14 @@ int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode
     a.grid_jitter = nullptr; a.grid_aabb = nullptr; a.G = 0; a.density_max = nullptr; a.passes = 1;
     a.batch_counter = nullptr; a.batch_first = 0; a.batch_stride = 1;
     a.peer_density = nullptr; a.n_peers = 0;
+    a.batch_order = nullptr; a.n_order = 0; a.batch_cost = nullptr;
     return launch_query(a, (cudaStream_t)stream);
 }
 
 static int occupancy_query_impl(const IaScene* scene, const float* jitter, const float* aabb, int G, int passes,
                                 float* density_max, float* const* peer_density, int n_peers, void* workspace, int shard,
-                                int n_shards, IaStats* stats, ia_stream_t stream) {
+                                int n_shards, IaStats* stats, ia_stream_t stream, const int* batch_order = nullptr,
+                                int n_order = 0, unsigned* batch_cost = nullptr) {
     IA_REQUIRE(jitter && aabb && (density_max || peer_density) && G > 0 && passes > 0 && passes <= 32);
     IA_REQUIRE(n_shards >= 1 && shard >= 0 && shard < n_shards);
     QueryArgs a;
@@ -1053,6 +1068,8 @@ static int occupancy_query_impl(const IaScene* scene, const float* jitter, const
     a.batch_counter = reinterpret_cast<int*>(workspace);
     a.batch_first = shard; a.batch_stride = n_shards;
     a.peer_density = peer_density; a.n_peers = n_peers;
+    a.batch_order = batch_order; a.n_order = n_order; a.batch_cost = batch_cost;
+    IA_REQUIRE(!batch_order || (workspace && n_order >= 0));
     if (workspace) IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream));
     // peer mode: every rank's buffer is written by all ranks -- the CALLER zeroes it (before the barrier that precedes this launch)
     if (!peer_density) IA_CHECK_CUDA(cudaMemsetAsync(density_max, 0, sizeof(float) * G * G * G, (cudaStream_t)stream));
@@ -1070,6 +1087,16 @@ extern "C" int ia_occupancy_query_peer(const IaScene* scene, const float* jitter
                                        IaStats* stats, ia_stream_t stream) {
     IA_REQUIRE(peer_density && n_peers >= 1 && n_peers <= 64);
     return occupancy_query_impl(scene, jitter, aabb, G, passes, nullptr, peer_density, n_peers, workspace, shard, n_shards, stats, stream);
+}
+
+extern "C" int ia_occupancy_query_ordered(const IaScene* scene, const float* jitter, const float* aabb, int G, int passes,
+                                          float* density_max, float* const* peer_density, int n_peers, void* workspace,
+                                          int shard, int n_shards, const int* batch_order, int n_order,
+                                          unsigned* batch_cost, IaStats* stats, ia_stream_t stream) {
+    IA_REQUIRE((density_max != nullptr) != (peer_density != nullptr));
+    IA_REQUIRE(!peer_density || (n_peers >= 1 && n_peers <= 64));
+    return occupancy_query_impl(scene, jitter, aabb, G, passes, density_max, peer_density, n_peers, workspace, shard, n_shards,
+                                stats, stream, batch_order, n_order, batch_cost);
 }
 
 int ia_broyden(const IaScene* scene, const float* xd, int n, float* xc, uint8_t* valid, float* j_inv, ia_stream_t stream) {

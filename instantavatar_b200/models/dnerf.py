@@ -22,6 +22,16 @@ class Rays:  # models/structures/utils.py:5-11
     far: torch.Tensor = None
 
 
+def sharded_rays_per_warp(full_frame_rpw: int, world: int) -> int:
+    """rays per warp of the eval renderer when a frame is split over `world` GPUs (see render_image_sharded)"""
+    rpw = full_frame_rpw
+    w = world
+    while w >= 4 and rpw > 1:
+        rpw //= 2
+        w //= 2
+    return rpw
+
+
 class DNeRFModel(torch.nn.Module):
     def __init__(self, opt=None, datamodule=None, smpl_data=None, model_path=None, gender="male", n_train_frames=1, device="cuda",
                  net_seed=1337, deformer_opt=None):
@@ -282,13 +292,21 @@ class DNeRFModel(torch.nn.Module):
         rays = Rays(o=o[None], d=d[None], near=near[None], far=far[None])
         self.renderer.image_width = W if tile % (2 * W) == 0 else 0
         bg = batch["bg_color"].reshape(-1, 3)[idx] if batch.get("bg_color", None) is not None else None
-        if peer is not None:
-            # peer-memory path (parallel.PeerFrame): the render kernel stores RGBA into every rank's image over NVLink
-            self.renderer.render_test(rays, BoundModel(self.deformer, self.net_coarse, True), bg,
-                                      peer=peer.image_ptrs(parallel.shard_tiles_cached(H * W, rank, world, tile, dev, torch.int32)))
-            peer.barrier_image()
-            return peer.image
-        out = self.renderer.render_test(rays, BoundModel(self.deformer, self.net_coarse, True), bg)
+        # a rank holds 1/world of the rays: keep the number of ray tiles (CTAs) of the full frame by shrinking the tile
+        # (rays per warp 4 -> 2 -> 1 at world 4 / 8; measured 0.96 -> 0.71 ms per frame at 8 GPUs,
+        # profiles/timeline_sharded_n8_r2.jsonl); results do not depend on the tile size
+        full_rpw = ops.get_option("render_rays_per_warp")
+        ops.set_option("render_rays_per_warp", getattr(self, "sharded_render_rays_per_warp", None) or sharded_rays_per_warp(full_rpw, world))
+        try:
+            if peer is not None:
+                # peer-memory path (parallel.PeerFrame): the render kernel stores RGBA into every rank's image over NVLink
+                self.renderer.render_test(rays, BoundModel(self.deformer, self.net_coarse, True), bg,
+                                          peer=peer.image_ptrs(parallel.shard_tiles_cached(H * W, rank, world, tile, dev, torch.int32)))
+                peer.barrier_image()
+                return peer.image
+            out = self.renderer.render_test(rays, BoundModel(self.deformer, self.net_coarse, True), bg)
+        finally:
+            ops.set_option("render_rays_per_warp", full_rpw)
         local = torch.cat([out["rgb_coarse"].reshape(-1, 3), out["alpha_coarse"].reshape(-1, 1)], dim=1)
         img = parallel.all_gather_image(local, H * W, tile)   # every rank ends up with the frame (one all-gather)
         if img is not None:

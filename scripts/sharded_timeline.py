@@ -88,7 +88,7 @@ if world > 1:
         if path == "peer" and pf is None:
             continue
         for rpw in (4, 2, 1, 8):
-            ops.set_option("render_rays_per_warp", rpw)
+            model.sharded_render_rays_per_warp = rpw   # overrides the tile size render_image_sharded picks for this world size
             try:
                 g = GraphedShardedFrame(model, b, (H, W), rank, world, jit, peer=pf)
                 run = lambda: g()
@@ -106,5 +106,5 @@ if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             if rank == 0:
                 print(json.dumps({"n_gpus": world, "path": path, "render_rays_per_warp": rpw, "frame_ms": float(ms.item())}), flush=True)
-    ops.set_option("render_rays_per_warp", 4)
+    model.sharded_render_rays_per_warp = None
     dist.destroy_process_group()
