@@ -344,7 +344,8 @@ def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, u
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return {"ms_per_step": float(ms.item()), "rays_per_step": int(len(idx)), "rays_per_rank": int(n), "steps": steps,
             "cuda_graph": bool(use_graph), "grid_refresh_every": 20,
-            "collective": "reduce_scatter(52 MB fp32 gradient) + all_gather(26 MB fp16 image), sharded Adam" if world > 1 else "none",
+            "collective": ("reduce-scatter (52 MB fp32 gradient) + sharded Adam + all-gather (26 MB fp16 image): inside two kernels over NVLink "
+                           "peer memory when available (config.train_exchange_path), else NCCL") if world > 1 else "none",
             "final_loss": float(out["loss"].item()), "scaling": "strong"}
 
 
@@ -501,6 +502,38 @@ def bench_collectives(model, device, rank, world, iters=20):
             "what": "reduce_scatter(fp32 flat gradient) + all_gather(fp16 image), NCCL over NVLink"}
 
 
+def bench_optimizer_step(model, device, world, iters=30):
+    """the sharded optimiser step alone (gradient exchange + Adam on the shard + fp16 image exchange), captured in a CUDA
+    graph, device time max over ranks; says which exchange path ran (NVLink peer memory or NCCL)"""
+    import torch
+    import torch.distributed as dist
+    opt = model.optimizer
+    opt.zero_grad()
+    fn = lambda: opt.step(model.scaler, world)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    for _ in range(3):
+        g.replay()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], device=device, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return {"ms": float(ms.item()), "path": "peer" if getattr(opt, "_peer", None) else "nccl"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -635,6 +668,7 @@ def run_ours(args):
     ref_struct = bench_ref_structure(model, batch, device) if rank == 0 else None
     train = bench_train(model, batch, device, rank, world, flush, use_graph=use_graph)
     comm = bench_collectives(model, device, rank, world) if world > 1 else None
+    opt_step = bench_optimizer_step(model, device, world) if world > 1 else None
     next_rows = None
     if rank == 0:
         try:
@@ -676,8 +710,14 @@ def run_ours(args):
                     "frame_sharded_peer_ms": sharded["peer"]["ms_per_frame"] if "peer" in sharded else None,
                     "frame_sharded_bit_equal": bool(sharded["bit_equal"] and checks["frame_bit_equal"]),
                     "train_grad_rel_err": checks["train_grad_rel_err"]})
+        from instantavatar_b200.models.dnerf import sharded_rays_per_warp
+        cfg["frame_sharded_render_rays_per_warp"] = sharded_rays_per_warp(ops.get_option("render_rays_per_warp"), world)
     if comm is not None:
         cfg.update({"grad_collective_ms": comm["ms"], "grad_collective_bus_GBps": comm["bus_GBps"], "grad_collective_bytes": comm["bytes"]})
+    if opt_step is not None:
+        # the step's real exchange: reduce + finite agreement + Adam on 1/G + fp16 image exchange, on the path the step used
+        cfg.update({"train_optimizer_step_ms": opt_step["ms"], "train_exchange_path": opt_step["path"],
+                    "train_rays_per_warp": ops.get_option("train_rays_per_warp")})
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
