@@ -275,7 +275,8 @@ def bench_ref_structure(model, batch, device, iters=5):
         return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
-def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, use_graph=True, train_rays_per_warp=None):
+def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, use_graph=True, train_rays_per_warp=None,
+                rays_cap=None):
     """second half of BASELINE.json's metric: ms per training step (DNeRF.py:112-161) at 4096 rays per step
     (4 patches of 32x32, confs/sampler/patch.yaml), rays sharded over the ranks, one gradient all-reduce per step;
     includes the every-20-steps occupancy-grid refresh amortised over the timed steps."""
@@ -291,6 +292,8 @@ def bench_train(model, batch, device, rank, world, flush, steps=40, warmup=25, u
         ys, xs = torch.arange(y0, y0 + 32), torch.arange(x0, x0 + 32)
         idx.append((ys[:, None] * W + xs[None]).reshape(-1))
     idx = torch.cat(idx)
+    if rays_cap:  # sweeps only: a smaller step (every 4096 // rays_cap-th ray of the four patches)
+        idx = idx[:: len(idx) // rays_cap][:rays_cap]
     sl = parallel.shard_train_rays(len(idx), rank, world)
     pick = idx[sl].to(device)
     n = len(pick)

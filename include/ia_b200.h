@@ -264,6 +264,19 @@ int ia_train_fwd(const IaScene* scene /*[host]*/, const float* rays_o, const flo
                  float* depth, float* alpha, float* weights, float* s_sigma, float* s_rgb, float* s_xc, float* s_z,
                  int* s_count, int8_t* s_best, void* workspace, IaStats* stats, ia_stream_t stream);
 
+/* The same training forward as three launches with identical results (bit for bit): (1) march -- one warp per ray, occupied
+ * steps become consecutive slots, their jittered posed points are appended to a device-side sample list; (2) the point-query
+ * kernel over that list, every 32-sample batch an independent work item of all resident warps; (3) per-ray compositing.
+ * ia_train_fwd walks a tile's samples inside one warp, so its time is the heaviest tile's critical path (it does not shrink
+ * below ~0.36 ms however few rays a step has); this form scales with the number of samples.  workspace:
+ * ia_train_fwd_workspace_bytes(n_rays) (256 + 4 * n_rays * 256). */
+size_t ia_train_fwd_workspace_bytes(int n_rays);
+int ia_train_fwd_split(const IaScene* scene /*[host]*/, const float* rays_o, const float* rays_d, const float* near,
+                       const float* far, int n_rays, const float* bg, const float* jitter, const float* noise, float* rgb,
+                       float* depth, float* alpha, float* weights, float* s_sigma, float* s_rgb, float* s_xc, float* s_z,
+                       int* s_count, int8_t* s_best, void* workspace, size_t workspace_bytes, IaStats* stats,
+                       ia_stream_t stream);
+
 /* Compositing backward (autograd of raymarcher_acc.py:25-36,166-186): upstream grads (nullable) of rgb [n][3],
  * depth [n], alpha [n], weights [n][256] -> compact list of (canonical point, d sigma, d rgb) of the samples that
  * reached the network; l_* arrays hold up to n*256 entries, l_count [1] must be zeroed by the caller. */

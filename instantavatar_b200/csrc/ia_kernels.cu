@@ -393,6 +393,9 @@ struct QueryArgs {
     // first removes the load-balance tail when a rank holds only a few batches per warp), and the measured cost of each
     // batch (SM cycles) that the next frame's order can be built from
     const int* batch_order; int n_order; unsigned* batch_cost;
+    // point mode, optional (split training forward, ia_train.cu): the number of points lives on the device (n = capacity)
+    // and point p reads pts / writes every output at element index[p] instead of p
+    const int* n_dev; const int* index;
 };
 
 template <int kWarps, bool kKeepXc>
@@ -428,7 +431,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
     // few voxels of the skinning field (L1 wavefronts, not DRAM, bound this kernel)
     const int cells_per_batch = a.grid_aabb ? 32 / a.passes : 32;
     const int n3g = a.G * a.G * a.G;
-    const int n_batches = a.grid_aabb ? (n3g + cells_per_batch - 1) / cells_per_batch : (a.n + 31) / 32;
+    const int n_pts = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+    const int n_batches = a.grid_aabb ? (n3g + cells_per_batch - 1) / cells_per_batch : (n_pts + 31) / 32;
     for (int lidx = blockIdx.x * kWarps + warp;; lidx += gridDim.x * kWarps) {
         if (a.batch_counter) {  // dynamic: batches near the body cost several times more than empty space
             int nb = 0;
@@ -443,7 +447,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
         if (bidx >= n_batches || bidx < 0) break;
         const long long t_start = a.batch_cost ? clock64() : 0;
         int p = bidx * 32 + lane;
-        bool act = p < a.n;
+        bool act = p < n_pts;
+        long q = p;  // element the point is read from / written to
+        if (act && a.index) q = a.index[p];
         float x = 0, y = 0, z = 0;
         int cell = 0;
         if (a.grid_aabb) {
@@ -463,7 +469,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
                 y = ((float)cj / fG + jit[1] / fG) * (a.grid_aabb[4] - a.grid_aabb[1]) + a.grid_aabb[1];
                 z = ((float)ck / fG + jit[2] / fG) * (a.grid_aabb[5] - a.grid_aabb[2]) + a.grid_aabb[2];
             } else {
-                x = a.pts[p * 3]; y = a.pts[p * 3 + 1]; z = a.pts[p * 3 + 2];
+                x = a.pts[q * 3]; y = a.pts[q * 3 + 1]; z = a.pts[q * 3 + 2];
             }
         }
         SampleOut so;
@@ -480,12 +486,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
                 }
             }
         } else if (act) {
-            a.sigma[p] = so.sigma;
-            a.rgb[p * 3] = so.r; a.rgb[p * 3 + 1] = so.g; a.rgb[p * 3 + 2] = so.b;
+            a.sigma[q] = so.sigma;
+            a.rgb[q * 3] = so.r; a.rgb[q * 3 + 1] = so.g; a.rgb[q * 3 + 2] = so.b;
             if constexpr (kKeepXc) {
-                if (a.xc_best) { a.xc_best[p * 3] = so.xc[0]; a.xc_best[p * 3 + 1] = so.xc[1]; a.xc_best[p * 3 + 2] = so.xc[2]; }
+                if (a.xc_best) { a.xc_best[q * 3] = so.xc[0]; a.xc_best[q * 3 + 1] = so.xc[1]; a.xc_best[q * 3 + 2] = so.xc[2]; }
             }
-            if (a.best_init) a.best_init[p] = (int8_t)so.best;
+            if (a.best_init) a.best_init[q] = (int8_t)so.best;
         }
         if (a.batch_cost) {
             __syncwarp();
@@ -1050,6 +1056,28 @@ int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode
     a.batch_counter = nullptr; a.batch_first = 0; a.batch_stride = 1;
     a.peer_density = nullptr; a.n_peers = 0;
     a.batch_order = nullptr; a.n_order = 0; a.batch_cost = nullptr;
+    a.n_dev = nullptr; a.index = nullptr;
+    return launch_query(a, (cudaStream_t)stream);
+}
+
+// library-internal (ia_train.cu, split training forward): the point-query kernel over a device-side list -- `capacity`
+// bounds *n_dev, point p is read from pts[index[p]] and its outputs are written at element index[p]; batches are handed
+// out dynamically through batch_counter (zeroed by the caller)
+__attribute__((visibility("hidden"))) int ia_internal_query_list(const IaScene* scene, const float* pts, const int* index,
+                                                                 const int* n_dev, int capacity, int eval_mode, float* rgb,
+                                                                 float* sigma, float* xc_best, int8_t* best_init,
+                                                                 int* batch_counter, IaStats* stats, ia_stream_t stream) {
+    IA_REQUIRE(pts && index && n_dev && capacity > 0 && rgb && sigma && xc_best && batch_counter);
+    QueryArgs a;
+    int rc = make_scene_dev(scene, a.sd, false);
+    if (rc) return rc;
+    a.pts = pts; a.n = capacity; a.eval_mode = eval_mode; a.rgb = rgb; a.sigma = sigma; a.xc_best = xc_best;
+    a.best_init = best_init; a.stats = stats;
+    a.grid_jitter = nullptr; a.grid_aabb = nullptr; a.G = 0; a.density_max = nullptr; a.passes = 1;
+    a.batch_counter = batch_counter; a.batch_first = 0; a.batch_stride = 1;
+    a.peer_density = nullptr; a.n_peers = 0;
+    a.batch_order = nullptr; a.n_order = 0; a.batch_cost = nullptr;
+    a.n_dev = n_dev; a.index = index;
     return launch_query(a, (cudaStream_t)stream);
 }
 
@@ -1069,6 +1097,7 @@ static int occupancy_query_impl(const IaScene* scene, const float* jitter, const
     a.batch_first = shard; a.batch_stride = n_shards;
     a.peer_density = peer_density; a.n_peers = n_peers;
     a.batch_order = batch_order; a.n_order = n_order; a.batch_cost = batch_cost;
+    a.n_dev = nullptr; a.index = nullptr;
     IA_REQUIRE(!batch_order || (workspace && n_order >= 0));
     if (workspace) IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream));
     // peer mode: every rank's buffer is written by all ranks -- the CALLER zeroes it (before the barrier that precedes this launch)

@@ -211,6 +211,139 @@ __global__ void __launch_bounds__(kWarps * 32, 1) train_fwd_kernel(const __grid_
 }
 
 // ================================================================================================
+// split training forward: march -> sample list -> point query over the list -> per-ray compositing.
+// The fused kernel above walks a tile's samples 32 at a time inside ONE warp, so a step takes as long as its heaviest
+// tile (390 / 385 / 363 us at 4096 / 2048 / 512 rays: it does not shrink with the ray count).  Here every 32-sample batch
+// of the step is an independent work item of the point-query kernel (ia_kernels.cu), spread over all resident warps.
+// Arithmetic per sample and per ray is the fused kernel's, operation for operation (same results, bit for bit).
+// ================================================================================================
+struct TrainMarchArgs {
+    const float* rays_o; const float* rays_d; const float* near; const float* far; const float* jitter;
+    const uint32_t* occ_bits; const float* occ_aabb; int G;
+    int n_rays;
+    float* weights; float* s_xc; float* s_z; int* s_count; int8_t* s_best;
+    int* list; int* list_count;
+};
+
+// one warp per ray: lane j tests steps j, j + 32, ... (t advanced by repeated addition exactly as the fused kernel's depth
+// lanes do), occupied steps get consecutive slots, their jittered posed points go to s_xc (the query overwrites them with
+// the canonical points), and the ray's slots are appended to the global sample list as one contiguous block
+__global__ void __launch_bounds__(256) train_march_kernel(TrainMarchArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ray >= a.n_rays) return;
+    const int G = a.G;
+    float occ_min[3], occ_s[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float mn = a.occ_aabb[i], mx = a.occ_aabb[3 + i];
+        occ_min[i] = mn;
+        occ_s[i] = (float)G / (mx - mn);  // raymarcher.cu:37 (load_frame_const)
+    }
+    const float ox = a.rays_o[ray * 3], oy = a.rays_o[ray * 3 + 1], oz = a.rays_o[ray * 3 + 2];
+    const float dx = a.rays_d[ray * 3], dy = a.rays_d[ray * 3 + 1], dz = a.rays_d[ray * 3 + 2];
+    float t = a.near[ray];
+    const float far = a.far[ray];
+    const float dt = (far - t) / (float)IA_MAX_SAMPLES;  // raymarcher_acc.py:147
+    for (int i = 0; i < lane; i++) t += dt;
+    const long base = (long)ray * IA_MAX_SAMPLES;
+    for (int s = lane; s < IA_MAX_SAMPLES; s += 32) {  // empty slots: weight 0, raymarcher_acc.py:161-171
+        a.weights[base + s] = 0.f;
+        a.s_best[base + s] = -1;
+    }
+    int ray_count = 0;
+    for (;;) {
+        const bool act = t < far && ray_count < IA_MAX_SAMPLES;
+        if (!__any_sync(kFull, act)) break;
+        bool occ = false;
+        if (act) {  // occupancy test on the un-jittered position, raymarcher.cu:140-152
+            const float x = __fmaf_rn(t, dx, ox), y = __fmaf_rn(t, dy, oy), z = __fmaf_rn(t, dz, oz);
+            const int nx = (int)clampf((x - occ_min[0]) * occ_s[0], 0.0f, (float)G - 1.0f);
+            const int ny = (int)clampf((y - occ_min[1]) * occ_s[1], 0.0f, (float)G - 1.0f);
+            const int nz = (int)clampf((z - occ_min[2]) * occ_s[2], 0.0f, (float)G - 1.0f);
+            const int bit = (nx * G + ny) * G + nz;
+            occ = (__ldg(a.occ_bits + (bit >> 5)) >> (bit & 31)) & 1u;
+        }
+        const unsigned m = __ballot_sync(kFull, occ);
+        const int slot_s = ray_count + __popc(m & ((1u << lane) - 1u));
+        if (occ && slot_s < IA_MAX_SAMPLES) {
+            // raymarcher_acc.py:158-159: z = t + U*step ; pts = z * d + o  (separate mul/add as in torch)
+            const float jit = a.jitter ? a.jitter[base + slot_s] : 0.f;
+            const float z = t + jit * dt;
+            const long o = base + slot_s;
+            a.s_xc[o * 3] = z * dx + ox; a.s_xc[o * 3 + 1] = z * dy + oy; a.s_xc[o * 3 + 2] = z * dz + oz;
+            a.s_z[o] = z;
+        }
+        ray_count += __popc(m);
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) t += dt;
+        }
+    }
+    const int cnt = min(ray_count, IA_MAX_SAMPLES);
+    int first = 0;
+    if (lane == 0) {
+        a.s_count[ray] = cnt;
+        if (cnt > 0) first = atomicAdd(a.list_count, cnt);
+    }
+    first = __shfl_sync(kFull, first, 0);
+    for (int s = lane; s < cnt; s += 32) a.list[first + s] = (int)(base + s);
+}
+
+struct TrainCompositeArgs {
+    int n_rays;
+    const float* near; const float* far; const float* bg; const float* noise;
+    const float* s_sigma; const float* s_rgb; const float* s_z; const int* s_count;
+    float* rgb; float* depth; float* alpha; float* weights;
+};
+
+// one ray per thread, slots in order (raymarcher_acc.py:25-36, :166-180); loads staged 8 slots ahead of the recurrence
+__global__ void __launch_bounds__(128) train_composite_kernel(TrainCompositeArgs a) {
+    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= a.n_rays) return;
+    const int cnt = a.s_count[ray];
+    const float dt = (a.far[ray] - a.near[ray]) / (float)IA_MAX_SAMPLES;
+    const long base = (long)ray * IA_MAX_SAMPLES;
+    const float* __restrict__ p_sig = a.s_sigma + base;
+    const float* __restrict__ p_noise = a.noise ? a.noise + base : nullptr;
+    const float* __restrict__ p_rgb = a.s_rgb + base * 3;
+    const float* __restrict__ p_z = a.s_z + base;
+    float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Dp = 0.f, Wsum = 0.f;
+    constexpr int kB = 8;
+    for (int s0 = 0; s0 < cnt; s0 += kB) {
+        float sg[kB], c0[kB], c1[kB], c2[kB], zz[kB];
+#pragma unroll
+        for (int j = 0; j < kB; j++) {
+            const int s = min(s0 + j, cnt - 1);
+            sg[j] = p_sig[s];
+            if (p_noise) sg[j] = sg[j] + p_noise[s];
+            c0[j] = p_rgb[s * 3]; c1[j] = p_rgb[s * 3 + 1]; c2[j] = p_rgb[s * 3 + 2];
+            zz[j] = p_z[s];
+        }
+#pragma unroll
+        for (int j = 0; j < kB; j++) {
+            if (s0 + j < cnt) {
+                const float tau = fmaxf(sg[j], 0.f) * dt;
+                const float al = 1.0f - expf(-tau);
+                const float w = al * T;
+                a.weights[base + s0 + j] = w;
+                Cr += w * c0[j]; Cg += w * c1[j]; Cb += w * c2[j];
+                Dp += w * zz[j];
+                Wsum += w;
+                T = T * ((1.0f - al) + 1e-10f);
+            }
+        }
+    }
+    float b0 = 1.f, b1 = 1.f, b2 = 1.f;
+    if (a.bg) { b0 = a.bg[ray * 3]; b1 = a.bg[ray * 3 + 1]; b2 = a.bg[ray * 3 + 2]; }
+    a.rgb[ray * 3 + 0] = Cr + T * b0;
+    a.rgb[ray * 3 + 1] = Cg + T * b1;
+    a.rgb[ray * 3 + 2] = Cb + T * b2;
+    a.depth[ray] = Dp;
+    a.alpha[ray] = Wsum;
+}
+
+// ================================================================================================
 // compositing backward: per ray, upstream grads of (rgb, depth, alpha, weights) -> per-sample (d sigma, d rgb),
 // compacted into the sample list the network backward consumes
 // ================================================================================================
@@ -1240,6 +1373,9 @@ extern "C" int ia_pose_grad(const IaScene* scene, const float* lbs_voxel, const 
 
 // ================================================================================================
 int ia_train_rays_per_warp();  // ia_kernels.cu (ia_set_option)
+extern "C" int ia_internal_query_list(const IaScene* scene, const float* pts, const int* index, const int* n_dev, int capacity,
+                                      int eval_mode, float* rgb, float* sigma, float* xc_best, int8_t* best_init,
+                                      int* batch_counter, IaStats* stats, ia_stream_t stream);  // ia_kernels.cu
 
 extern "C" {
 
@@ -1278,6 +1414,43 @@ int ia_train_fwd(const IaScene* scene, const float* rays_o, const float* rays_d,
     if (kR == 4) train_fwd_kernel<kW, 4><<<grid, kW * 32, smem, st>>>(a);
     else if (kR == 1) train_fwd_kernel<kW, 1><<<grid, kW * 32, smem, st>>>(a);
     else train_fwd_kernel<kW, 2><<<grid, kW * 32, smem, st>>>(a);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    return IA_OK;
+}
+
+size_t ia_train_fwd_workspace_bytes(int n_rays) { return 256 + sizeof(int) * (size_t)max(n_rays, 0) * IA_MAX_SAMPLES; }
+
+int ia_train_fwd_split(const IaScene* scene, const float* rays_o, const float* rays_d, const float* near, const float* far,
+                       int n_rays, const float* bg, const float* jitter, const float* noise, float* rgb, float* depth,
+                       float* alpha, float* weights, float* s_sigma, float* s_rgb, float* s_xc, float* s_z, int* s_count,
+                       int8_t* s_best, void* workspace, size_t workspace_bytes, IaStats* stats, ia_stream_t stream) {
+    IA_REQUIRE(n_rays >= 0);
+    if (n_rays == 0) return IA_OK;
+    IA_REQUIRE(rays_o && rays_d && near && far && rgb && depth && alpha && weights && workspace);
+    IA_REQUIRE(s_sigma && s_rgb && s_xc && s_z && s_count && s_best);
+    IA_REQUIRE(workspace_bytes >= ia_train_fwd_workspace_bytes(n_rays));
+    IA_REQUIRE((long)n_rays * IA_MAX_SAMPLES < (1l << 31));
+    IA_REQUIRE(scene && scene->occ_bits && scene->occ_aabb && scene->G > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    int* counters = reinterpret_cast<int*>(workspace);  // [0] batch counter of the query, [1] number of samples
+    int* list = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + 256);
+    IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+    TrainMarchArgs m;
+    m.rays_o = rays_o; m.rays_d = rays_d; m.near = near; m.far = far; m.jitter = jitter;
+    m.occ_bits = reinterpret_cast<const uint32_t*>(scene->occ_bits); m.occ_aabb = scene->occ_aabb; m.G = scene->G;
+    m.n_rays = n_rays; m.weights = weights; m.s_xc = s_xc; m.s_z = s_z; m.s_count = s_count; m.s_best = s_best;
+    m.list = list; m.list_count = counters + 1;
+    train_march_kernel<<<(n_rays + 7) / 8, 256, 0, st>>>(m);
+    IA_CHECK_CUDA(cudaPeekAtLastError());
+    // the canonical point replaces the posed one in s_xc (a lane reads its point before it writes its outputs)
+    int rc = ia_internal_query_list(scene, s_xc, list, counters + 1, n_rays * IA_MAX_SAMPLES, /*eval_mode=*/0, s_rgb, s_sigma,
+                                    s_xc, s_best, counters, stats, stream);
+    if (rc) return rc;
+    TrainCompositeArgs c;
+    c.n_rays = n_rays; c.near = near; c.far = far; c.bg = bg; c.noise = noise;
+    c.s_sigma = s_sigma; c.s_rgb = s_rgb; c.s_z = s_z; c.s_count = s_count;
+    c.rgb = rgb; c.depth = depth; c.alpha = alpha; c.weights = weights;
+    train_composite_kernel<<<(n_rays + 127) / 128, 128, 0, st>>>(c);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

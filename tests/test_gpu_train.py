@@ -111,6 +111,41 @@ def test_train_fwd_matches_oracle(sc, dev):
     assert (ref["alpha"] > 0.5).sum() > 100
 
 
+def test_train_fwd_split_equals_fused_bit_for_bit(sc, dev):
+    """ia_train_fwd_split (march -> sample list -> point query -> compositing; the default) and the one-kernel ia_train_fwd
+    must agree in every output and every saved-for-backward value, for every tile shape of the fused kernel"""
+    import torch
+    from instantavatar_b200 import ops
+    scene, _ = dev
+    rays = patch_rays(sc, seed=4)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    o, d, near, far, jitter, noise, bg = rays
+    res = {}
+    try:
+        for name, split, trpw in (("split", 1, 2), ("fused2", 0, 2), ("fused1", 0, 1)):
+            ops.set_option("train_split", split); ops.set_option("train_rays_per_warp", trpw)
+            stats = ops.new_stats("cuda")
+            out, saved = ops.train_fwd(scene, t(o), t(d), t(near), t(far), t(bg), t(jitter), t(noise), stats)
+            torch.cuda.synchronize()
+            res[name] = (out, saved, ops.stats_dict(stats))
+    finally:
+        ops.set_option("train_split", 1); ops.set_option("train_rays_per_warp", 2)
+    out0, saved0, st0 = res["split"]
+    assert st0["samples"] > 1000
+    cnt = saved0["count"].long()
+    live = torch.arange(saved0["sigma"].shape[1], device="cuda")[None] < cnt[:, None]   # slots the forward filled
+    for name in ("fused2", "fused1"):
+        out1, saved1, st1 = res[name]
+        assert st1["samples"] == st0["samples"] and st1["net_evals"] == st0["net_evals"] and st1["field_loads"] == st0["field_loads"]
+        for k in out0:
+            assert torch.equal(out0[k], out1[k]), (name, k)
+        assert torch.equal(saved0["count"], saved1["count"]) and torch.equal(saved0["best"], saved1["best"])
+        for k in ("sigma", "z"):
+            assert torch.equal(saved0[k][live], saved1[k][live]), (name, k)
+        for k in ("rgb", "xc"):
+            assert torch.equal(saved0[k][live], saved1[k][live]), (name, k)
+
+
 def test_train_backward_matches_oracle(sc, dev):
     import torch
     from instantavatar_b200 import ops
