@@ -297,9 +297,13 @@ struct TrainCompositeArgs {
     float* rgb; float* depth; float* alpha; float* weights;
 };
 
-// one ray per thread, slots in order (raymarcher_acc.py:25-36, :166-180); loads staged 8 slots ahead of the recurrence
-__global__ void __launch_bounds__(128) train_composite_kernel(TrainCompositeArgs a) {
-    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per ray: 32 slots are loaded at once (coalesced) and their alphas computed in parallel; the transmittance and
+// the five sums then advance slot by slot in the fused kernel's order (operands broadcast by shuffle), so the results are
+// bit-identical.  (The first version, one thread per ray with 8-slot staging, cost 20 us at any ray count: a 256-slot ray
+// is 32 dependent load round trips.)
+__global__ void __launch_bounds__(256) train_composite_kernel(TrainCompositeArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ray >= a.n_rays) return;
     const int cnt = a.s_count[ray];
     const float dt = (a.far[ray] - a.near[ray]) / (float)IA_MAX_SAMPLES;
@@ -309,38 +313,40 @@ __global__ void __launch_bounds__(128) train_composite_kernel(TrainCompositeArgs
     const float* __restrict__ p_rgb = a.s_rgb + base * 3;
     const float* __restrict__ p_z = a.s_z + base;
     float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Dp = 0.f, Wsum = 0.f;
-    constexpr int kB = 8;
-    for (int s0 = 0; s0 < cnt; s0 += kB) {
-        float sg[kB], c0[kB], c1[kB], c2[kB], zz[kB];
-#pragma unroll
-        for (int j = 0; j < kB; j++) {
-            const int s = min(s0 + j, cnt - 1);
-            sg[j] = p_sig[s];
-            if (p_noise) sg[j] = sg[j] + p_noise[s];
-            c0[j] = p_rgb[s * 3]; c1[j] = p_rgb[s * 3 + 1]; c2[j] = p_rgb[s * 3 + 2];
-            zz[j] = p_z[s];
+    for (int s0 = 0; s0 < cnt; s0 += 32) {
+        const int s = s0 + lane;
+        const bool in = s < cnt;
+        float sg = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, zz = 0.f;
+        if (in) {
+            sg = p_sig[s];
+            if (p_noise) sg = sg + p_noise[s];
+            c0 = p_rgb[s * 3]; c1 = p_rgb[s * 3 + 1]; c2 = p_rgb[s * 3 + 2];
+            zz = p_z[s];
         }
-#pragma unroll
-        for (int j = 0; j < kB; j++) {
-            if (s0 + j < cnt) {
-                const float tau = fmaxf(sg[j], 0.f) * dt;
-                const float al = 1.0f - expf(-tau);
-                const float w = al * T;
-                a.weights[base + s0 + j] = w;
-                Cr += w * c0[j]; Cg += w * c1[j]; Cb += w * c2[j];
-                Dp += w * zz[j];
-                Wsum += w;
-                T = T * ((1.0f - al) + 1e-10f);
-            }
+        const float tau = fmaxf(sg, 0.f) * dt;
+        const float al = 1.0f - expf(-tau);
+        const float f = (1.0f - al) + 1e-10f;
+        const int m = min(32, cnt - s0);
+        float my_w = 0.f;
+        for (int j = 0; j < m; j++) {
+            const float w = __shfl_sync(kFull, al, j) * T;
+            if (j == lane) my_w = w;
+            Cr += w * __shfl_sync(kFull, c0, j); Cg += w * __shfl_sync(kFull, c1, j); Cb += w * __shfl_sync(kFull, c2, j);
+            Dp += w * __shfl_sync(kFull, zz, j);
+            Wsum += w;
+            T = T * __shfl_sync(kFull, f, j);
         }
+        if (in) a.weights[base + s] = my_w;
     }
-    float b0 = 1.f, b1 = 1.f, b2 = 1.f;
-    if (a.bg) { b0 = a.bg[ray * 3]; b1 = a.bg[ray * 3 + 1]; b2 = a.bg[ray * 3 + 2]; }
-    a.rgb[ray * 3 + 0] = Cr + T * b0;
-    a.rgb[ray * 3 + 1] = Cg + T * b1;
-    a.rgb[ray * 3 + 2] = Cb + T * b2;
-    a.depth[ray] = Dp;
-    a.alpha[ray] = Wsum;
+    if (lane == 0) {
+        float b0 = 1.f, b1 = 1.f, b2 = 1.f;
+        if (a.bg) { b0 = a.bg[ray * 3]; b1 = a.bg[ray * 3 + 1]; b2 = a.bg[ray * 3 + 2]; }
+        a.rgb[ray * 3 + 0] = Cr + T * b0;
+        a.rgb[ray * 3 + 1] = Cg + T * b1;
+        a.rgb[ray * 3 + 2] = Cb + T * b2;
+        a.depth[ray] = Dp;
+        a.alpha[ray] = Wsum;
+    }
 }
 
 // ================================================================================================
@@ -356,10 +362,14 @@ struct CompBwdArgs {
     const float* rays_o; const float* rays_d; float* l_xd; int8_t* l_best;  // optional (pose gradients): posed point + init id
 };
 
-// One ray per thread, but the per-slot loads are staged 8 slots at a time into registers ahead of the serial
-// transmittance recurrence (the first version was bound by one dependent global-load latency per slot).
-__global__ void __launch_bounds__(128) composite_bwd_kernel(CompBwdArgs a) {
-    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per ray: 32 slots are loaded at once (coalesced) and everything that does not depend on the transmittance
+// recurrence (exp, alpha, the upstream dot products) is computed in parallel; the recurrence itself runs slot by slot in the
+// original order with operands broadcast by shuffle, each lane keeping the values of its own slot.  (The thread-per-ray
+// version took ~50 us at any ray count: a 256-slot ray is 2 x 32 dependent load round trips.)  Same list layout as before:
+// a ray's samples occupy one contiguous block in slot order.
+__global__ void __launch_bounds__(256) composite_bwd_kernel(CompBwdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ray >= a.n_rays) return;
     const int cnt = a.s_count[ray];
     if (cnt == 0) return;
@@ -378,72 +388,72 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(CompBwdArgs a) {
     if (a.g_alpha) ga = a.g_alpha[ray];
     float b[3] = {1.f, 1.f, 1.f};
     if (a.bg) { b[0] = a.bg[ray * 3]; b[1] = a.bg[ray * 3 + 1]; b[2] = a.bg[ray * 3 + 2]; }
-    constexpr int kB = 8;
     // ---- forward sweep: T after the last sample, number of samples that reached the network ----
     float T = 1.f;
     int nvalid = 0;
-    for (int s0 = 0; s0 < cnt; s0 += kB) {
-        float sg[kB]; int bs[kB];
-#pragma unroll
-        for (int j = 0; j < kB; j++) {
-            const int s = min(s0 + j, cnt - 1);
-            sg[j] = p_sig[s] + (p_noise ? p_noise[s] : 0.f);
-            bs[j] = p_best[s];
-        }
-#pragma unroll
-        for (int j = 0; j < kB; j++) {
-            if (s0 + j < cnt) {
-                const float al = 1.0f - expf(-fmaxf(sg[j], 0.f) * dt);
-                T = T * ((1.0f - al) + 1e-10f);
-                nvalid += bs[j] >= 0 ? 1 : 0;
-            }
-        }
+    for (int s0 = 0; s0 < cnt; s0 += 32) {
+        const int s = s0 + lane;
+        const bool in = s < cnt;
+        float sg = 0.f;
+        int bs = -1;
+        if (in) { sg = p_sig[s] + (p_noise ? p_noise[s] : 0.f); bs = p_best[s]; }
+        const float al = 1.0f - expf(-fmaxf(sg, 0.f) * dt);
+        const float f = (1.0f - al) + 1e-10f;
+        nvalid += __popc(__ballot_sync(kFull, in && bs >= 0));
+        const int m = min(32, cnt - s0);
+        for (int j = 0; j < m; j++) T = T * __shfl_sync(kFull, f, j);
     }
     if (nvalid == 0) return;
-    int pos = atomicAdd(a.l_count, nvalid) + nvalid;  // fill this ray's block back to front
+    int start = 0;
+    if (lane == 0) start = atomicAdd(a.l_count, nvalid);
+    start = __shfl_sync(kFull, start, 0);
     float S = gc[0] * b[0] + gc[1] * b[1] + gc[2] * b[2];  // dL/dT entering the next sample; starts at the background term
     float Tn = T;                                          // T after sample s
-    for (int s1 = cnt - 1; s1 >= 0; s1 -= kB) {
-        float sg[kB], c0[kB], c1[kB], c2[kB], zz[kB], gw[kB]; int bs[kB];
-#pragma unroll
-        for (int j = 0; j < kB; j++) {
-            const int s = max(s1 - j, 0);
-            sg[j] = p_sig[s] + (p_noise ? p_noise[s] : 0.f);
-            bs[j] = p_best[s];
-            c0[j] = p_rgb[s * 3]; c1[j] = p_rgb[s * 3 + 1]; c2[j] = p_rgb[s * 3 + 2];
-            zz[j] = p_z[s];
-            gw[j] = p_gw ? p_gw[s] : 0.f;
+    int above = 0;                                         // valid samples in the groups already processed (higher slots)
+    for (int s0 = ((cnt - 1) / 32) * 32; s0 >= 0; s0 -= 32) {
+        const int s = s0 + lane;
+        const bool in = s < cnt;
+        float sig = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, zz = 0.f, gw = 0.f;
+        int bs = -1;
+        if (in) {
+            sig = p_sig[s] + (p_noise ? p_noise[s] : 0.f);
+            bs = p_best[s];
+            c0 = p_rgb[s * 3]; c1 = p_rgb[s * 3 + 1]; c2 = p_rgb[s * 3 + 2];
+            zz = p_z[s];
+            gw = p_gw ? p_gw[s] : 0.f;
         }
-#pragma unroll
-        for (int j = 0; j < kB; j++) {
-            const int s = s1 - j;
-            if (s < 0) break;
-            const float sig = sg[j];
-            const float e = expf(-fmaxf(sig, 0.f) * dt);
-            const float al = 1.0f - e;
-            const float f = (1.0f - al) + 1e-10f;
-            const float Tb = Tn / f;  // T before sample s
-            const float Gs = gc[0] * c0[j] + gc[1] * c1[j] + gc[2] * c2[j] + gd * zz[j] + ga + gw[j];
+        const float e = expf(-fmaxf(sig, 0.f) * dt);
+        const float al = 1.0f - e;
+        const float f = (1.0f - al) + 1e-10f;
+        const float Gs = gc[0] * c0 + gc[1] * c1 + gc[2] * c2 + gd * zz + ga + gw;
+        const int m = min(32, cnt - s0);
+        float my_Tb = 0.f, my_dLdal = 0.f;
+        for (int j = m - 1; j >= 0; j--) {
+            const float fj = __shfl_sync(kFull, f, j), Gj = __shfl_sync(kFull, Gs, j), aj = __shfl_sync(kFull, al, j);
+            const float Tb = Tn / fj;  // T before sample j
             const float dLdf = S * Tb;
-            const float dLdal = Gs * Tb - dLdf;
-            S = S * f + Gs * al;
+            const float dLdal = Gj * Tb - dLdf;
+            S = S * fj + Gj * aj;
             Tn = Tb;
-            if (bs[j] >= 0) {
-                const float dsig = sig > 0.f ? dLdal * e * dt : 0.f;  // d alpha / d sigma = exp(-tau) * dt through the relu
-                const float w = al * Tb;
-                pos--;
-                a.l_xc[pos * 3] = p_xc[s * 3]; a.l_xc[pos * 3 + 1] = p_xc[s * 3 + 1]; a.l_xc[pos * 3 + 2] = p_xc[s * 3 + 2];
-                a.l_dsigma[pos] = dsig;
-                a.l_drgb[pos * 3] = w * gc[0]; a.l_drgb[pos * 3 + 1] = w * gc[1]; a.l_drgb[pos * 3 + 2] = w * gc[2];
-                if (a.l_xd) {  // posed sample position exactly as the forward generated it (z * d + o, separate mul/add)
-                    const float z = zz[j];
-                    a.l_xd[pos * 3] = z * a.rays_d[ray * 3] + a.rays_o[ray * 3];
-                    a.l_xd[pos * 3 + 1] = z * a.rays_d[ray * 3 + 1] + a.rays_o[ray * 3 + 1];
-                    a.l_xd[pos * 3 + 2] = z * a.rays_d[ray * 3 + 2] + a.rays_o[ray * 3 + 2];
-                    a.l_best[pos] = (int8_t)bs[j];
-                }
+            if (j == lane) { my_Tb = Tb; my_dLdal = dLdal; }
+        }
+        const bool valid = in && bs >= 0;
+        const unsigned vm = __ballot_sync(kFull, valid);
+        if (valid) {
+            const int pos = start + nvalid - above - __popc(vm) + __popc(vm & ((1u << lane) - 1u));
+            const float dsig = sig > 0.f ? my_dLdal * e * dt : 0.f;  // d alpha / d sigma = exp(-tau) * dt through the relu
+            const float w = al * my_Tb;
+            a.l_xc[pos * 3] = p_xc[s * 3]; a.l_xc[pos * 3 + 1] = p_xc[s * 3 + 1]; a.l_xc[pos * 3 + 2] = p_xc[s * 3 + 2];
+            a.l_dsigma[pos] = dsig;
+            a.l_drgb[pos * 3] = w * gc[0]; a.l_drgb[pos * 3 + 1] = w * gc[1]; a.l_drgb[pos * 3 + 2] = w * gc[2];
+            if (a.l_xd) {  // posed sample position exactly as the forward generated it (z * d + o, separate mul/add)
+                a.l_xd[pos * 3] = zz * a.rays_d[ray * 3] + a.rays_o[ray * 3];
+                a.l_xd[pos * 3 + 1] = zz * a.rays_d[ray * 3 + 1] + a.rays_o[ray * 3 + 1];
+                a.l_xd[pos * 3 + 2] = zz * a.rays_d[ray * 3 + 2] + a.rays_o[ray * 3 + 2];
+                a.l_best[pos] = (int8_t)bs;
             }
         }
+        above += __popc(vm);
     }
 }
 
@@ -1450,7 +1460,7 @@ int ia_train_fwd_split(const IaScene* scene, const float* rays_o, const float* r
     c.n_rays = n_rays; c.near = near; c.far = far; c.bg = bg; c.noise = noise;
     c.s_sigma = s_sigma; c.s_rgb = s_rgb; c.s_z = s_z; c.s_count = s_count;
     c.rgb = rgb; c.depth = depth; c.alpha = alpha; c.weights = weights;
-    train_composite_kernel<<<(n_rays + 127) / 128, 128, 0, st>>>(c);
+    train_composite_kernel<<<(n_rays + 7) / 8, 256, 0, st>>>(c);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }
@@ -1470,7 +1480,7 @@ int ia_composite_bwd(int n_rays, const float* near, const float* far, const floa
     a.g_rgb = g_rgb; a.g_depth = g_depth; a.g_alpha = g_alpha; a.g_weights = g_weights;
     a.l_xc = l_xc; a.l_dsigma = l_dsigma; a.l_drgb = l_drgb; a.l_count = l_count;
     a.rays_o = rays_o; a.rays_d = rays_d; a.l_xd = l_xd; a.l_best = l_best;
-    composite_bwd_kernel<<<(n_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    composite_bwd_kernel<<<(n_rays + 7) / 8, 256, 0, (cudaStream_t)stream>>>(a);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }

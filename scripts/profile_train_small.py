@@ -12,9 +12,11 @@ from instantavatar_b200 import ops  # noqa: E402
 
 n_rays = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 trpw = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+split = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dev = torch.device("cuda", 0)
 model, hb, batch = bench.build_model(dev, 0)
 ops.set_option("train_rays_per_warp", trpw)
+ops.set_option("train_split", split)
 rgb, _, alpha, _ = model.render_image_fast(dict(batch), (bench.H, bench.W))
 rgb, alpha = rgb.reshape(-1, 3), alpha.reshape(-1)
 idx = torch.cat([((torch.arange(y0, y0 + 32))[:, None] * bench.W + torch.arange(x0, x0 + 32)[None]).reshape(-1)
@@ -35,4 +37,4 @@ model.training_step(b)   # step 2005: no grid refresh
 ev1.record()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print("rays", n, "train_rays_per_warp", trpw, "eager step ms", ev0.elapsed_time(ev1))
+print("rays", n, "train_rays_per_warp", trpw, "split", split, "eager step ms", ev0.elapsed_time(ev1))
