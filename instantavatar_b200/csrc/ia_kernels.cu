@@ -12,6 +12,7 @@ static int g_render_rays = 4;  // rays per warp (32 / 16 / 8 / 4), tunable throu
 static int g_render_plan = 1;  // longest-first tile scheduling (needs the large workspace)
 static int g_query_warps = 12;   // same for the point-query kernel (12 / 16 / 20; 16 and 20 only without xc output)
 static int g_train_rays = 2;   // rays per warp of the training forward (4 / 2 / 1)
+static int g_query_lanes = 0;  // lanes per point of the list-mode point query (split training forward): 0 = auto, 1 / 2 / 4
 int ia_train_rays_per_warp() { return g_train_rays; }
 
 #include "ia_host.h"
@@ -396,6 +397,7 @@ struct QueryArgs {
     // point mode, optional (split training forward, ia_train.cu): the number of points lives on the device (n = capacity)
     // and point p reads pts / writes every output at element index[p] instead of p
     const int* n_dev; const int* index;
+    int lanes_per_sample;  // point mode: 1 / 2 / 4 lanes share a point's 13 root finds (narrow batches); 0 = pick from the load
 };
 
 template <int kWarps, bool kKeepXc>
@@ -432,7 +434,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
     const int cells_per_batch = a.grid_aabb ? 32 / a.passes : 32;
     const int n3g = a.G * a.G * a.G;
     const int n_pts = a.n_dev ? min(*a.n_dev, a.n) : a.n;
-    const int n_batches = a.grid_aabb ? (n3g + cells_per_batch - 1) / cells_per_batch : (n_pts + 31) / 32;
+    // point mode: with few points per resident warp a batch's latency (13 serial root finds per lane) is the kernel's time;
+    // k lanes per point divide it (warp_eval_samples) at no extra memory traffic
+    int k = 1;
+    if (kKeepXc && !a.grid_aabb) {   // (the occupancy-pass instantiation keeps the one-lane-per-point code, k is a literal 1 there)
+        k = a.lanes_per_sample;
+        if (k == 0) {
+            const int n_warps = gridDim.x * kWarps, n32 = (n_pts + 31) / 32;
+            k = n32 <= n_warps ? 4 : (n32 <= 2 * n_warps ? 2 : 1);
+        }
+    }
+    const int spw = 32 / k;  // points per warp batch
+    const int n_batches = a.grid_aabb ? (n3g + cells_per_batch - 1) / cells_per_batch : (n_pts + spw - 1) / spw;
     for (int lidx = blockIdx.x * kWarps + warp;; lidx += gridDim.x * kWarps) {
         if (a.batch_counter) {  // dynamic: batches near the body cost several times more than empty space
             int nb = 0;
@@ -446,8 +459,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
         }
         if (bidx >= n_batches || bidx < 0) break;
         const long long t_start = a.batch_cost ? clock64() : 0;
-        int p = bidx * 32 + lane;
+        int p = bidx * spw + (lane & (spw - 1));
         bool act = p < n_pts;
+        const bool owner = lane < spw;  // helper lanes (k > 1) evaluate some of their point's root finds, nothing else
         long q = p;  // element the point is read from / written to
         if (act && a.index) q = a.index[p];
         float x = 0, y = 0, z = 0;
@@ -473,7 +487,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
             }
         }
         SampleOut so;
-        warp_eval_samples<kKeepXc>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots, st_load, st_hash);
+        if constexpr (kKeepXc) {
+            warp_eval_samples<kKeepXc>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots, st_load, st_hash, k);
+        } else {
+            warp_eval_samples<kKeepXc>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots, st_load, st_hash);
+        }
+        act = act && owner;
         st_samples += act ? 1u : 0u;
         if (act && a.grid_aabb) {
             if (so.sigma > 0.f) {
@@ -861,6 +880,11 @@ int ia_set_option(const char* name, int value) {
         g_query_warps = value;
         return IA_OK;
     }
+    if (!strcmp(name, "query_lanes_per_sample")) {
+        IA_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4);
+        g_query_lanes = value;
+        return IA_OK;
+    }
     if (!strcmp(name, "train_rays_per_warp")) {
         IA_REQUIRE(value == 4 || value == 2 || value == 1);
         g_train_rays = value;
@@ -1056,7 +1080,7 @@ int ia_deform_query(const IaScene* scene, const float* pts, int n, int eval_mode
     a.batch_counter = nullptr; a.batch_first = 0; a.batch_stride = 1;
     a.peer_density = nullptr; a.n_peers = 0;
     a.batch_order = nullptr; a.n_order = 0; a.batch_cost = nullptr;
-    a.n_dev = nullptr; a.index = nullptr;
+    a.n_dev = nullptr; a.index = nullptr; a.lanes_per_sample = 1;
     return launch_query(a, (cudaStream_t)stream);
 }
 
@@ -1077,7 +1101,7 @@ __attribute__((visibility("hidden"))) int ia_internal_query_list(const IaScene* 
     a.batch_counter = batch_counter; a.batch_first = 0; a.batch_stride = 1;
     a.peer_density = nullptr; a.n_peers = 0;
     a.batch_order = nullptr; a.n_order = 0; a.batch_cost = nullptr;
-    a.n_dev = n_dev; a.index = index;
+    a.n_dev = n_dev; a.index = index; a.lanes_per_sample = g_query_lanes;
     return launch_query(a, (cudaStream_t)stream);
 }
 
@@ -1097,7 +1121,7 @@ static int occupancy_query_impl(const IaScene* scene, const float* jitter, const
     a.batch_first = shard; a.batch_stride = n_shards;
     a.peer_density = peer_density; a.n_peers = n_peers;
     a.batch_order = batch_order; a.n_order = n_order; a.batch_cost = batch_cost;
-    a.n_dev = nullptr; a.index = nullptr;
+    a.n_dev = nullptr; a.index = nullptr; a.lanes_per_sample = 1;
     IA_REQUIRE(!batch_order || (workspace && n_order >= 0));
     if (workspace) IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream));
     // peer mode: every rank's buffer is written by all ranks -- the CALLER zeroes it (before the barrier that precedes this launch)

@@ -57,23 +57,35 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
 template <bool kKeepXc>
 __device__ __forceinline__ void warp_eval_samples(const EvalCtx& ctx, WarpScratch<kKeepXc>& ws, bool active, float xd0,
                                                   float xd1, float xd2, bool eval_mode, int lane, SampleOut& out,
-                                                  unsigned& ngather, unsigned& nroots, unsigned& nload, unsigned& nhash) {
+                                                  unsigned& ngather, unsigned& nroots, unsigned& nload, unsigned& nhash,
+                                                  const int lanes_per_sample = 1) {
     const FrameConst& fc = *ctx.fc;
     // ---- 1. Broyden from the 13 bone initialisations ------------------------------------------------
+    // lanes_per_sample k in {1, 2, 4}: the warp holds 32/k samples (lanes 0 .. 32/k-1 own them, lane l + j*32/k helps
+    // sample l and must be given the same point and `active`); the 13 solves of a sample are dealt round-robin to its k
+    // lanes, which divides the latency of this step -- the critical path of a batch -- by up to k.  Everything after
+    // this step runs on the owner lanes only; results do not depend on k (every solve is independent).
+    const int spw = 32 / lanes_per_sample;          // samples per warp
+    const int sl0 = lane & (spw - 1), sub = lane / spw;
     unsigned vmask = 0;
 #pragma unroll 1
-    for (int b = 0; b < kNumInit; b++) {
+    for (int b = sub; b < kNumInit; b += lanes_per_sample) {
         if (active) {
             float x[3];
             int ng = 0;
             const bool ok = broyden_solve(ctx.field, fc.bp, fc.Tb[b], xd0, xd1, xd2, x, nullptr, ng);
             ngather += ng & 0xffff;
             nload += (unsigned)ng >> 16;
-            ws.cand[0][b][lane] = x[0];
-            ws.cand[1][b][lane] = x[1];
-            ws.cand[2][b][lane] = x[2];
+            ws.cand[0][b][sl0] = x[0];
+            ws.cand[1][b][sl0] = x[1];
+            ws.cand[2][b][sl0] = x[2];
             if (ok) vmask |= 1u << b;
         }
+    }
+    if (lanes_per_sample > 1) {
+        for (int o = spw; o < 32; o <<= 1) vmask |= __shfl_xor_sync(kFull, vmask, o);
+        if (sub) vmask = 0;   // helper lanes contribute no roots and produce no output
+        __syncwarp();
     }
     // ---- 2. duplicate filter (filter.cu:25-52): drop root i if a later valid root is within 1e-4 ------
     unsigned kept = vmask;

@@ -122,19 +122,21 @@ def test_train_fwd_split_equals_fused_bit_for_bit(sc, dev):
     o, d, near, far, jitter, noise, bg = rays
     res = {}
     try:
-        for name, split, trpw in (("split", 1, 2), ("fused2", 0, 2), ("fused1", 0, 1)):
+        for name, split, trpw, k in (("split", 1, 2, 1), ("split_k2", 1, 2, 2), ("split_k4", 1, 2, 4), ("split_auto", 1, 2, 0),
+                                     ("fused2", 0, 2, 0), ("fused1", 0, 1, 0)):
             ops.set_option("train_split", split); ops.set_option("train_rays_per_warp", trpw)
+            ops.set_option("query_lanes_per_sample", k)   # lanes sharing a sample's 13 root finds in the split form's query
             stats = ops.new_stats("cuda")
             out, saved = ops.train_fwd(scene, t(o), t(d), t(near), t(far), t(bg), t(jitter), t(noise), stats)
             torch.cuda.synchronize()
             res[name] = (out, saved, ops.stats_dict(stats))
     finally:
-        ops.set_option("train_split", 1); ops.set_option("train_rays_per_warp", 2)
+        ops.set_option("train_split", 1); ops.set_option("train_rays_per_warp", 2); ops.set_option("query_lanes_per_sample", 0)
     out0, saved0, st0 = res["split"]
     assert st0["samples"] > 1000
     cnt = saved0["count"].long()
     live = torch.arange(saved0["sigma"].shape[1], device="cuda")[None] < cnt[:, None]   # slots the forward filled
-    for name in ("fused2", "fused1"):
+    for name in ("split_k2", "split_k4", "split_auto", "fused2", "fused1"):
         out1, saved1, st1 = res[name]
         assert st1["samples"] == st0["samples"] and st1["net_evals"] == st0["net_evals"] and st1["field_loads"] == st0["field_loads"]
         for k in out0:
