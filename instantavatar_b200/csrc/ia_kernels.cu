@@ -13,6 +13,7 @@ static int g_render_plan = 1;  // longest-first tile scheduling (needs the large
 static int g_query_warps = 12;   // same for the point-query kernel (12 / 16 / 20; 16 and 20 only without xc output)
 static int g_train_rays = 2;   // rays per warp of the training forward (4 / 2 / 1)
 static int g_query_lanes = 0;  // lanes per point of the list-mode point query (split training forward): 0 = auto, 1 / 2 / 4
+static int g_occ_lanes = 0;    // lanes per point of the occupancy passes: 0 = 2 when a launch covers <= 1/4 of the grid, else 1
 int ia_train_rays_per_warp() { return g_train_rays; }
 
 #include "ia_host.h"
@@ -410,7 +411,9 @@ struct QuerySmem {
 
 // kKeepXc: the canonical point of the winning candidate is an output (xc_best; training-time queries); the occupancy
 // passes do not need it, which frees 5 KB of shared memory per warp => more resident warps per SM
-template <int kWarps, bool kKeepXc>
+// kDynLanes: lanes per point chosen at run time (a.lanes_per_sample); the default occupancy-pass instantiation keeps the
+// one-lane-per-point code with a literal 1
+template <int kWarps, bool kKeepXc, bool kDynLanes = kKeepXc>
 __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __grid_constant__ QueryArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     QuerySmem<kWarps, kKeepXc>& sm = *reinterpret_cast<QuerySmem<kWarps, kKeepXc>*>(smem_raw);
@@ -431,20 +434,20 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
     unsigned st_gather = 0, st_roots = 0, st_samples = 0, st_load = 0, st_hash = 0;
     // grid mode: a batch holds all jitter passes of 32/passes neighbouring cells, so that the 32 lanes stay within a
     // few voxels of the skinning field (L1 wavefronts, not DRAM, bound this kernel)
-    const int cells_per_batch = a.grid_aabb ? 32 / a.passes : 32;
     const int n3g = a.G * a.G * a.G;
     const int n_pts = a.n_dev ? min(*a.n_dev, a.n) : a.n;
-    // point mode: with few points per resident warp a batch's latency (13 serial root finds per lane) is the kernel's time;
-    // k lanes per point divide it (warp_eval_samples) at no extra memory traffic
+    // with few points per resident warp a batch's latency (13 serial root finds per lane) is the kernel's time; k lanes per
+    // point divide it (warp_eval_samples) at no extra memory traffic.  Point mode, k = 0: about one batch per warp.
     int k = 1;
-    if (kKeepXc && !a.grid_aabb) {   // (the occupancy-pass instantiation keeps the one-lane-per-point code, k is a literal 1 there)
+    if (kDynLanes) {
         k = a.lanes_per_sample;
         if (k == 0) {
             const int n_warps = gridDim.x * kWarps, n32 = (n_pts + 31) / 32;
-            k = n32 <= n_warps ? 4 : (n32 <= 2 * n_warps ? 2 : 1);
+            k = 4 * n32 * 4 <= 5 * n_warps ? 4 : (4 * n32 * 2 <= 5 * n_warps ? 2 : 1);
         }
     }
     const int spw = 32 / k;  // points per warp batch
+    const int cells_per_batch = a.grid_aabb ? spw / a.passes : spw;
     const int n_batches = a.grid_aabb ? (n3g + cells_per_batch - 1) / cells_per_batch : (n_pts + spw - 1) / spw;
     for (int lidx = blockIdx.x * kWarps + warp;; lidx += gridDim.x * kWarps) {
         if (a.batch_counter) {  // dynamic: batches near the body cost several times more than empty space
@@ -467,9 +470,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
         float x = 0, y = 0, z = 0;
         int cell = 0;
         if (a.grid_aabb) {
-            cell = bidx * cells_per_batch + lane / a.passes;
-            const int pass = lane % a.passes;
-            act = lane < cells_per_batch * a.passes && cell < n3g;
+            const int pl = lane & (spw - 1);  // point slot inside the batch (helper lanes repeat their owner's)
+            cell = bidx * cells_per_batch + pl / a.passes;
+            const int pass = pl % a.passes;
+            act = pl < cells_per_batch * a.passes && cell < n3g;
             p = pass * n3g + cell;
         }
         if (act) {
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deform_query_kernel(const __gr
             }
         }
         SampleOut so;
-        if constexpr (kKeepXc) {
+        if constexpr (kDynLanes) {
             warp_eval_samples<kKeepXc>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots, st_load, st_hash, k);
         } else {
             warp_eval_samples<kKeepXc>(ctx, sm.ws[warp], act, x, y, z, a.eval_mode != 0, lane, so, st_gather, st_roots, st_load, st_hash);
@@ -880,6 +884,11 @@ int ia_set_option(const char* name, int value) {
         g_query_warps = value;
         return IA_OK;
     }
+    if (!strcmp(name, "occupancy_lanes_per_point")) {
+        IA_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4);
+        g_occ_lanes = value;
+        return IA_OK;
+    }
     if (!strcmp(name, "query_lanes_per_sample")) {
         IA_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4);
         g_query_lanes = value;
@@ -983,25 +992,26 @@ static int launch_render(RenderArgs& a, bool plan, int* ws_cost, int* ws_order, 
     return IA_OK;
 }
 
-template <int kWarps, bool kKeepXc>
+template <int kWarps, bool kKeepXc, bool kDynLanes = kKeepXc>
 static int launch_query_t(QueryArgs& a, cudaStream_t stream) {
     const size_t smem = sizeof(QuerySmem<kWarps, kKeepXc>);
     static PerDeviceFlag attr_set;
     if (!attr_set.get()) {
-        IA_CHECK_CUDA(cudaFuncSetAttribute(deform_query_kernel<kWarps, kKeepXc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(deform_query_kernel<kWarps, kKeepXc, kDynLanes>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set.set();
     }
     const int n_batches = a.grid_aabb ? (a.G * a.G * a.G + (32 / a.passes) - 1) / (32 / a.passes) : (a.n + 31) / 32;
     int grid = sm_count();
     if (grid <= 0) return set_err(IA_ECUDA, "no CUDA device%s");
     grid = min(grid, (n_batches + kWarps - 1) / kWarps);
-    deform_query_kernel<kWarps, kKeepXc><<<grid, kWarps * 32, smem, stream>>>(a);
+    deform_query_kernel<kWarps, kKeepXc, kDynLanes><<<grid, kWarps * 32, smem, stream>>>(a);
     IA_CHECK_CUDA(cudaPeekAtLastError());
     return IA_OK;
 }
 
 static int launch_query(QueryArgs& a, cudaStream_t stream) {
     if (a.xc_best) return launch_query_t<12, true>(a, stream);
+    if (a.grid_aabb && a.lanes_per_sample > 1) return launch_query_t<12, false, true>(a, stream);  // narrow occupancy batches
     switch (g_query_warps) {
         case 20: return launch_query_t<20, false>(a, stream);
         case 16: return launch_query_t<16, false>(a, stream);
@@ -1121,7 +1131,12 @@ static int occupancy_query_impl(const IaScene* scene, const float* jitter, const
     a.batch_first = shard; a.batch_stride = n_shards;
     a.peer_density = peer_density; a.n_peers = n_peers;
     a.batch_order = batch_order; a.n_order = n_order; a.batch_cost = batch_cost;
-    a.n_dev = nullptr; a.index = nullptr; a.lanes_per_sample = 1;
+    a.n_dev = nullptr; a.index = nullptr;
+    // a shard of 1/4 of the grid or less leaves a warp only a handful of batches, and the slowest batch (0.25 ms) is then
+    // longer than the shard's ideal time: two lanes per point halve it (the batch list / cost interface keeps the
+    // 32/passes-cell batches it is defined on)
+    a.lanes_per_sample = g_occ_lanes ? g_occ_lanes : ((n_shards >= 4 && !batch_order && !batch_cost && 2 * passes <= 16) ? 2 : 1);
+    if (batch_order || batch_cost || 32 / a.lanes_per_sample < passes) a.lanes_per_sample = 1;
     IA_REQUIRE(!batch_order || (workspace && n_order >= 0));
     if (workspace) IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream));
     // peer mode: every rank's buffer is written by all ranks -- the CALLER zeroes it (before the barrier that precedes this launch)

@@ -162,7 +162,7 @@ def gather_ceiling(field: torch.Tensor, iters: int = 200, warps: int = 12, coher
 
 # the library's tuning knobs (ia_set_option) and their defaults, mirrored here so that a caller can change one temporarily
 _OPTIONS = {"render_rays_per_warp": 4, "render_plan": 1, "render_warps": 12, "query_warps": 12, "train_rays_per_warp": 2,
-            "train_split": 1, "query_lanes_per_sample": 0}
+            "train_split": 1, "query_lanes_per_sample": 0, "occupancy_lanes_per_point": 0}
 _train_ws: dict = {}
 
 

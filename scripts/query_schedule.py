@@ -78,12 +78,20 @@ print(json.dumps({"batches": nb, "sm_mhz_assumed": clk_mhz, "full_query_ms": ful
                   "corr_prev_frame_cost": float(np.corrcoef(c, cp)[0, 1]),
                   "share_of_cycles_in_top_10pct_batches": float(np.sort(c)[::-1][: nb // 10].sum() / c.sum())}), flush=True)
 
-for world in (2, 4, 8):
-    rows = {"natural": [], "lpt_same_frame": [], "lpt_prev_frame": []}
+for world in (1, 2, 4, 8):
+    rows = {"natural": [], "lpt_same_frame": [], "lpt_prev_frame": [], "two_lanes_per_point": [], "four_lanes_per_point": []}
     dens = torch.zeros_like(ref)
+    dens_k = {2: torch.zeros_like(ref), 4: torch.zeros_like(ref)}
     for r in range(world):
         mine = torch.arange(r, nb, world, device=dev, dtype=torch.int64)
+        ops.set_option("occupancy_lanes_per_point", 1)
         rows["natural"].append(timed(lambda: ops.occupancy_query(scene, jit, aabb6, shard=(r, world))))
+        # narrow batches: 2 / 4 lanes share a point's 13 root finds (batch latency / 2, / 3.25)
+        for k, name in ((2, "two_lanes_per_point"), (4, "four_lanes_per_point")):
+            ops.set_option("occupancy_lanes_per_point", k)
+            dens_k[k] = torch.maximum(dens_k[k], ops.occupancy_query(scene, jit, aabb6, shard=(r, world)))
+            rows[name].append(timed(lambda: ops.occupancy_query(scene, jit, aabb6, shard=(r, world))))
+        ops.set_option("occupancy_lanes_per_point", 1)
         for name, cc in (("lpt_same_frame", cost), ("lpt_prev_frame", cost_prev)):
             order = mine[torch.argsort(cc[mine], descending=True, stable=True)].to(torch.int32).contiguous()
             d = ops.occupancy_query(scene, jit, aabb6, order=order)
@@ -91,6 +99,7 @@ for world in (2, 4, 8):
                 dens = torch.maximum(dens, d)
             rows[name].append(timed(lambda: ops.occupancy_query(scene, jit, aabb6, order=order)))
     assert torch.equal(dens, ref), "ordered shards do not reproduce the full grid"
+    assert torch.equal(dens_k[2], ref) and torch.equal(dens_k[4], ref), "narrow batches do not reproduce the full grid"
     print(json.dumps({"n_shards": world, "ideal_ms": full_ms / world,
                       **{k + "_ms_max_over_shards": max(v) for k, v in rows.items()},
                       **{k + "_ms_mean": float(np.mean(v)) for k, v in rows.items()}}), flush=True)

@@ -281,3 +281,18 @@ def test_occupancy_query_shards_and_explicit_order_reproduce_the_grid(sc, dev):
         acc = torch.maximum(acc, ops.occupancy_query(scene, jit, aabb, order=part.contiguous()))
     assert torch.equal(acc, full)
     assert torch.equal(ops.occupancy_query(scene, jit, aabb, order=by_cost.contiguous()), full)
+    # narrow batches (2 / 4 lanes share a point's 13 root finds; the default for shards of <= 1/4 of the grid)
+    try:
+        for k in (2, 4):
+            ops.set_option("occupancy_lanes_per_point", k)
+            assert torch.equal(ops.occupancy_query(scene, jit, aabb), full), k
+            acc = torch.zeros_like(full)
+            for r in range(4):
+                acc = torch.maximum(acc, ops.occupancy_query(scene, jit, aabb, shard=(r, 4)))
+            assert torch.equal(acc, full), k
+    finally:
+        ops.set_option("occupancy_lanes_per_point", 0)
+    acc = torch.zeros_like(full)
+    for r in range(4):   # default policy at 4 shards
+        acc = torch.maximum(acc, ops.occupancy_query(scene, jit, aabb, shard=(r, 4)))
+    assert torch.equal(acc, full)
