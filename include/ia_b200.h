@@ -68,7 +68,7 @@ int ia_sm_count(void);
 /* tuning knobs (do not change results): "render_rays_per_warp" in {32,16,8,4,2,1}, "render_plan" in {0,1},
  * "train_rays_per_warp" in {4,2,1} (ia_train_fwd), "query_warps" in {12,16,20}, "query_lanes_per_sample" in {0 = from the
  * load, 1, 2, 4} (lanes sharing one sample's 13 root finds in ia_train_fwd_split's point query),
- * "occupancy_lanes_per_point" in {0, 1, 2, 4} (the same for ia_occupancy_query*; 0 = 2 when n_shards >= 4, else 1) */
+ * "occupancy_lanes_per_point" in {0, 1, 2, 4} (the same for ia_occupancy_query*; measured slower there, 0 = 1) */
 int ia_set_option(const char* name, int value);
 
 /* tiny-cuda-nn HashGrid level table (models/networks/ngp.py:27-37 config). [host] outputs. */

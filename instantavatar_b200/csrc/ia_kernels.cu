@@ -13,7 +13,7 @@ static int g_render_plan = 1;  // longest-first tile scheduling (needs the large
 static int g_query_warps = 12;   // same for the point-query kernel (12 / 16 / 20; 16 and 20 only without xc output)
 static int g_train_rays = 2;   // rays per warp of the training forward (4 / 2 / 1)
 static int g_query_lanes = 0;  // lanes per point of the list-mode point query (split training forward): 0 = auto, 1 / 2 / 4
-static int g_occ_lanes = 0;    // lanes per point of the occupancy passes: 0 = 2 when a launch covers <= 1/4 of the grid, else 1
+static int g_occ_lanes = 0;    // lanes per point of the occupancy passes: 0 = 1 (more were measured slower, see occupancy_query_impl)
 int ia_train_rays_per_warp() { return g_train_rays; }
 
 #include "ia_host.h"
@@ -1132,10 +1132,11 @@ static int occupancy_query_impl(const IaScene* scene, const float* jitter, const
     a.peer_density = peer_density; a.n_peers = n_peers;
     a.batch_order = batch_order; a.n_order = n_order; a.batch_cost = batch_cost;
     a.n_dev = nullptr; a.index = nullptr;
-    // a shard of 1/4 of the grid or less leaves a warp only a handful of batches, and the slowest batch (0.25 ms) is then
-    // longer than the shard's ideal time: two lanes per point halve it (the batch list / cost interface keeps the
-    // 32/passes-cell batches it is defined on)
-    a.lanes_per_sample = g_occ_lanes ? g_occ_lanes : ((n_shards >= 4 && !batch_order && !batch_cost && 2 * passes <= 16) ? 2 : 1);
+    // several lanes per point ("occupancy_lanes_per_point") were measured and do NOT pay here, unlike in the training list
+    // query: 98 % of the grid points are empty space whose solves end after one or two gathers, so splitting a point's 13
+    // solves over lanes shortens nothing and idles the helper lanes in every later stage (1/8 shard: 0.295 -> 0.297 ms
+    // with 2 lanes, 0.50 ms with 4; whole grid 1.60 -> 1.80 / 3.39 ms; profiles/query_schedule_r2.jsonl).  Default 1.
+    a.lanes_per_sample = g_occ_lanes ? g_occ_lanes : 1;
     if (batch_order || batch_cost || 32 / a.lanes_per_sample < passes) a.lanes_per_sample = 1;
     IA_REQUIRE(!batch_order || (workspace && n_order >= 0));
     if (workspace) IA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream));

@@ -281,7 +281,7 @@ def test_occupancy_query_shards_and_explicit_order_reproduce_the_grid(sc, dev):
         acc = torch.maximum(acc, ops.occupancy_query(scene, jit, aabb, order=part.contiguous()))
     assert torch.equal(acc, full)
     assert torch.equal(ops.occupancy_query(scene, jit, aabb, order=by_cost.contiguous()), full)
-    # narrow batches (2 / 4 lanes share a point's 13 root finds; the default for shards of <= 1/4 of the grid)
+    # narrow batches (2 / 4 lanes share a point's 13 root finds; an option, off by default: measured slower for these passes)
     try:
         for k in (2, 4):
             ops.set_option("occupancy_lanes_per_point", k)
