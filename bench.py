@@ -706,7 +706,8 @@ def run_ours(args):
            # scalar keys (the driver's record keeps scalars of `config`): per-kernel times of the frame, then the second half of
            # BASELINE.json's metric (train-step ms, 4096 rays strong-scaled over the ranks) and the strong-scaled single frame
            "ms_occupancy_query_kernel": q_ms, "ms_occupancy_init": occ_ms, "ms_render_kernel": k_ms, "ms_frame": total_ms / args.steps,
-           "train_ms_per_step": train["ms_per_step"], "train_rays_per_step": train["rays_per_step"], "train_scaling": "strong"}
+           "train_ms_per_step": train["ms_per_step"], "train_rays_per_step": train["rays_per_step"], "train_scaling": "strong",
+           "train_forward": "split (march -> sample list -> point query -> compositing)" if ops.get_option("train_split") else "fused (one kernel)"}
     if sharded is not None:
         cfg.update({"frame_sharded_ms": sharded["ms_per_frame"], "frame_sharded_rays_per_s": sharded["rays_per_s"],
                     "frame_sharded_path": sharded["path"], "frame_sharded_nccl_ms": sharded["nccl"]["ms_per_frame"],
