@@ -22,7 +22,7 @@ for line in txt.splitlines():
         kern = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
         hist[kern], total[kern] = collections.Counter(), 0
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P\d+\s+)?([A-Z][\w.]*)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,8}\*/\s+(@!?U?P\d+\s+)?([A-Z][\w.]*)", line)
     if kern and m:
         op = m.group(2)
         total[kern] += 1
