@@ -52,3 +52,16 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports oracle/"
+
+
+def test_every_entry_point_is_documented_for_integrators():
+    """INTEGRATION.md must name every function include/ia_b200.h declares (the binding guide is part of the boundary)"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "ia_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    syms = sorted(set(re.findall(r"\b(ia_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(syms) >= 50
+    missing = [s for s in syms if s not in doc]
+    assert not missing, missing
