@@ -94,6 +94,14 @@ class ForwardDeformer(torch.nn.Module):
         self.voxel_d = None
         self.aabb = None
 
+    def check_train_supported(self):
+        """`version: 2` (deformer_torch.py:68-75, selected by confs/deformer/fast_snarf_debug.yaml) replaces the training-time
+        canonical points by the explicit inverse of the blended transform; only version 1 (implicit differentiation,
+        :50-67) is implemented.  Evaluation is identical for both versions (:46-47), so only training refuses."""
+        if self.version != 1:
+            raise NotImplementedError(f"ForwardDeformer version {self.version}: training-time forward not implemented "
+                                      "(version 1 only); evaluation / rendering is unaffected")
+
     def switch_to_explicit(self, resolution=32, smpl_verts=None, smpl_weights=None, use_smpl=True, lbs_voxel=None):
         """deformer_torch.py:130-202"""
         self.resolution = resolution
@@ -246,6 +254,8 @@ class SNARFDeformer:
 
     def __call__(self, pts, model, eval_mode=True):
         from ..models.networks.ngp import NeRFNGPNet
+        if not eval_mode:
+            self.deformer.check_train_supported()
         pts = pts.reshape(-1, 3).type(self.dtype).contiguous()
         if isinstance(model, NeRFNGPNet):
             model.initialize(self.bbox)

@@ -172,6 +172,9 @@ class DNeRFModel(torch.nn.Module):
         With world_size > 1 the rays of `batch` are this rank's shard and gradients are all-reduced (sum) before
         the step, which divides by world_size."""
         self.train()
+        inner = getattr(self.deformer, "deformer", None)
+        if hasattr(inner, "check_train_supported"):
+            inner.check_train_supported()   # `version: 2` configs fail loudly instead of training with version-1 semantics
         self.renderer.idx = int(batch.get("idx", 0)) if not torch.is_tensor(batch.get("idx", 0)) else 0
         if self.SMPL_param is not None:  # DNeRF.py:113-127
             batch = dict(batch)

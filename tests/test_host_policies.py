@@ -27,3 +27,13 @@ def test_option_mirror_defaults_match_the_library_defaults():
                       ("occupancy_lanes_per_point", "g_occ_lanes")):
         m = re.search(r"static int %s = (\d+);" % var, src)
         assert m and int(m.group(1)) == ops._OPTIONS[name], name
+
+
+def test_version2_deformer_refuses_training_but_not_construction():
+    import pytest
+    from instantavatar_b200.deformers.snarf_deformer import ForwardDeformer
+    ForwardDeformer(opt={"version": 1}).check_train_supported()
+    ForwardDeformer(opt=None).check_train_supported()
+    d2 = ForwardDeformer(opt={"version": 2})     # fast_snarf_debug.yaml: constructing and evaluating stay possible
+    with pytest.raises(NotImplementedError):
+        d2.check_train_supported()
